@@ -1,0 +1,116 @@
+/* milb_capi.h -- thin C-ABI over the sm_100a kernels of the microImageLib hot path.
+ *
+ * This is the layer the reference-facing host code (libapi.h: decon_singleview, decon_dualview,
+ * reg3d ...) calls to reach CUDA.  Plain pointers and sizes only; no C++ or torch types.
+ * Every entry point names the reference interface it replaces (paths relative to the reference
+ * tree).  All functions return MILB_OK (0) or a MILB_ERR_* code; nothing here exits the process.
+ *
+ * Conventions shared with libapi.h:
+ *   - volumes are contiguous float32, x-fastest: idx = x + y*W + z*W*H, sizes given as {W, H, S}
+ *     exactly as gettifinfo returns them (src/apifunc.cpp:123-133);
+ *   - affine matrices are 12 floats, row-major 3x4, mapping target voxel -> source voxel;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream);
+ *   - `on_device` != 0 means the pointer is device memory on the current device.
+ */
+#ifndef MILB_CAPI_H
+#define MILB_CAPI_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MILB_OK 0
+#define MILB_ERR_ARG 1
+#define MILB_ERR_CUDA 2
+#define MILB_ERR_SIZE 3
+#define MILB_ERR_EMPTY 4 /* an input volume has zero variance (reference: exit(1), src/api_subfunc.cu:2864-2867) */
+
+/* library / device ------------------------------------------------------------------------- */
+const char *milb_version(void);
+/* replaces snapTransformSize, src/api_subfunc.cu:57-87 */
+int milb_snap_transform_size(int n);
+/* number of kernels this library launched since load (bench.py's gpu_launches claim) */
+long long milb_launch_count(void);
+
+/* Richardson-Lucy deconvolution ---------------------------------------------------------------
+ * A handle owns the device state one decon call of the reference allocates per call
+ * (src/api_decon.cpp:201-205, 511-516): padded views A (and B), estimate E, one half spectrum and
+ * the OTFs.  nviews = 1 replaces decon_singleview_OTF1 (src/api_subfunc.cu:3361-3430), nviews = 2
+ * replaces decon_dualview_OTF1 (src/api_subfunc.cu:3587-3674). */
+typedef struct milb_decon milb_decon_t;
+
+int milb_decon_create(milb_decon_t **out, int nviews, const unsigned int *imSize /* {W,H,S} */);
+void milb_decon_destroy(milb_decon_t *h);
+/* FFT box {W,H,S} chosen for this image size (src/api_decon.cpp:77-79) */
+int milb_decon_fft_size(const milb_decon_t *h, unsigned int *fftSize);
+
+/* replaces genOTFgpu (+ flipgpu for the matched back projector), src/api_subfunc.cu:3270-3307,
+ * src/api_decon.cpp:213-223.  psf_bp is read only when unmatched != 0. */
+int milb_decon_set_psf(milb_decon_t *h, int view, const float *psf, const float *psf_bp,
+	const unsigned int *psfSize, int unmatched, int on_device, void *stream);
+
+/* replaces the H2D + padstackgpu + max(.,0.01) preparation, src/api_decon.cpp:225-231,
+ * src/api_subfunc.cu:3380 */
+int milb_decon_set_image(milb_decon_t *h, int view, const float *img, int on_device, void *stream);
+
+/* the iteration loop, src/api_subfunc.cu:3404-3416 / 3634-3660.  const_init: flagConstInitial */
+int milb_decon_run(milb_decon_t *h, int iterations, int const_init, void *stream);
+
+/* replaces cropgpu + D2H, src/api_decon.cpp:237-243 */
+int milb_decon_get_result(milb_decon_t *h, float *out, int on_device, void *stream);
+
+/* tuning: planes of the half spectrum processed per L2-resident chunk (0 = whole volume) */
+int milb_decon_set_chunk_planes(milb_decon_t *h, int planes);
+
+/* yardstick: the same loop through cuFFT + unfused element-wise kernels, i.e. the reference's own
+ * launch structure (src/api_subfunc.cu:3404-3416) on this GPU.  Used by bench.py only. */
+int milb_decon_run_cufft_yardstick(milb_decon_t *h, int iterations, int const_init, void *stream);
+
+/* Registration ----------------------------------------------------------------------------------
+ * A handle owns the mean-removed target and source volumes of one reg3d_affine1 call
+ * (src/api_subfunc.cu:2838-2875). */
+typedef struct milb_reg milb_reg_t;
+
+int milb_reg_create(milb_reg_t **out, const unsigned int *sizeT /* {W,H,S} */);
+void milb_reg_destroy(milb_reg_t *h);
+/* upload (or adopt) target and source, same size (reg3d aligns sizes first, src/api_reg.cpp:401-406) */
+int milb_reg_set_images(milb_reg_t *h, const float *target, const float *source, int on_device, void *stream);
+/* mean removal of both volumes and sqrt(sum t^2); if pre_tmx != NULL the source is first warped
+ * by it (src/api_subfunc.cu:2817-2868).  Returns valueStatic in *sd_t. */
+int milb_reg_prepare(milb_reg_t *h, const float *pre_tmx, float *sd_t, void *stream);
+/* K cost evaluations in one launch: costs[k] = -ZNCC for matrices[12*k..] ; +2 when sum s^2 == 0.
+ * Replaces costfunc -> corrfunc -> corrkernel + sumgpu1D, src/api_subfunc.cu:954-988, 2377-2388. */
+int milb_reg_cost(milb_reg_t *h, const float *matrices, int K, float *costs, void *stream);
+/* raw double sums (sum s*s, sum s*t) per matrix, for parity tests */
+int milb_reg_cost_sums(milb_reg_t *h, const float *matrices, int K, double *ss, double *st, void *stream);
+/* final warp of the raw source, replaces affineTransform, src/api_subfunc.cu:942-948, 2974-2978 */
+int milb_reg_warp_source(milb_reg_t *h, const float *tmx, float *out, int on_device, void *stream);
+
+/* stand-alone warp: replaces affinetrans3d1/2, src/api_subfunc.cu:2345-2375 */
+int milb_affine_warp(float *out, const unsigned int *sizeOut, const float *src, const unsigned int *sizeSrc,
+	const float *tmx, int on_device, void *stream);
+
+/* the whole affine registration: schedule + Powell on the host, cost on the device.
+ * Replaces reg3d_affine1, src/api_subfunc.cu:2733-2994.  records as in libapi.h (>= 11 floats). */
+int milb_reg3d_affine(float *reg_out, float *iTmx, const float *target, const float *source,
+	const unsigned int *size, int affMethod, int flagTmx, float FTOL, int itLimit, int on_device,
+	int verbose, float *records, void *stream);
+
+/* host-side helpers exported for parity tests: src/api_subfunc.cu:557-623, 715-824 */
+void milb_p2matrix(float *m, const float *x);
+void milb_matrix2p(const float *m, float *x);
+void milb_matrixmultiply(float *m, const float *m1, const float *m2);
+void milb_dof9tomatrix(float *p_out, const float *p_dof, int dofNum);
+
+/* Powell direction-set minimiser with the reference's modifications (src/api_powell.c:305-361).
+ * p is 1-indexed (p[0] unused), xi is n*n row-major holding xi[i][j] for 1 <= i,j <= n.
+ * func(x, user) receives a 1-indexed trial vector.  *totalIt is read, never written (the cost
+ * function counts its own evaluations, as the reference's costfunc does). */
+typedef float (*milb_costfn)(const float *x, void *user);
+int milb_powell(float *p, float *xi, int n, float ftol, int *iter, float *fret, milb_costfn func,
+	void *user, const int *totalIt, int itLimit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MILB_CAPI_H */

@@ -1,0 +1,459 @@
+// Richardson-Lucy deconvolution on sm_100a: plans, OTF generation, the fused iteration loop.
+// Replaces decon_singleview_OTF1 / decon_dualview_OTF1 / genOTFgpu and the kernels they call
+// (src/api_subfunc.cu:3270-3307, 3361-3430, 3587-3674; include/cukernel.cuh:113-206, 381-392,
+// 667-770).  Written from the algorithm, not from those sources.
+#include <math.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/milb_capi.h"
+#include "common.h"
+#include "fft_kernels.cuh"
+#include "fft_plan.h"
+#include "decon_internal.h"
+#include "launch_count.h"
+
+// ------------------------------------------------------------------------------------------------
+int milb_snap_transform_size(int n)
+{
+	n = (n + 15) / 16 * 16;
+	int low = 1;
+	while (low * 2 <= n) low *= 2;
+	if (low == n) return n;
+	if (low * 2 <= 128) return low * 2;
+	return (n + 63) / 64 * 64;
+}
+
+// ------------------------------------------------------------------------------------------------
+static int make_axis_plan(AxisPlan &ap, int n)
+{
+	AxisPlanTables t;
+	if (!milb_plan_axis(n, t)) return MILB_ERR_SIZE;
+	AxisPlanDev &d = ap.dev;
+	memset(&d, 0, sizeof d);
+	d.n = n;
+	d.nstages = t.nstages;
+	for (int s = 0; s < t.nstages; s++) d.radix[s] = t.radix[s];
+	MILB_CUDA_TRY(cudaMalloc(&ap.d_tw, sizeof(float2) * n));
+	MILB_CUDA_TRY(cudaMalloc(&ap.d_pos, sizeof(int) * n));
+	MILB_CUDA_TRY(cudaMemcpy(ap.d_tw, t.tw.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+	MILB_CUDA_TRY(cudaMemcpy(ap.d_pos, t.pos.data(), sizeof(int) * n, cudaMemcpyHostToDevice));
+	d.tw = ap.d_tw;
+	d.pos = ap.d_pos;
+	return MILB_OK;
+}
+
+static void free_axis_plan(AxisPlan &ap)
+{
+	if (ap.d_tw) cudaFree(ap.d_tw);
+	if (ap.d_pos) cudaFree(ap.d_pos);
+	ap.d_tw = nullptr;
+	ap.d_pos = nullptr;
+}
+
+// largest power-of-two lane count <= maxL whose tile (+twiddles) fits the shared-memory budget
+static int pick_lanes(int n, int maxL, int pad, size_t budget)
+{
+	int L = maxL;
+	while (L > 1 && ((size_t)n * (L + pad) + n) * sizeof(float2) > budget) L /= 2;
+	return L;
+}
+
+// ------------------------------------------------------------------------------------------------
+// small element-wise / layout kernels
+// ------------------------------------------------------------------------------------------------
+
+// Edge-replicate pad of the image into the FFT box + clamp at 0.01
+// (padstackgpukernel, include/cukernel.cuh:699-737; maxvalue3Dgpu, src/api_subfunc.cu:3380).
+// Box dims (X,Y,Z), image dims (ix,iy,iz), z fastest.
+__global__ void k_pad_clamp(float *__restrict__ out, const float *__restrict__ in, int X, int Y, int Z, int ix, int iy, int iz)
+{
+	const long long n = (long long)X * Y * Z;
+	const int ox = (X - ix) / 2, oy = (Y - iy) / 2, oz = (Z - iz) / 2;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		int z = (int)(i % Z);
+		long long t = i / Z;
+		int y = (int)(t % Y), x = (int)(t / Y);
+		int sx = min(max(x - ox, 0), ix - 1), sy = min(max(y - oy, 0), iy - 1), sz = min(max(z - oz, 0), iz - 1);
+		float v = in[((long long)sx * iy + sy) * iz + sz];
+		out[i] = (v > SMALLVALUE_F) ? v : SMALLVALUE_F;
+	}
+}
+
+// Centred crop (cropgpukernel, include/cukernel.cuh:739-753)
+__global__ void k_crop(float *__restrict__ out, const float *__restrict__ in, int X, int Y, int Z, int ix, int iy, int iz)
+{
+	const long long n = (long long)ix * iy * iz;
+	const int ox = (X - ix) / 2, oy = (Y - iy) / 2, oz = (Z - iz) / 2;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		int z = (int)(i % iz);
+		long long t = i / iz;
+		int y = (int)(t % iy), x = (int)(t / iy);
+		out[i] = in[((long long)(x + ox) * Y + (y + oy)) * Z + (z + oz)];
+	}
+}
+
+// PSF -> normalised, (optionally flipped,) boxed, centre-to-origin shifted real volume.
+// Restates flipgpukernel / alignsize3Dgpukernel / padPSFgpukernel (include/cukernel.cuh:667-697,
+// 754-770) and the normalisation of genOTFgpu (src/api_subfunc.cu:3283-3284) as one gather over
+// the output box.  inv_sum = (float)(1/sum).
+__device__ __forceinline__ int psf_src_index(int d, int F, int P, bool boxed)
+{
+	// returns source index along one axis or -1 for "zero"
+	const int Pb = boxed ? F : P;
+	int b = d + Pb / 2;
+	if (b >= F) b -= F;
+	if (b >= Pb) return -1;
+	if (!boxed) return b;
+	const int diff = F - P;
+	const int off = diff < 0 ? -((-diff) / 2) : diff / 2; // C truncating division
+	const int i = b - off;
+	return (i < 0 || i >= P) ? -1 : i;
+}
+
+__global__ void k_psf_box(float *__restrict__ out, const float *__restrict__ psf, const double *__restrict__ d_sum,
+	int X, int Y, int Z, int px, int py, int pz, int flip)
+{
+	const long long n = (long long)X * Y * Z;
+	const bool boxed = (X < px) || (Y < py) || (Z < pz);
+	const float inv_sum = (float)(1.0 / d_sum[0]);
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		int z = (int)(i % Z);
+		long long t = i / Z;
+		int y = (int)(t % Y), x = (int)(t / Y);
+		int sx = psf_src_index(x, X, px, boxed), sy = psf_src_index(y, Y, py, boxed), sz = psf_src_index(z, Z, pz, boxed);
+		float v = 0.f;
+		if (sx >= 0 && sy >= 0 && sz >= 0) {
+			if (flip) { sx = px - 1 - sx; sy = py - 1 - sy; sz = pz - 1 - sz; }
+			v = psf[((long long)sx * py + sy) * pz + sz] * inv_sum;
+		}
+		out[i] = v;
+	}
+}
+
+// E initialisation (src/api_subfunc.cu:3381-3388, 3608-3618)
+//   mode 0: E = A                       mode 1: E = (A + B) * 0.5
+//   mode 2: E = (float)sumA             mode 3: E = ((float)sumA + (float)sumB) / 2
+__global__ void k_init_estimate(float *__restrict__ E, const float *__restrict__ A, const float *__restrict__ B,
+	const double *__restrict__ sums, long long n, int mode)
+{
+	float c = 0.f;
+	if (mode == 2) c = (float)sums[0];
+	if (mode == 3) c = ((float)sums[0] + (float)sums[1]) / 2;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		float v;
+		if (mode == 0) v = A[i];
+		else if (mode == 1) v = (A[i] + B[i]) * 0.5f;
+		else v = c;
+		E[i] = v;
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// deterministic reductions
+// ------------------------------------------------------------------------------------------------
+template <bool SQ>
+__global__ void __launch_bounds__(256) k_reduce_partial(const float *__restrict__ in, long long n, double *__restrict__ partial)
+{
+	__shared__ double sh[256];
+	double acc = 0;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		float v = in[i];
+		if (SQ) v = v * v; // float square first, like multi3Dgpu then sum3Dgpu (src/api_subfunc.cu:2861-2862)
+		acc += (double)v;
+	}
+	sh[threadIdx.x] = acc;
+	__syncthreads();
+	for (int s = 128; s > 0; s >>= 1) {
+		if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
+}
+
+__global__ void k_reduce_final(const double *__restrict__ partial, int np, double *__restrict__ out)
+{
+	if (threadIdx.x == 0 && blockIdx.x == 0) {
+		double s = 0;
+		for (int i = 0; i < np; i++) s += partial[i];
+		out[0] = s;
+	}
+}
+
+int milb_sum_f64_async(const float *d_in, long long n, double *d_scratch, double *d_out, cudaStream_t st)
+{
+	k_reduce_partial<false><<<MILB_REDUCE_BLOCKS, 256, 0, st>>>(d_in, n, d_scratch);
+	k_reduce_final<<<1, 32, 0, st>>>(d_scratch, MILB_REDUCE_BLOCKS, d_out);
+	milb_count_launches(2);
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+int milb_sumsq_f64_async(const float *d_in, long long n, double *d_scratch, double *d_out, cudaStream_t st)
+{
+	k_reduce_partial<true><<<MILB_REDUCE_BLOCKS, 256, 0, st>>>(d_in, n, d_scratch);
+	k_reduce_final<<<1, 32, 0, st>>>(d_scratch, MILB_REDUCE_BLOCKS, d_out);
+	milb_count_launches(2);
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the handle
+// ------------------------------------------------------------------------------------------------
+static const size_t kSmemBudget = 96 * 1024;
+
+template <typename K>
+static int set_smem(K kernel, size_t bytes)
+{
+	MILB_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+	return MILB_OK;
+}
+
+int milb_decon_create(milb_decon_t **out, int nviews, const unsigned int *imSize)
+{
+	if (!out || !imSize || (nviews != 1 && nviews != 2)) return MILB_ERR_ARG;
+	if (imSize[0] == 0 || imSize[1] == 0 || imSize[2] == 0) return MILB_ERR_ARG;
+	milb_decon *h = new milb_decon();
+	h->nviews = nviews;
+	h->iz = (int)imSize[0]; h->iy = (int)imSize[1]; h->ix = (int)imSize[2]; // src/api_decon.cpp:68
+	h->X = milb_snap_transform_size(h->ix);
+	h->Y = milb_snap_transform_size(h->iy);
+	h->Z = milb_snap_transform_size(h->iz);
+	h->nreal = (long long)h->X * h->Y * h->Z;
+	h->nspec = (long long)(h->X / 2 + 1) * h->Y * h->Z;
+	int rc;
+	if ((rc = make_axis_plan(h->px, h->X)) || (rc = make_axis_plan(h->py, h->Y)) || (rc = make_axis_plan(h->pz, h->Z))) {
+		milb_decon_destroy(h);
+		return rc;
+	}
+	h->Lx = pick_lanes(h->X, 32, 0, kSmemBudget);
+	h->Ly = pick_lanes(h->Y, (h->Z % 32 == 0) ? 32 : 16, 0, kSmemBudget);
+	h->Lz = pick_lanes(h->Z, 16, 1, kSmemBudget);
+	h->smx = ((size_t)h->X * h->Lx + h->X) * sizeof(float2);
+	h->smy = ((size_t)h->Y * h->Ly + h->Y) * sizeof(float2);
+	h->smz = ((size_t)h->Z * (h->Lz + 1) + h->Z) * sizeof(float2);
+	if ((rc = set_smem(k_xpass<X_FWD_REAL>, h->smx)) || (rc = set_smem(k_xpass<X_RATIO>, h->smx)) ||
+		(rc = set_smem(k_xpass<X_UPDATE>, h->smx)) || (rc = set_smem(k_xpass<X_UPDATE_LAST>, h->smx)) ||
+		(rc = set_smem(k_xpass<X_INV_REAL>, h->smx)) || (rc = set_smem(k_ypass<false>, h->smy)) ||
+		(rc = set_smem(k_ypass<true>, h->smy)) || (rc = set_smem(k_zpass<true>, h->smz)) ||
+		(rc = set_smem(k_zpass<false>, h->smz))) {
+		milb_decon_destroy(h);
+		return rc;
+	}
+	cudaError_t e = cudaSuccess;
+	for (int v = 0; v < nviews && e == cudaSuccess; v++) {
+		e = cudaMalloc(&h->A[v], sizeof(float) * h->nreal);
+		if (e == cudaSuccess) e = cudaMalloc(&h->otf[v], sizeof(float2) * h->nspec);
+		if (e == cudaSuccess) e = cudaMalloc(&h->otf_bp[v], sizeof(float2) * h->nspec);
+	}
+	if (e == cudaSuccess) e = cudaMalloc(&h->E, sizeof(float) * h->nreal);
+	if (e == cudaSuccess) e = cudaMalloc(&h->stage, sizeof(float) * h->nreal);
+	if (e == cudaSuccess) e = cudaMalloc(&h->S, sizeof(float2) * h->nspec);
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_sums, sizeof(double) * (2 + MILB_REDUCE_BLOCKS));
+	if (e != cudaSuccess) {
+		fprintf(stderr, "milb_decon_create: %s\n", cudaGetErrorString(e));
+		milb_decon_destroy(h);
+		return MILB_ERR_CUDA;
+	}
+	*out = h;
+	return MILB_OK;
+}
+
+void milb_decon_destroy(milb_decon_t *h)
+{
+	if (!h) return;
+	for (int v = 0; v < 2; v++) {
+		if (h->A[v]) cudaFree(h->A[v]);
+		if (h->otf[v]) cudaFree(h->otf[v]);
+		if (h->otf_bp[v]) cudaFree(h->otf_bp[v]);
+	}
+	if (h->E) cudaFree(h->E);
+	if (h->stage) cudaFree(h->stage);
+	if (h->S) cudaFree(h->S);
+	if (h->d_sums) cudaFree(h->d_sums);
+	free_axis_plan(h->px);
+	free_axis_plan(h->py);
+	free_axis_plan(h->pz);
+	delete h;
+}
+
+int milb_decon_fft_size(const milb_decon_t *h, unsigned int *fftSize)
+{
+	if (!h || !fftSize) return MILB_ERR_ARG;
+	fftSize[0] = h->Z; fftSize[1] = h->Y; fftSize[2] = h->X;
+	return MILB_OK;
+}
+
+int milb_decon_set_chunk_planes(milb_decon_t *h, int planes)
+{
+	if (!h || planes < 0) return MILB_ERR_ARG;
+	h->chunk_planes = planes;
+	return MILB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+static const int kThreads = 512;
+
+template <int MODE>
+static void launch_xpass(milb_decon *h, float *vol_io, const float *aux, cudaStream_t st)
+{
+	const long long M = (long long)h->Y * h->Z / 2;
+	k_xpass<MODE><<<(unsigned)(M / h->Lx), kThreads, h->smx, st>>>(h->px.dev, M, h->Lx, (float2 *)vol_io, (const float2 *)aux,
+		(float4 *)h->S, 1.0f);
+	milb_count_launches(1);
+}
+
+// Y-forward, Z-forward * otf Z-inverse, Y-inverse over all kx planes, in L2-sized chunks of planes.
+// otf == nullptr: forward only (OTF generation), output scaled by `scale`.
+static void plane_stage(milb_decon *h, const float2 *otf, float scale, cudaStream_t st)
+{
+	const int planes = h->X / 2 + 1;
+	int chunk = h->chunk_planes > 0 ? h->chunk_planes : planes;
+	for (int p0 = 0; p0 < planes; p0 += chunk) {
+		const int np = (p0 + chunk <= planes) ? chunk : planes - p0;
+		dim3 gy(h->Z / h->Ly, np);
+		k_ypass<false><<<gy, kThreads, h->smy, st>>>(h->py.dev, h->Z, h->Ly, h->S, p0);
+		const long long row0 = (long long)p0 * h->Y, rows = (long long)np * h->Y;
+		if (otf) {
+			k_zpass<true><<<(unsigned)(rows / h->Lz), kThreads, h->smz, st>>>(h->pz.dev, h->Lz, h->S, otf, row0, 1.0f);
+			k_ypass<true><<<gy, kThreads, h->smy, st>>>(h->py.dev, h->Z, h->Ly, h->S, p0);
+			milb_count_launches(3);
+		} else {
+			k_zpass<false><<<(unsigned)(rows / h->Lz), kThreads, h->smz, st>>>(h->pz.dev, h->Lz, h->S, nullptr, row0, scale);
+			milb_count_launches(2);
+		}
+	}
+}
+
+int milb_psf_box_async(float *d_out, const float *d_psf, const double *d_sum, int X, int Y, int Z, int px, int py, int pz, int flip,
+	cudaStream_t st)
+{
+	const long long n = (long long)X * Y * Z;
+	long long b = cdiv_ll(n, 256);
+	k_psf_box<<<(int)(b > 148 * 16 ? 148 * 16 : b), 256, 0, st>>>(d_out, d_psf, d_sum, X, Y, Z, px, py, pz, flip);
+	milb_count_launches(1);
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+static int grid_for(long long n) { long long b = cdiv_ll(n, 256); return (int)(b > 148 * 16 ? 148 * 16 : b); }
+
+// OTF of one PSF into dst (genOTFgpu).  The 1/N of the two un-normalised transforms of each
+// convolution is folded in here, so the loop needs no scaling pass: dst = FFT(psf_boxed) / N.
+static int gen_otf(milb_decon *h, float2 *dst, const float *d_psf, int px, int py, int pz, int flip, cudaStream_t st)
+{
+	const long long np = (long long)px * py * pz;
+	MILB_TRY(milb_sum_f64_async(d_psf, np, h->d_sums + 2, h->d_sums, st));
+	k_psf_box<<<grid_for(h->nreal), 256, 0, st>>>(h->E, d_psf, h->d_sums, h->X, h->Y, h->Z, px, py, pz, flip);
+	milb_count_launches(1);
+	launch_xpass<X_FWD_REAL>(h, h->E, nullptr, st);
+	plane_stage(h, nullptr, (float)(1.0 / (double)h->nreal), st);
+	MILB_CUDA_TRY(cudaMemcpyAsync(dst, h->S, sizeof(float2) * h->nspec, cudaMemcpyDeviceToDevice, st));
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+int milb_decon_set_psf(milb_decon_t *h, int view, const float *psf, const float *psf_bp, const unsigned int *psfSize,
+	int unmatched, int on_device, void *stream)
+{
+	if (!h || view < 0 || view >= h->nviews || !psf || !psfSize || (unmatched && !psf_bp)) return MILB_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	const int pz = (int)psfSize[0], py = (int)psfSize[1], px = (int)psfSize[2]; // src/api_decon.cpp:72
+	const long long np = (long long)px * py * pz;
+	if (np <= 0) return MILB_ERR_ARG;
+	float *d_psf = nullptr;
+	MILB_CUDA_TRY(cudaMalloc(&d_psf, sizeof(float) * np));
+	int rc = MILB_OK;
+	for (int which = 0; which < 2 && rc == MILB_OK; which++) {
+		const float *src = (which == 1 && unmatched) ? psf_bp : psf;
+		const int flip = (which == 1 && !unmatched) ? 1 : 0;
+		cudaError_t e = cudaMemcpyAsync(d_psf, src, sizeof(float) * np, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st);
+		if (e != cudaSuccess) { rc = MILB_ERR_CUDA; break; }
+		rc = gen_otf(h, which ? h->otf_bp[view] : h->otf[view], d_psf, px, py, pz, flip, st);
+	}
+	cudaStreamSynchronize(st);
+	cudaFree(d_psf);
+	if (rc == MILB_OK) {
+		h->have_psf[view] = true;
+		// keep the raw PSFs (small) for the cuFFT yardstick, which builds its own OTF layout
+		h->psf_dims[0] = px; h->psf_dims[1] = py; h->psf_dims[2] = pz;
+		h->unmatched = unmatched != 0;
+		for (int which = 0; which < 2; which++) {
+			const float *src = (which == 1 && unmatched) ? psf_bp : psf;
+			h->raw_psf[view][which].resize((size_t)np);
+			if (on_device) cudaMemcpy(h->raw_psf[view][which].data(), src, sizeof(float) * np, cudaMemcpyDeviceToHost);
+			else memcpy(h->raw_psf[view][which].data(), src, sizeof(float) * np);
+		}
+	}
+	return rc;
+}
+
+int milb_decon_set_image(milb_decon_t *h, int view, const float *img, int on_device, void *stream)
+{
+	if (!h || view < 0 || view >= h->nviews || !img) return MILB_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	const long long nimg = (long long)h->ix * h->iy * h->iz;
+	const float *d_img = img;
+	if (!on_device) {
+		MILB_CUDA_TRY(cudaMemcpyAsync(h->stage, img, sizeof(float) * nimg, cudaMemcpyHostToDevice, st));
+		d_img = h->stage;
+	}
+	k_pad_clamp<<<grid_for(h->nreal), 256, 0, st>>>(h->A[view], d_img, h->X, h->Y, h->Z, h->ix, h->iy, h->iz);
+	milb_count_launches(1);
+	MILB_CUDA_TRY(cudaGetLastError());
+	h->have_img[view] = true;
+	return MILB_OK;
+}
+
+int milb_decon_run(milb_decon_t *h, int iterations, int const_init, void *stream)
+{
+	if (!h || iterations < 0) return MILB_ERR_ARG;
+	for (int v = 0; v < h->nviews; v++)
+		if (!h->have_psf[v] || !h->have_img[v]) return MILB_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	const int nv = h->nviews;
+	// initial estimate
+	int mode = (nv == 1) ? 0 : 1;
+	if (const_init) {
+		mode = (nv == 1) ? 2 : 3;
+		for (int v = 0; v < nv; v++) MILB_TRY(milb_sum_f64_async(h->A[v], h->nreal, h->d_sums + 2, h->d_sums + v, st));
+	}
+	k_init_estimate<<<grid_for(h->nreal), 256, 0, st>>>(h->E, h->A[0], h->A[1], h->d_sums, h->nreal, mode);
+	milb_count_launches(1);
+	if (iterations == 0) { MILB_CUDA_TRY(cudaGetLastError()); return MILB_OK; }
+	launch_xpass<X_FWD_REAL>(h, h->E, nullptr, st);
+	for (int it = 0; it < iterations; it++) {
+		for (int v = 0; v < nv; v++) {
+			plane_stage(h, h->otf[v], 1.0f, st);                 // S = F(E) * OTF, back to kx-planes
+			launch_xpass<X_RATIO>(h, nullptr, h->A[v], st);      // T = A / C2R(S); S = R2C(T)
+			plane_stage(h, h->otf_bp[v], 1.0f, st);              // S = F(T) * OTF_bp
+			const bool last = (it == iterations - 1) && (v == nv - 1);
+			if (last) launch_xpass<X_UPDATE_LAST>(h, h->E, nullptr, st); // E = max(E * C2R(S), .01)
+			else launch_xpass<X_UPDATE>(h, h->E, nullptr, st);           //  ... and S = R2C(E)
+		}
+	}
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+int milb_decon_get_result(milb_decon_t *h, float *out, int on_device, void *stream)
+{
+	if (!h || !out) return MILB_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	const long long nimg = (long long)h->ix * h->iy * h->iz;
+	const bool padded = (h->ix < h->X) || (h->iy < h->Y) || (h->iz < h->Z);
+	const float *src = h->E;
+	if (padded) {
+		float *dst = on_device ? out : h->stage;
+		k_crop<<<grid_for(nimg), 256, 0, st>>>(dst, h->E, h->X, h->Y, h->Z, h->ix, h->iy, h->iz);
+		milb_count_launches(1);
+		src = dst;
+	}
+	if (src != out)
+		MILB_CUDA_TRY(cudaMemcpyAsync(out, src, sizeof(float) * nimg, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+	MILB_CUDA_TRY(cudaStreamSynchronize(st));
+	return MILB_OK;
+}

@@ -1,0 +1,217 @@
+// Mixed-radix in-place FFT stages on a shared-memory tile of independent pencils.
+//
+// One "tile" holds L independent length-n pencils; element i of pencil `lane` lives at
+// tile[i * pitch + lane], so the 32 lanes of a warp touch consecutive banks and the twiddle of a
+// butterfly is the same for every lane of a row (warp-uniform).
+//
+// Forward  = decimation in frequency, stages 0..S-1, natural order in, digit-scrambled order out.
+// Inverse  = decimation in time, stages S-1..0, scrambled order in, natural order out.
+// Nothing is ever un-scrambled: the spectrum, the OTFs and every frequency-domain product are all
+// kept in "position order", which the inverse consumes directly.  Only the real-pencil
+// split/merge along the first axis needs pos(k) (see AxisPlan::pos).
+//
+// This replaces the cuFFT R2C/C2R calls of the reference (src/api_subfunc.cu:3395-3413); it is
+// written from the DFT definition, not from the reference.
+//
+// Every function is __host__ __device__ so the index arithmetic is unit-tested on the CPU
+// (tests/test_fft_emulation.py builds this header with g++) before it ever runs on a GPU.
+#pragma once
+
+#if defined(__CUDACC__)
+#define MILB_HD __host__ __device__ __forceinline__
+#include <cuda_runtime.h>
+#else
+#define MILB_HD inline
+struct float2 { float x, y; };
+struct float4 { float x, y, z, w; };
+static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+#endif
+
+#define MILB_MAX_STAGES 8
+#define MILB_MAX_RADIX 64
+
+// Device-visible description of one FFT axis.
+struct AxisPlanDev {
+	int n;                          // transform length
+	int nstages;
+	int radix[MILB_MAX_STAGES];     // product == n
+	const float2 *tw;               // tw[t] = exp(-2*pi*i*t/n), t in [0,n)
+	const int *pos;                 // pos[k] = position of frequency k after the forward stages
+};
+
+MILB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
+MILB_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); } // a*conj(b)
+MILB_HD float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+MILB_HD float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+// multiply by -i (forward) or +i (inverse)
+template <bool INV> MILB_HD float2 mul_mi(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+
+// ---- radix-2/4/8 butterflies, in registers, natural order in and out -------------------------
+template <bool INV> MILB_HD void bfly2(float2 &a, float2 &b)
+{
+	float2 t = a;
+	a = cadd(t, b);
+	b = csub(t, b);
+}
+
+template <bool INV> MILB_HD void bfly4(float2 &a0, float2 &a1, float2 &a2, float2 &a3)
+{
+	float2 s02 = cadd(a0, a2), d02 = csub(a0, a2);
+	float2 s13 = cadd(a1, a3), d13 = mul_mi<INV>(csub(a1, a3));
+	a0 = cadd(s02, s13);
+	a2 = csub(s02, s13);
+	a1 = cadd(d02, d13);
+	a3 = csub(d02, d13);
+}
+
+template <bool INV> MILB_HD void bfly8(float2 *v)
+{
+	const float h = 0.70710678118654752440f;
+	// three radix-2 layers (DIF), then bit-reversal fix-up into natural order
+	float2 a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+	float2 a1 = cadd(v[1], v[5]), a5 = csub(v[1], v[5]);
+	float2 a2 = cadd(v[2], v[6]), a6 = csub(v[2], v[6]);
+	float2 a3 = cadd(v[3], v[7]), a7 = csub(v[3], v[7]);
+	// twiddles w8^1, w8^2, w8^3 on the odd half
+	a5 = INV ? make_float2((a5.x - a5.y) * h, (a5.x + a5.y) * h) : make_float2((a5.x + a5.y) * h, (a5.y - a5.x) * h);
+	a6 = mul_mi<INV>(a6);
+	a7 = INV ? make_float2((-a7.x - a7.y) * h, (a7.x - a7.y) * h) : make_float2((a7.y - a7.x) * h, (-a7.x - a7.y) * h);
+	bfly4<INV>(a0, a1, a2, a3); // outputs k = 0,2,4,6 in a0,a1,a2,a3
+	bfly4<INV>(a4, a5, a6, a7); // outputs k = 1,3,5,7
+	v[0] = a0; v[2] = a1; v[4] = a2; v[6] = a3;
+	v[1] = a4; v[3] = a5; v[5] = a6; v[7] = a7;
+}
+
+// naive length-r DFT using the axis twiddle table (r divides n): w_r^t = tw[t * (n / r)]
+template <bool INV> MILB_HD void bfly_generic(float2 *v, int r, const float2 *tw, int n)
+{
+	float2 o[MILB_MAX_RADIX];
+	const int step = n / r;
+	for (int k = 0; k < r; k++) {
+		float2 acc = v[0];
+		int t = 0;
+		for (int j = 1; j < r; j++) {
+			t += k;
+			if (t >= r) t -= r;
+			float2 w = tw[t * step];
+			acc = cadd(acc, INV ? cmulc(v[j], w) : cmul(v[j], w));
+		}
+		o[k] = acc;
+	}
+	for (int k = 0; k < r; k++) v[k] = o[k];
+}
+
+template <bool INV, int R> MILB_HD void bfly_fixed(float2 *v, const float2 *tw, int n)
+{
+	float2 o[R];
+	const int step = n / R;
+#pragma unroll
+	for (int k = 0; k < R; k++) {
+		float2 acc = v[0];
+#pragma unroll
+		for (int j = 1; j < R; j++) {
+			float2 w = tw[((j * k) % R) * step];
+			acc = cadd(acc, INV ? cmulc(v[j], w) : cmul(v[j], w));
+		}
+		o[k] = acc;
+	}
+#pragma unroll
+	for (int k = 0; k < R; k++) v[k] = o[k];
+}
+
+template <bool INV> MILB_HD void bfly_any(float2 *v, int r, const float2 *tw, int n)
+{
+	switch (r) {
+	case 2: bfly2<INV>(v[0], v[1]); break;
+	case 4: bfly4<INV>(v[0], v[1], v[2], v[3]); break;
+	case 8: bfly8<INV>(v); break;
+	case 3: bfly_fixed<INV, 3>(v, tw, n); break;
+	case 5: bfly_fixed<INV, 5>(v, tw, n); break;
+	case 7: bfly_fixed<INV, 7>(v, tw, n); break;
+	default: bfly_generic<INV>(v, r, tw, n); break;
+	}
+}
+
+// One butterfly `b` (0 <= b < n/r) of stage `s` for pencil `lane`.
+//   forward: load, DFT_r, multiply output j by w_ns^(q*j), store in place
+//   inverse: load, multiply input j by conj(w_ns^(q*j)), inverse DFT_r, store in place
+template <bool INV, int R>
+MILB_HD void stage_butterfly_r(float2 *tile, int pitch, int lane, int b, int ns, const AxisPlanDev &pl)
+{
+	const int r = R;
+	const int m = ns / r;
+	const int blk = b / m, q = b - blk * m;
+	const int base = blk * ns + q;
+	const int tstep = q * (pl.n / ns);
+	float2 v[R];
+#pragma unroll
+	for (int j = 0; j < R; j++) v[j] = tile[(base + j * m) * pitch + lane];
+	if (INV) {
+#pragma unroll
+		for (int j = 1; j < R; j++) v[j] = cmulc(v[j], pl.tw[tstep * j]);
+	}
+	if (R == 2) bfly2<INV>(v[0], v[1]);
+	else if (R == 4) bfly4<INV>(v[0], v[1], v[2], v[3]);
+	else if (R == 8) bfly8<INV>(v);
+	else bfly_fixed<INV, R>(v, pl.tw, pl.n);
+	if (!INV) {
+#pragma unroll
+		for (int j = 1; j < R; j++) v[j] = cmul(v[j], pl.tw[tstep * j]);
+	}
+#pragma unroll
+	for (int j = 0; j < R; j++) tile[(base + j * m) * pitch + lane] = v[j];
+}
+
+template <bool INV>
+MILB_HD void stage_butterfly_dyn(float2 *tile, int pitch, int lane, int b, int ns, int r, const AxisPlanDev &pl)
+{
+	const int m = ns / r;
+	const int blk = b / m, q = b - blk * m;
+	const int base = blk * ns + q;
+	const int tstep = q * (pl.n / ns);
+	float2 v[MILB_MAX_RADIX];
+	for (int j = 0; j < r; j++) v[j] = tile[(base + j * m) * pitch + lane];
+	if (INV)
+		for (int j = 1; j < r; j++) v[j] = cmulc(v[j], pl.tw[tstep * j]);
+	bfly_generic<INV>(v, r, pl.tw, pl.n);
+	if (!INV)
+		for (int j = 1; j < r; j++) v[j] = cmul(v[j], pl.tw[tstep * j]);
+	for (int j = 0; j < r; j++) tile[(base + j * m) * pitch + lane] = v[j];
+}
+
+template <bool INV>
+MILB_HD void stage_butterfly(float2 *tile, int pitch, int lane, int b, int ns, int r, const AxisPlanDev &pl)
+{
+	switch (r) {
+	case 2: stage_butterfly_r<INV, 2>(tile, pitch, lane, b, ns, pl); break;
+	case 3: stage_butterfly_r<INV, 3>(tile, pitch, lane, b, ns, pl); break;
+	case 4: stage_butterfly_r<INV, 4>(tile, pitch, lane, b, ns, pl); break;
+	case 5: stage_butterfly_r<INV, 5>(tile, pitch, lane, b, ns, pl); break;
+	case 7: stage_butterfly_r<INV, 7>(tile, pitch, lane, b, ns, pl); break;
+	case 8: stage_butterfly_r<INV, 8>(tile, pitch, lane, b, ns, pl); break;
+	default: stage_butterfly_dyn<INV>(tile, pitch, lane, b, ns, r, pl); break;
+	}
+}
+
+// sub-transform length entering stage s
+MILB_HD int stage_ns(const AxisPlanDev &pl, int s)
+{
+	int ns = pl.n;
+	for (int i = 0; i < s; i++) ns /= pl.radix[i];
+	return ns;
+}
+
+// ---- two real pencils in one complex pencil ----------------------------------------------------
+// c[x] = a[x] + i*b[x]  (a, b real)  =>  C[k] = A[k] + i*B[k],  C[n-k] = conj(A[k]) + i*conj(B[k]).
+// split: (C[k], C[n-k]) -> (A[k], B[k]);  merge: the reverse.  k = 0 and k = n/2 are self-paired
+// and A, B are real there.
+MILB_HD float4 split_pair(float2 ck, float2 cn)
+{
+	return make_float4(0.5f * (ck.x + cn.x), 0.5f * (ck.y - cn.y), 0.5f * (ck.y + cn.y), 0.5f * (cn.x - ck.x));
+}
+MILB_HD void merge_pair(float4 ab, float2 &ck, float2 &cn)
+{
+	ck = make_float2(ab.x - ab.w, ab.y + ab.z);
+	cn = make_float2(ab.x + ab.w, ab.z - ab.y);
+}

@@ -1,0 +1,538 @@
+// libapi: the reference's public C API (include/libapi.h) on top of the sm_100a backend.
+// Host orchestration only -- argument conventions, memory-mode bookkeeping, records[] and error
+// behaviour follow src/api_decon.cpp:53-704, src/api_reg.cpp:57-652 and src/apifunc.cpp:396-644;
+// all arithmetic happens in the CUDA kernels behind include/milb_capi.h.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <time.h>
+
+#include <atomic>
+#include <chrono>
+#include <mutex>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/libapi.h"
+#include "../../include/milb_capi.h"
+#include "common.h"
+#include "geom.h"
+
+std::atomic<long long> g_milb_launches{0};
+
+extern "C" long long milb_launch_count(void) { return g_milb_launches.load(); }
+extern "C" const char *milb_version(void) { return "microimagelib_b200 0.1 (sm_100a)"; }
+
+namespace {
+
+// reference convention: CUDA / allocation failures are fatal (src/api_subfunc.cu:27-37)
+void fatal_if(int rc, const char *what)
+{
+	if (rc == MILB_OK) return;
+	fprintf(stderr, "Fatal error: %s (milb status %d)\n*** FAILED - ABORTING\n", what, rc);
+	exit(1);
+}
+
+void cuda_fatal(cudaError_t e, const char *what)
+{
+	if (e == cudaSuccess) return;
+	fprintf(stderr, "Fatal error: %s (%s)\n*** FAILED - ABORTING\n", what, cudaGetErrorString(e));
+	exit(1);
+}
+
+float free_mb()
+{
+	size_t fr = 0, tot = 0;
+	cudaMemGetInfo(&fr, &tot);
+	return (float)fr / 1048576.0f;
+}
+
+double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+unsigned long long fnv1a(const void *p, size_t n, unsigned long long h = 1469598103934665603ull)
+{
+	const unsigned char *b = (const unsigned char *)p;
+	for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
+	return h;
+}
+
+// One cached deconvolution context per (device, nviews): the batch app calls decon_dualview once
+// per time point with the same sizes and PSFs (src/spim_fusion_batch.cpp:881); the reference
+// re-allocates and recomputes all OTFs every call, here they are kept while the key matches.
+struct DeconCache {
+	milb_decon_t *h = nullptr;
+	int device = -1, nviews = 0;
+	unsigned int im[3] = {0, 0, 0}, psf[3] = {0, 0, 0};
+	unsigned long long psf_hash = 0;
+};
+DeconCache g_cache[2];
+std::mutex g_cache_mu;
+
+bool cache_enabled()
+{
+	const char *e = getenv("MILB_DECON_CACHE");
+	return !(e && e[0] == '0');
+}
+
+int decon_common(int nviews, float *h_decon, float *const h_img[2], unsigned int *imSize, float *const h_psf[2],
+	unsigned int *psfSize, bool flagConstInitial, int itNumForDecon, int deviceNum, int gpuMemMode, float *deconRecords,
+	bool flagUnmatch, float *const h_psf_bp[2], int bad_mode_rc)
+{
+	const double t_start = now_s();
+	printf("Image information:\n");
+	printf("...Image size %u x %u x %u\n  ", imSize[0], imSize[1], imSize[2]);
+	printf("...PSF size %u x %u x %u\n  ", psfSize[0], psfSize[1], psfSize[2]);
+	printf("...FFT size %d x %d x %d\n  ", milb_snap_transform_size((int)imSize[0]), milb_snap_transform_size((int)imSize[1]),
+		milb_snap_transform_size((int)imSize[2]));
+	printf("...Output Image size %u x %u x %u \n   ", imSize[0], imSize[1], imSize[2]);
+	if (gpuMemMode < -1 || gpuMemMode > 2) {
+		printf("\n****Wrong gpuMemMode setup, no deconvolution performed !!! ****\n");
+		return bad_mode_rc;
+	}
+	cuda_fatal(cudaSetDevice(deviceNum), "cudaSetDevice");
+	deconRecords[1] = free_mb();
+	printf("...GPU free memory(at beginning) is %.0f MBites\n", deconRecords[1]);
+	// Every mode runs the all-on-GPU path: 180 GB of HBM holds the largest documented case
+	// (1024x1024x512 dual view, about 9 x 2 GiB) and this backend has no CPU path.
+	deconRecords[0] = 1;
+	const double t1 = now_s();
+
+	std::lock_guard<std::mutex> lock(g_cache_mu);
+	DeconCache &c = g_cache[nviews - 1];
+	const size_t npsf = (size_t)psfSize[0] * psfSize[1] * psfSize[2];
+	unsigned long long hash = fnv1a(&flagUnmatch, sizeof flagUnmatch);
+	for (int v = 0; v < nviews; v++) {
+		hash = fnv1a(h_psf[v], npsf * sizeof(float), hash);
+		if (flagUnmatch) hash = fnv1a(h_psf_bp[v], npsf * sizeof(float), hash);
+	}
+	const bool hit = cache_enabled() && c.h && c.device == deviceNum && c.nviews == nviews &&
+		!memcmp(c.im, imSize, sizeof c.im) && !memcmp(c.psf, psfSize, sizeof c.psf) && c.psf_hash == hash;
+	if (!hit) {
+		if (c.h) { milb_decon_destroy(c.h); c.h = nullptr; }
+		fatal_if(milb_decon_create(&c.h, nviews, imSize), "****Memory allocating fails... GPU out of memory !!!!*****");
+		for (int v = 0; v < nviews; v++)
+			fatal_if(milb_decon_set_psf(c.h, v, h_psf[v], flagUnmatch ? h_psf_bp[v] : nullptr, psfSize, flagUnmatch ? 1 : 0, 0, nullptr),
+				"****PSF and OTF preparation failed !!!!*****");
+		c.device = deviceNum; c.nviews = nviews; c.psf_hash = hash;
+		memcpy(c.im, imSize, sizeof c.im);
+		memcpy(c.psf, psfSize, sizeof c.psf);
+	}
+	deconRecords[2] = free_mb();
+	printf("...GPU free memory(after mallocing) is %.0f MBites\n", deconRecords[2]);
+	for (int v = 0; v < nviews; v++) fatal_if(milb_decon_set_image(c.h, v, h_img[v], 0, nullptr), "****Image preparation failed !!!!*****");
+	const double t2 = now_s();
+	fatal_if(milb_decon_run(c.h, itNumForDecon, flagConstInitial ? 1 : 0, nullptr), "decon iterration error");
+	fatal_if(milb_decon_get_result(c.h, h_decon, 0, nullptr), "decon result transfer");
+	const double t3 = now_s();
+	deconRecords[4] = free_mb();
+	printf("...GPU free memory (after processing) is %.0f MBites\n", deconRecords[4]);
+	if (!cache_enabled()) { milb_decon_destroy(c.h); c.h = nullptr; }
+	const double t_end = now_s();
+	deconRecords[5] = free_mb();
+	printf("GPU free memory (after variable released): %.0f MBites\n", deconRecords[5]);
+	deconRecords[6] = (float)(t1 - t_start);
+	deconRecords[7] = (float)(t2 - t1);
+	deconRecords[8] = (float)(t3 - t2);
+	deconRecords[9] = (float)(t_end - t_start);
+	return 0;
+}
+
+} // namespace
+
+extern "C" {
+
+// ---------------------------------------------------------------------------------------------
+// deconvolution
+// ---------------------------------------------------------------------------------------------
+int decon_singleview(float *h_decon, float *h_img, unsigned int *imSize, float *h_psf, unsigned int *psfSize, bool flagConstInitial,
+	int itNumForDecon, int deviceNum, int gpuMemMode, bool verbose, float *deconRecords, bool flagUnmatch, float *h_psf_bp)
+{
+	(void)verbose;
+	float *img[2] = {h_img, nullptr}, *psf[2] = {h_psf, nullptr}, *bp[2] = {h_psf_bp, nullptr};
+	return decon_common(1, h_decon, img, imSize, psf, psfSize, flagConstInitial, itNumForDecon, deviceNum, gpuMemMode, deconRecords,
+		flagUnmatch, bp, 1); // bad mode -> 1, src/api_decon.cpp:318
+}
+
+int decon_dualview(float *h_decon, float *h_img1, float *h_img2, unsigned int *imSize, float *h_psf1, float *h_psf2,
+	unsigned int *psfSize, bool flagConstInitial, int itNumForDecon, int deviceNum, int gpuMemMode, bool verbose,
+	float *deconRecords, bool flagUnmatch, float *h_psf_bp1, float *h_psf_bp2)
+{
+	(void)verbose;
+	float *img[2] = {h_img1, h_img2}, *psf[2] = {h_psf1, h_psf2}, *bp[2] = {h_psf_bp1, h_psf_bp2};
+	return decon_common(2, h_decon, img, imSize, psf, psfSize, flagConstInitial, itNumForDecon, deviceNum, gpuMemMode, deconRecords,
+		flagUnmatch, bp, -1); // bad mode -> -1, src/api_decon.cpp:687
+}
+
+// The reference's fusion_dualview never gets past its mode check (src/api_decon.cpp:1133-1136):
+// `(gpuMemMode != 1) || (gpuMemMode != 2)` is always true, so it prints and returns 1.
+int fusion_dualview(float *, float *, float *, float *, float *, float *, float *, unsigned int *, unsigned int *, float *, float *,
+	int, bool, int, float, int, float *, float *, unsigned int *, int, int, int, bool, float *, bool, float *, float *)
+{
+	printf("\n****Wrong gpuMemMode setup (All in GPU mode or Memory-saved GPU mode), processing stopped !!! ****\n");
+	return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// registration
+// ---------------------------------------------------------------------------------------------
+bool checkmatrix(float *m, long long int sx, long long int sy, long long int sz)
+{
+	// src/api_reg.cpp:247-262
+	bool ok = true;
+	const float scaleLow = 0.5f, scaleUp = 1.4f, scaleSumLow = 2, scaleSumUp = 4, shiftRatio = 0.8f;
+	if (m[0] < scaleLow || m[0] > scaleUp || m[5] < scaleLow || m[5] > scaleUp || m[10] < scaleLow || m[10] > scaleUp) ok = false;
+	if ((m[0] + m[5] + m[10]) < scaleSumLow || (m[0] + m[5] + m[10]) > scaleSumUp) ok = false;
+	if (fabsf(m[3]) > shiftRatio * sx || fabsf(m[7]) > shiftRatio * sy || fabsf(m[11]) > shiftRatio * sz) ok = false;
+	return ok;
+}
+
+int reg3d(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int *imSize1, unsigned int *imSize2, int regChoice,
+	int affMethod, bool flagTmx, float FTOL, int itLimit, int deviceNum, int gpuMemMode, bool verbose, float *records)
+{
+	const double t_start = now_s();
+	const long long n1 = (long long)imSize1[0] * imSize1[1] * imSize1[2];
+	const long long n2 = (long long)imSize2[0] * imSize2[1] * imSize2[2];
+	const long long nmax = n1 > n2 ? n1 : n2;
+	if (gpuMemMode != 0) {
+		cuda_fatal(cudaSetDevice(deviceNum), "cudaSetDevice");
+		records[8] = free_mb();
+		if (verbose) printf("\t... GPU free memory before registration is %.0f MB\n", records[8]);
+	}
+	if (gpuMemMode == -1) { // src/api_reg.cpp:330-372
+		size_t fr = 0, tot = 0;
+		cudaMemGetInfo(&fr, &tot);
+		const long long plane = 4ll * imSize1[0] * imSize1[1];
+		const bool phasor = (regChoice == 1) || (regChoice == 3);
+		const long long need1 = ((phasor ? 5 : 4) * nmax + plane) * (long long)sizeof(float);
+		const long long need2 = ((phasor ? 4 : 2) * nmax + plane) * (long long)sizeof(float);
+		gpuMemMode = ((long long)fr > need1) ? 1 : ((long long)fr > need2) ? 2 : 0;
+		if (verbose) printf("\t... GPU memory mode selected: %d\n", gpuMemMode);
+	}
+	records[0] = (float)gpuMemMode;
+	if (gpuMemMode == 0) {
+		printf("\n ****CPU registraion function is under developing **** \n");
+		return -1;
+	}
+	if (gpuMemMode != 1 && gpuMemMode != 2) {
+		printf("\n****Wrong gpuMemMode setup, no deconvolution performed !!! ****\n");
+		return 1;
+	}
+	if (regChoice < 0 || regChoice > 4) {
+		printf("\n*** Wrong registration choice is setup, no registraiton performed !!! **** \n");
+		return 1;
+	}
+	if (regChoice == 1 || regChoice == 3 || regChoice == 4) {
+		// phasor / 2-D MIP pre-alignment: SURVEY.md section 8(f) rank 3, not built yet
+		printf("\n ****regChoice %d (pre-alignment) is not available in the B200 backend yet **** \n", regChoice);
+		return -1;
+	}
+	// modes 1 and 2 run the same device-resident path
+	float *d_t = nullptr, *d_s = nullptr, *d_tmp = nullptr, *d_reg = nullptr;
+	cuda_fatal(cudaMalloc(&d_t, sizeof(float) * n1), "****Memory allocating fails... GPU out of memory !!!!*****");
+	cuda_fatal(cudaMalloc(&d_s, sizeof(float) * n1), "****Memory allocating fails... GPU out of memory !!!!*****");
+	cuda_fatal(cudaMalloc(&d_reg, sizeof(float) * n1), "****Memory allocating fails... GPU out of memory !!!!*****");
+	const bool same = imSize1[0] == imSize2[0] && imSize1[1] == imSize2[1] && imSize1[2] == imSize2[2];
+	if (same) cuda_fatal(cudaMemcpy(d_s, h_img2, sizeof(float) * n2, cudaMemcpyHostToDevice), "H2D");
+	else { // centre crop / zero pad the source to the target size, src/api_reg.cpp:401-406
+		cuda_fatal(cudaMalloc(&d_tmp, sizeof(float) * n2), "cudaMalloc");
+		cuda_fatal(cudaMemcpy(d_tmp, h_img2, sizeof(float) * n2, cudaMemcpyHostToDevice), "H2D");
+		fatal_if(milb_alignsize_dev(d_s, d_tmp, imSize1[0], imSize1[1], imSize1[2], imSize2[0], imSize2[1], imSize2[2], nullptr), "alignsize");
+	}
+	cuda_fatal(cudaMemcpy(d_t, h_img1, sizeof(float) * n1, cudaMemcpyHostToDevice), "H2D");
+	records[9] = free_mb();
+	if (regChoice == 0) affMethod = 0;
+	int rc = milb_reg3d_affine(d_reg, iTmx, d_t, d_s, imSize1, affMethod, flagTmx ? 1 : 0, FTOL, itLimit, 1, verbose ? 1 : 0, records, nullptr);
+	if (rc == 4) {
+		fprintf(stderr, "*** SD of image is zero, empty image input or empty image after initial transformation **** \n");
+		exit(1);
+	}
+	fatal_if(rc == MILB_ERR_ARG ? MILB_OK : rc, "registration failed");
+	cuda_fatal(cudaMemcpy(h_reg, d_reg, sizeof(float) * n1, cudaMemcpyDeviceToHost), "D2H");
+	cudaFree(d_t); cudaFree(d_s); cudaFree(d_reg);
+	if (d_tmp) cudaFree(d_tmp);
+	records[10] = free_mb();
+	records[7] = (float)(now_s() - t_start);
+	if (verbose) printf("\t... registration done !!! \n");
+	return 0;
+}
+
+int reg_3dgpu(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int *imSize1, unsigned int *imSize2, int affMethod,
+	int inputTmx, float FTOL, int itLimit, int subBgTrigger, int deviceNum, float *regRecords)
+{
+	// src/api_reg.cpp:609-652
+	(void)subBgTrigger;
+	int regChoice = 4;
+	bool flagTmx = false;
+	if (inputTmx == 1) { flagTmx = true; regChoice = 2; }
+	int st = reg3d(h_reg, iTmx, h_img1, h_img2, imSize1, imSize2, regChoice, affMethod, flagTmx, FTOL, itLimit, deviceNum, 1, false, regRecords);
+	if (!checkmatrix(iTmx, imSize1[0], imSize1[1], imSize1[2])) {
+		regChoice = 2;
+		st = reg3d(h_reg, iTmx, h_img1, h_img2, imSize1, imSize2, regChoice, affMethod, flagTmx, FTOL, itLimit, deviceNum, 1, false, regRecords);
+	}
+	return st;
+}
+
+int reg2d(float *, float *, float *, float *, unsigned int *, unsigned int *, int, bool, float, int, int, int, bool, float *)
+{
+	// 2-D registration is only reached through the pre-alignment choices
+	printf("\n ****reg2d is not available in the B200 backend **** \n");
+	return -1;
+}
+
+int atrans3dgpu(float *h_reg, float *iTmx, float *h_img2, unsigned int *imSize1, unsigned int *imSize2, int deviceNum)
+{
+	cuda_fatal(cudaSetDevice(deviceNum), "cudaSetDevice");
+	fatal_if(milb_affine_warp(h_reg, imSize1, h_img2, imSize2, iTmx, 0, nullptr), "affine transformation");
+	return 0;
+}
+
+int atrans3dgpu_16bit(unsigned short *h_reg, float *iTmx, unsigned short *h_img2, unsigned int *imSize1, unsigned int *imSize2, int deviceNum)
+{
+	cuda_fatal(cudaSetDevice(deviceNum), "cudaSetDevice");
+	const long long n1 = (long long)imSize1[0] * imSize1[1] * imSize1[2], n2 = (long long)imSize2[0] * imSize2[1] * imSize2[2];
+	unsigned short *d_o = nullptr, *d_i = nullptr;
+	cuda_fatal(cudaMalloc(&d_o, n1 * 2), "cudaMalloc");
+	cuda_fatal(cudaMalloc(&d_i, n2 * 2), "cudaMalloc");
+	cuda_fatal(cudaMemcpy(d_i, h_img2, n2 * 2, cudaMemcpyHostToDevice), "H2D");
+	fatal_if(milb_warp_u16_dev(d_o, d_i, imSize1[0], imSize1[1], imSize1[2], imSize2[0], imSize2[1], imSize2[2], iTmx, nullptr), "warp16");
+	cuda_fatal(cudaMemcpy(h_reg, d_o, n1 * 2, cudaMemcpyDeviceToHost), "D2H");
+	cudaFree(d_o); cudaFree(d_i);
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------
+int alignsize3d(float *h_odata, float *h_idata, long long int sx, long long int sy, long long int sz, long long int sx2,
+	long long int sy2, long long int sz2, int gpuMemMode)
+{
+	if (gpuMemMode < 0 || gpuMemMode > 2) {
+		printf("\n****Wrong gpuMemMode setup, processing stopped !!! ****\n");
+		return 1;
+	}
+	float *d_o = nullptr, *d_i = nullptr;
+	cuda_fatal(cudaMalloc(&d_o, sizeof(float) * sx * sy * sz), "cudaMalloc");
+	cuda_fatal(cudaMalloc(&d_i, sizeof(float) * sx2 * sy2 * sz2), "cudaMalloc");
+	cuda_fatal(cudaMemcpy(d_i, h_idata, sizeof(float) * sx2 * sy2 * sz2, cudaMemcpyHostToDevice), "H2D");
+	// the reference passes (sx,sy,sz) with sx the SLOWEST axis of its kernel; the per-axis rule is
+	// symmetric, so in x-fastest terms this is the same call with the axes reversed
+	fatal_if(milb_alignsize_dev(d_o, d_i, (int)sz, (int)sy, (int)sx, (int)sz2, (int)sy2, (int)sx2, nullptr), "alignsize");
+	cuda_fatal(cudaMemcpy(h_odata, d_o, sizeof(float) * sx * sy * sz, cudaMemcpyDeviceToHost), "D2H");
+	cudaFree(d_o); cudaFree(d_i);
+	return 0;
+}
+
+int imresize3d(float *h_odata, float *h_idata, long long int sx, long long int sy, long long int sz, long long int sx2,
+	long long int sy2, long long int sz2, int deviceNum)
+{
+	// src/apifunc.cpp:431-447: warp with diag(in/out), zero translation
+	float tmx[12] = {0};
+	tmx[0] = float(sx2) / float(sx);
+	tmx[5] = float(sy2) / float(sy);
+	tmx[10] = float(sz2) / float(sz);
+	unsigned int s1[3] = {(unsigned)sx, (unsigned)sy, (unsigned)sz}, s2[3] = {(unsigned)sx2, (unsigned)sy2, (unsigned)sz2};
+	(void)atrans3dgpu(h_odata, tmx, h_idata, s1, s2, deviceNum);
+	return 0;
+}
+
+int imoperation3D(float *h_odata, unsigned int *sizeOut, float *h_idata, unsigned int *sizeIn, int opChoice, int deviceNum)
+{
+	(void)deviceNum; // the reference never selects the device here either (src/apifunc.cpp:449-483)
+	if (opChoice == 0) return 0;
+	if (opChoice != 1 && opChoice != 2) {
+		printf("\n*** Wrong operation choice !!! **** \n");
+		return 1;
+	}
+	const long long n = (long long)sizeIn[0] * sizeIn[1] * sizeIn[2];
+	float *d_o = nullptr, *d_i = nullptr;
+	cuda_fatal(cudaMalloc(&d_o, sizeof(float) * n), "cudaMalloc");
+	cuda_fatal(cudaMalloc(&d_i, sizeof(float) * n), "cudaMalloc");
+	cuda_fatal(cudaMemcpy(d_i, h_idata, sizeof(float) * n, cudaMemcpyHostToDevice), "H2D");
+	fatal_if(milb_rot_y_dev(d_o, d_i, sizeIn[0], sizeIn[1], sizeIn[2], opChoice == 1 ? 1 : -1, nullptr), "rotation");
+	cuda_fatal(cudaMemcpy(h_odata, d_o, sizeof(float) * n, cudaMemcpyDeviceToHost), "D2H");
+	cudaFree(d_o); cudaFree(d_i);
+	const unsigned int a = sizeIn[0], b = sizeIn[1], c = sizeIn[2];
+	sizeOut[0] = c; sizeOut[1] = b; sizeOut[2] = a;
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// maximum-intensity projections
+// ---------------------------------------------------------------------------------------------
+int mp2dgpu(float *h_MP, unsigned int *sizeMP, float *h_img, unsigned int *sizeImg, bool flagZProj, bool flagXProj, bool flagYProj)
+{
+	(void)flagYProj; // sic: the reference gates the Y projection by flagZProj (src/apifunc.cpp:498)
+	const int sx = sizeImg[0], sy = sizeImg[1], sz = sizeImg[2];
+	const long long n = (long long)sx * sy * sz, nmp = (long long)sx * sy + (long long)sy * sz + (long long)sz * sx;
+	float *d_img = nullptr, *d_mp = nullptr;
+	cuda_fatal(cudaMalloc(&d_img, sizeof(float) * n), "cudaMalloc");
+	cuda_fatal(cudaMalloc(&d_mp, sizeof(float) * nmp), "cudaMalloc");
+	cuda_fatal(cudaMemset(d_mp, 0, sizeof(float) * nmp), "memset");
+	cuda_fatal(cudaMemcpy(d_img, h_img, sizeof(float) * n, cudaMemcpyHostToDevice), "H2D");
+	if (flagZProj) fatal_if(milb_mip_dev(d_mp, d_img, sx, sy, sz, 1, nullptr), "mip");
+	if (flagXProj) fatal_if(milb_mip_dev(d_mp + (long long)sx * sy, d_img, sx, sy, sz, 3, nullptr), "mip");
+	if (flagZProj) fatal_if(milb_mip_dev(d_mp + (long long)sx * sy + (long long)sy * sz, d_img, sx, sy, sz, 2, nullptr), "mip");
+	sizeMP[0] = sx; sizeMP[1] = sy; sizeMP[2] = sy; sizeMP[3] = sz; sizeMP[4] = sz; sizeMP[5] = sx;
+	cuda_fatal(cudaMemcpy(h_MP, d_mp, sizeof(float) * nmp, cudaMemcpyDeviceToHost), "D2H");
+	cudaFree(d_img); cudaFree(d_mp);
+	return 0;
+}
+
+// T(+size/2) * Rot(theta) * T(-R/2) with integer halves, src/api_subfunc.cu:626-713
+static void rot2matrix(float *p_out, float theta, long long sx, long long sy, long long sz, int rotAxis)
+{
+	float t1[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}, t2[12] = {0}, t3[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}, t[12];
+	const float c = cosf(theta), s = sinf(theta);
+	long long sNew;
+	if (rotAxis == 1) {
+		t1[7] = (float)(sy / 2); t1[11] = (float)(sz / 2);
+		const float r[12] = {1, 0, 0, 0, 0, c, s, 0, 0, -s, c, 0};
+		memcpy(t2, r, sizeof r);
+		sNew = (long long)round(sqrt((double)(sy * sy + sz * sz)));
+		t3[7] = (float)(-sNew / 2); t3[11] = (float)(-sNew / 2);
+	} else if (rotAxis == 2) {
+		t1[3] = (float)(sx / 2); t1[11] = (float)(sz / 2);
+		const float r[12] = {c, 0, -s, 0, 0, 1, 0, 0, s, 0, c, 0};
+		memcpy(t2, r, sizeof r);
+		sNew = (long long)round(sqrt((double)(sx * sx + sz * sz)));
+		t3[3] = (float)(-sNew / 2); t3[11] = (float)(-sNew / 2);
+	} else {
+		t1[3] = (float)(sx / 2); t1[7] = (float)(sy / 2);
+		const float r[12] = {c, s, 0, 0, -s, c, 0, 0, 0, 0, 1, 0};
+		memcpy(t2, r, sizeof r);
+		sNew = (long long)round(sqrt((double)(sx * sx + sy * sy)));
+		t3[3] = (float)(-sNew / 2); t3[7] = (float)(-sNew / 2);
+	}
+	milb_matrixmultiply(t, t1, t2);
+	milb_matrixmultiply(p_out, t, t3);
+}
+
+static int mip3d_axis(float *h_MP, float *d_img, const unsigned int *sizeImg, int rAxis, long long projectNum, float projectStep,
+	unsigned int *sizeOut /* 3 */)
+{
+	const long long sx = sizeImg[0], sy = sizeImg[1], sz = sizeImg[2];
+	long long sr, R;
+	if (rAxis == 1) { sr = sx; R = (long long)round(sqrt((double)(sy * sy + sz * sz))); }
+	else { sr = sy; R = (long long)round(sqrt((double)(sx * sx + sz * sz))); }
+	const unsigned int so[3] = {(unsigned)(rAxis == 1 ? sr : R), (unsigned)(rAxis == 1 ? R : sr), (unsigned)R};
+	const long long nrot = sr * R * R, nproj = sr * R;
+	float *d_rot = nullptr, *d_proj = nullptr;
+	cuda_fatal(cudaMalloc(&d_rot, sizeof(float) * nrot), "cudaMalloc");
+	cuda_fatal(cudaMalloc(&d_proj, sizeof(float) * nproj), "cudaMalloc");
+	for (long long i = 0; i < projectNum; i++) {
+		const float ang = projectStep * i;
+		float aff[12];
+		rot2matrix(aff, ang, sx, sy, sz, rAxis);
+		fatal_if(milb_affine_warp(d_rot, so, d_img, sizeImg, aff, 1, nullptr), "mip3d warp");
+		fatal_if(milb_mip_dev(d_proj, d_rot, so[0], so[1], so[2], 1, nullptr), "mip3d projection");
+		cuda_fatal(cudaMemcpy(h_MP + nproj * i, d_proj, sizeof(float) * nproj, cudaMemcpyDeviceToHost), "D2H");
+	}
+	cudaFree(d_rot); cudaFree(d_proj);
+	sizeOut[0] = so[0]; sizeOut[1] = so[1]; sizeOut[2] = (unsigned)projectNum;
+	return 0;
+}
+
+int mip3dgpu(float *h_MP, unsigned int *sizeMP, float *h_img, unsigned int *sizeImg, int rAxis, long long int projectNum)
+{
+	// src/apifunc.cpp:576-644
+	if (rAxis != 1 && rAxis != 2) return -1;
+	const long long n = (long long)sizeImg[0] * sizeImg[1] * sizeImg[2];
+	float *d_img = nullptr;
+	cuda_fatal(cudaMalloc(&d_img, sizeof(float) * n), "cudaMalloc");
+	cuda_fatal(cudaMemcpy(d_img, h_img, sizeof(float) * n, cudaMemcpyHostToDevice), "H2D");
+	const float projectStep = (float)(3.14159 * 2 / (float)projectNum);
+	mip3d_axis(h_MP, d_img, sizeImg, rAxis, projectNum, projectStep, sizeMP);
+	cudaFree(d_img);
+	return 0;
+}
+
+int mp3dgpu(float *h_MP, unsigned int *sizeMP, float *h_img, unsigned int *sizeImg, bool flagXaxis, bool flagYaxis, int projectNum)
+{
+	// src/apifunc.cpp:507-574
+	if (!flagXaxis && !flagYaxis) return -1;
+	const long long sx = sizeImg[0], sy = sizeImg[1], sz = sizeImg[2];
+	const long long n = sx * sy * sz;
+	float *d_img = nullptr;
+	cuda_fatal(cudaMalloc(&d_img, sizeof(float) * n), "cudaMalloc");
+	cuda_fatal(cudaMemcpy(d_img, h_img, sizeof(float) * n, cudaMemcpyHostToDevice), "H2D");
+	const float projectStep = (float)(3.14159 * 2 / projectNum);
+	if (flagXaxis) mip3d_axis(h_MP, d_img, sizeImg, 1, projectNum, projectStep, sizeMP);
+	if (flagYaxis) {
+		const long long Ry = (long long)round(sqrt((double)(sy * sy + sz * sz)));
+		const long long ystart = sx * Ry * projectNum; // offset is applied even when the X stack is absent (:548)
+		mip3d_axis(h_MP + ystart, d_img, sizeImg, 2, projectNum, projectStep, sizeMP + 3);
+	}
+	cudaFree(d_img);
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// misc
+// ---------------------------------------------------------------------------------------------
+char *concat(int count, ...)
+{
+	va_list ap;
+	size_t len = 1;
+	va_start(ap, count);
+	for (int i = 0; i < count; i++) len += strlen(va_arg(ap, char *));
+	va_end(ap);
+	char *merged = (char *)calloc(len, sizeof(char));
+	size_t at = 0;
+	va_start(ap, count);
+	for (int i = 0; i < count; i++) {
+		const char *s = va_arg(ap, char *);
+		const size_t l = strlen(s);
+		memcpy(merged + at, s, l);
+		at += l;
+	}
+	va_end(ap);
+	return merged;
+}
+
+bool fexists(const char *filename)
+{
+	FILE *f = fopen(filename, "r");
+	if (!f) return false;
+	fclose(f);
+	return true;
+}
+
+void queryDevice()
+{
+	printf(" \n ===========================================\n");
+	int count = 0;
+	cudaError_t e = cudaGetDeviceCount(&count);
+	if (e != cudaSuccess) {
+		printf("cudaGetDeviceCount returned %d\n-> %s\nResult = FAIL\n", (int)e, cudaGetErrorString(e));
+		exit(EXIT_FAILURE);
+	}
+	if (count == 0) printf("There are no available device(s) that support CUDA\n");
+	else printf("Detected %d CUDA Capable device(s)\n", count);
+	for (int dev = 0; dev < count; dev++) {
+		cudaDeviceProp p;
+		cudaGetDeviceProperties(&p, dev);
+		int drv = 0, rt = 0;
+		cudaDriverGetVersion(&drv);
+		cudaRuntimeGetVersion(&rt);
+		printf("\nDevice %d: \"%s\"\n", dev, p.name);
+		printf("  CUDA Driver Version / Runtime Version          %d.%d / %d.%d\n", drv / 1000, (drv % 100) / 10, rt / 1000, (rt % 100) / 10);
+		printf("  CUDA Capability Major/Minor version number:    %d.%d\n", p.major, p.minor);
+		printf("  Total amount of global memory:                 %.0f MBytes (%llu bytes)\n", (float)p.totalGlobalMem / 1048576.0f,
+			(unsigned long long)p.totalGlobalMem);
+		printf("  Multiprocessors:                               %d\n", p.multiProcessorCount);
+		printf("  Total amount of shared memory per block:       %lu bytes\n", (unsigned long)p.sharedMemPerBlock);
+		printf("  Shared memory per multiprocessor (opt-in max): %lu / %lu bytes\n", (unsigned long)p.sharedMemPerMultiprocessor,
+			(unsigned long)p.sharedMemPerBlockOptin);
+		printf("  L2 cache size:                                 %d bytes\n", p.l2CacheSize);
+		printf("  Warp size:                                     %d\n", p.warpSize);
+		printf("  Maximum number of threads per multiprocessor:  %d\n", p.maxThreadsPerMultiProcessor);
+		printf("  Maximum number of threads per block:           %d\n", p.maxThreadsPerBlock);
+		printf("  Device has ECC support:                        %s\n", p.ECCEnabled ? "Enabled" : "Disabled");
+	}
+	printf(" ===========================================\n\n");
+}
+
+} // extern "C"

@@ -1,0 +1,415 @@
+// Affine warp + ZNCC cost on sm_100a.
+// Replaces corrkernel / affinetransformkernel / sumgpu1Dkernel / reduceZ and their host wrappers
+// (include/cukernel.cuh:328-360, 500-556; src/api_subfunc.cu:942-988, 2345-2388, 2838-2868).
+// The reference samples the source through a linear-filtered 3-D texture; here the same fetch is
+// restated in software (documented CUDA texture-filtering formula, 8 fractional weight bits,
+// clamp addressing) with every rounding pinned by _rn intrinsics, so that the CPU oracle
+// (oracle/reg_oracle.c) and this kernel agree bit for bit on each interpolated sample.
+#include <math.h>
+#include <string.h>
+
+#include "../../include/milb_capi.h"
+#include "common.h"
+#include "launch_count.h"
+
+#define MILB_REG_MAXK 8
+
+struct AffBatch {
+	float m[MILB_REG_MAXK][12];
+};
+
+// ---- texture-equivalent trilinear fetch ---------------------------------------------------------
+__device__ __forceinline__ void split_coord(float t, int &i0, float &a)
+{
+	const float xb = __fsub_rn(t, 0.5f);
+	const float fl = floorf(xb);
+	const float fr = __fsub_rn(xb, fl);
+	a = __fmul_rn(floorf(__fadd_rn(__fmul_rn(fr, 256.0f), 0.5f)), 1.0f / 256.0f);
+	i0 = (int)fl;
+}
+
+__device__ __forceinline__ float lerp_rn(float w1, float lo, float hi)
+{
+	// (1 - w1) * lo + w1 * hi with separate roundings (no FMA contraction)
+	return __fadd_rn(__fmul_rn(__fsub_rn(1.0f, w1), lo), __fmul_rn(w1, hi));
+}
+
+__device__ __forceinline__ float tex3d_linear(const float *__restrict__ v, int sx, int sy, int sz, float tx, float ty, float tz)
+{
+	int ix, iy, iz;
+	float ax, ay, az;
+	split_coord(tx, ix, ax);
+	split_coord(ty, iy, ay);
+	split_coord(tz, iz, az);
+	const int x0 = min(max(ix, 0), sx - 1), x1 = min(max(ix + 1, 0), sx - 1);
+	const int y0 = min(max(iy, 0), sy - 1), y1 = min(max(iy + 1, 0), sy - 1);
+	const int z0 = min(max(iz, 0), sz - 1), z1 = min(max(iz + 1, 0), sz - 1);
+	const long long pl = (long long)sx * sy;
+	const float *p00 = v + (long long)y0 * sx + z0 * pl;
+	const float *p10 = v + (long long)y1 * sx + z0 * pl;
+	const float *p01 = v + (long long)y0 * sx + z1 * pl;
+	const float *p11 = v + (long long)y1 * sx + z1 * pl;
+	const float c00 = lerp_rn(ax, __ldg(p00 + x0), __ldg(p00 + x1));
+	const float c10 = lerp_rn(ax, __ldg(p10 + x0), __ldg(p10 + x1));
+	const float c01 = lerp_rn(ax, __ldg(p01 + x0), __ldg(p01 + x1));
+	const float c11 = lerp_rn(ax, __ldg(p11 + x0), __ldg(p11 + x1));
+	const float c0 = lerp_rn(ay, c00, c10);
+	const float c1 = lerp_rn(ay, c01, c11);
+	return lerp_rn(az, c0, c1);
+}
+
+// a0*x + a1*y + a2*z + a3 + 0.5 with the contraction nvcc -fmad=true gives the reference
+// expression (include/cukernel.cuh:510-512): mul, fma, fma, add, add.
+__device__ __forceinline__ float aff_coord(const float *a, float fx, float fy, float fz)
+{
+	float t = __fmul_rn(a[0], fx);
+	t = __fmaf_rn(a[1], fy, t);
+	t = __fmaf_rn(a[2], fz, t);
+	t = __fadd_rn(t, a[3]);
+	return __fadd_rn(t, 0.5f);
+}
+
+// ---- warp kernel (a17) ------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_affine_warp(float *__restrict__ out, const float *__restrict__ src, int sx, int sy, int sz,
+	int sx2, int sy2, int sz2, AffBatch aff)
+{
+	const long long n = (long long)sx * sy * sz;
+	const float *a = aff.m[0];
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		const int x = (int)(i % sx);
+		const long long t = i / sx;
+		const int y = (int)(t % sy), z = (int)(t / sy);
+		const float fx = (float)x, fy = (float)y, fz = (float)z;
+		const float tx = aff_coord(a + 0, fx, fy, fz), ty = aff_coord(a + 4, fx, fy, fz), tz = aff_coord(a + 8, fx, fy, fz);
+		float r = 0.f;
+		if (tx >= 0 && tx < (float)sx2 && ty >= 0 && ty < (float)sy2 && tz >= 0 && tz < (float)sz2)
+			r = tex3d_linear(src, sx2, sy2, sz2, tx, ty, tz);
+		out[i] = r;
+	}
+}
+
+// ---- fused warp + ZNCC sums (a14), K candidate matrices per launch -------------------------------
+// Tiles of 32(x) x 8(y) x ZT(z) target voxels; a block walks its tiles in a fixed order and every
+// thread owns fixed voxels, so the double-precision partial sums are reproducible run to run.
+#define REG_ZT 8
+template <int K>
+__global__ void __launch_bounds__(256) k_zncc(const float *__restrict__ tgt, const float *__restrict__ src, int sx, int sy, int sz,
+	AffBatch aff, double *__restrict__ partial /* [gridDim.x][K][2] */)
+{
+	__shared__ double sh[8][K][2];
+	double ss[K], st[K];
+#pragma unroll
+	for (int k = 0; k < K; k++) { ss[k] = 0; st[k] = 0; }
+	const int tx_n = (sx + 31) / 32, ty_n = (sy + 7) / 8, tz_n = (sz + REG_ZT - 1) / REG_ZT;
+	const long long ntiles = (long long)tx_n * ty_n * tz_n;
+	const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
+	const float fsx = (float)sx, fsy = (float)sy, fsz = (float)sz;
+	for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+		const int bx = (int)(tile % tx_n);
+		const long long r = tile / tx_n;
+		const int by = (int)(r % ty_n), bz = (int)(r / ty_n);
+		const int x = bx * 32 + lx, y = by * 8 + ly;
+		if (x >= sx || y >= sy) continue;
+		const float fx = (float)x, fy = (float)y;
+		const int z_end = min(sz, (bz + 1) * REG_ZT);
+		for (int z = bz * REG_ZT; z < z_end; z++) {
+			const float fz = (float)z;
+			const float t = tgt[x + (long long)y * sx + (long long)z * sx * sy];
+#pragma unroll
+			for (int k = 0; k < K; k++) {
+				const float *a = aff.m[k];
+				const float cx = aff_coord(a + 0, fx, fy, fz), cy = aff_coord(a + 4, fx, fy, fz), cz = aff_coord(a + 8, fx, fy, fz);
+				float s = 0.f;
+				if (cx > 0 && cx < fsx && cy > 0 && cy < fsy && cz > 0 && cz < fsz)
+					s = tex3d_linear(src, sx, sy, sz, cx, cy, cz);
+				ss[k] = fma((double)s, (double)s, ss[k]); // exact product, one rounding == (double)s*s then +=
+				st[k] = fma((double)s, (double)t, st[k]);
+			}
+		}
+	}
+	// fixed-order reduction: lanes (xor tree), then the 8 warps in order
+#pragma unroll
+	for (int k = 0; k < K; k++) {
+#pragma unroll
+		for (int o = 16; o > 0; o >>= 1) {
+			ss[k] += __shfl_xor_sync(0xffffffffu, ss[k], o);
+			st[k] += __shfl_xor_sync(0xffffffffu, st[k], o);
+		}
+		if (lx == 0) { sh[ly][k][0] = ss[k]; sh[ly][k][1] = st[k]; }
+	}
+	__syncthreads();
+	if (threadIdx.x < 2 * K) {
+		const int k = threadIdx.x >> 1, c = threadIdx.x & 1;
+		double a = 0;
+		for (int w = 0; w < 8; w++) a += sh[w][k][c];
+		partial[((long long)blockIdx.x * K + k) * 2 + c] = a;
+	}
+}
+
+// sums the per-block partials in block order: out[k*2 + c]
+__global__ void __launch_bounds__(256) k_zncc_final(const double *__restrict__ partial, int nblocks, int K, double *__restrict__ out)
+{
+	__shared__ double sh[256];
+	for (int q = 0; q < 2 * K; q++) {
+		double a = 0;
+		for (int b = threadIdx.x; b < nblocks; b += 256) a += partial[(long long)b * 2 * K + q];
+		sh[threadIdx.x] = a;
+		__syncthreads();
+		for (int s = 128; s > 0; s >>= 1) {
+			if (threadIdx.x < s) sh[threadIdx.x] += sh[threadIdx.x + s];
+			__syncthreads();
+		}
+		if (threadIdx.x == 0) out[q] = sh[0];
+		__syncthreads();
+	}
+}
+
+// out = in + shift, shift = -(float)sum / (float)n  (addvaluegpu with the reference's float mix)
+__global__ void k_demean(float *__restrict__ out, const float *__restrict__ in, const double *__restrict__ d_sum, long long n)
+{
+	const float shift = -(float)d_sum[0] / (float)n;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+		out[i] = __fadd_rn(in[i], shift);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct milb_reg {
+	int sx = 0, sy = 0, sz = 0;
+	long long n = 0;
+	float *tgt_raw = nullptr, *src_raw = nullptr; // owned copies
+	float *tgt_dm = nullptr, *src_dm = nullptr;
+	float *tmp = nullptr;
+	double *d_red = nullptr;     // [0..1] sums, [2..] scratch
+	double *d_partial = nullptr; // zncc partials
+	double *d_out = nullptr;     // 2*MAXK results
+	double *h_out = nullptr;     // pinned
+	int grid = 0;
+	float sd_t = 0.f;
+	bool have_images = false, prepared = false;
+};
+
+static int reg_grid_for(long long n) { long long b = cdiv_ll(n, 256); return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
+
+int milb_reg_create(milb_reg_t **out, const unsigned int *sizeT)
+{
+	if (!out || !sizeT || !sizeT[0] || !sizeT[1] || !sizeT[2]) return MILB_ERR_ARG;
+	milb_reg *h = new milb_reg();
+	h->sx = (int)sizeT[0]; h->sy = (int)sizeT[1]; h->sz = (int)sizeT[2];
+	h->n = (long long)h->sx * h->sy * h->sz;
+	const long long ntiles = (long long)((h->sx + 31) / 32) * ((h->sy + 7) / 8) * ((h->sz + REG_ZT - 1) / REG_ZT);
+	h->grid = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+	cudaError_t e = cudaMalloc(&h->tgt_raw, sizeof(float) * h->n);
+	if (e == cudaSuccess) e = cudaMalloc(&h->src_raw, sizeof(float) * h->n);
+	if (e == cudaSuccess) e = cudaMalloc(&h->tgt_dm, sizeof(float) * h->n);
+	if (e == cudaSuccess) e = cudaMalloc(&h->src_dm, sizeof(float) * h->n);
+	if (e == cudaSuccess) e = cudaMalloc(&h->tmp, sizeof(float) * h->n);
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_red, sizeof(double) * (2 + MILB_REDUCE_BLOCKS));
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_partial, sizeof(double) * 2 * MILB_REG_MAXK * h->grid);
+	if (e == cudaSuccess) e = cudaMalloc(&h->d_out, sizeof(double) * 2 * MILB_REG_MAXK);
+	if (e == cudaSuccess) e = cudaMallocHost(&h->h_out, sizeof(double) * 2 * MILB_REG_MAXK);
+	if (e != cudaSuccess) {
+		fprintf(stderr, "milb_reg_create: %s\n", cudaGetErrorString(e));
+		milb_reg_destroy(h);
+		return MILB_ERR_CUDA;
+	}
+	*out = h;
+	return MILB_OK;
+}
+
+void milb_reg_destroy(milb_reg_t *h)
+{
+	if (!h) return;
+	cudaFree(h->tgt_raw); cudaFree(h->src_raw); cudaFree(h->tgt_dm); cudaFree(h->src_dm); cudaFree(h->tmp);
+	cudaFree(h->d_red); cudaFree(h->d_partial); cudaFree(h->d_out);
+	if (h->h_out) cudaFreeHost(h->h_out);
+	delete h;
+}
+
+int milb_reg_set_images(milb_reg_t *h, const float *target, const float *source, int on_device, void *stream)
+{
+	if (!h || !target || !source) return MILB_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+	MILB_CUDA_TRY(cudaMemcpyAsync(h->tgt_raw, target, sizeof(float) * h->n, kind, st));
+	MILB_CUDA_TRY(cudaMemcpyAsync(h->src_raw, source, sizeof(float) * h->n, kind, st));
+	h->have_images = true;
+	h->prepared = false;
+	return MILB_OK;
+}
+
+static void aff_set(AffBatch &b, int k, const float *m) { memcpy(b.m[k], m, 12 * sizeof(float)); }
+
+static int launch_warp(float *out, const float *src, int sx, int sy, int sz, int sx2, int sy2, int sz2, const float *tmx, cudaStream_t st)
+{
+	AffBatch b;
+	memset(&b, 0, sizeof b);
+	aff_set(b, 0, tmx);
+	k_affine_warp<<<reg_grid_for((long long)sx * sy * sz), 256, 0, st>>>(out, src, sx, sy, sz, sx2, sy2, sz2, b);
+	milb_count_launches(1);
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+int milb_reg_prepare(milb_reg_t *h, const float *pre_tmx, float *sd_t, void *stream)
+{
+	if (!h || !h->have_images) return MILB_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	const float *src = h->src_raw;
+	if (pre_tmx) {
+		MILB_TRY(launch_warp(h->tmp, h->src_raw, h->sx, h->sy, h->sz, h->sx, h->sy, h->sz, pre_tmx, st));
+		src = h->tmp;
+	}
+	const int g = reg_grid_for(h->n);
+	MILB_TRY(milb_sum_f64_async(src, h->n, h->d_red + 2, h->d_red, st));
+	k_demean<<<g, 256, 0, st>>>(h->src_dm, src, h->d_red, h->n);
+	MILB_TRY(milb_sum_f64_async(h->tgt_raw, h->n, h->d_red + 2, h->d_red, st));
+	k_demean<<<g, 256, 0, st>>>(h->tgt_dm, h->tgt_raw, h->d_red, h->n);
+	milb_count_launches(2);
+	MILB_TRY(milb_sumsq_f64_async(h->src_dm, h->n, h->d_red + 2, h->d_red, st));
+	MILB_TRY(milb_sumsq_f64_async(h->tgt_dm, h->n, h->d_red + 2, h->d_red + 1, st));
+	double sq[2] = {0, 0};
+	MILB_CUDA_TRY(cudaMemcpyAsync(sq, h->d_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
+	MILB_CUDA_TRY(cudaStreamSynchronize(st));
+	h->sd_t = (float)sqrt(sq[1]); // valueStatic, src/api_subfunc.cu:2863
+	if (sd_t) *sd_t = h->sd_t;
+	if ((float)sqrt(sq[0]) == 0 || h->sd_t == 0) return MILB_ERR_EMPTY; // :2852-2855, :2864-2867
+	h->prepared = true;
+	return MILB_OK;
+}
+
+template <int K>
+static void launch_zncc(milb_reg *h, const AffBatch &b, cudaStream_t st)
+{
+	k_zncc<K><<<h->grid, 256, 0, st>>>(h->tgt_dm, h->src_dm, h->sx, h->sy, h->sz, b, h->d_partial);
+	k_zncc_final<<<1, 256, 0, st>>>(h->d_partial, h->grid, K, h->d_out);
+	milb_count_launches(2);
+}
+
+int milb_reg_cost_sums(milb_reg_t *h, const float *matrices, int K, double *ss, double *st_out, void *stream)
+{
+	if (!h || !h->prepared || !matrices || K < 1 || K > MILB_REG_MAXK) return MILB_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	AffBatch b;
+	memset(&b, 0, sizeof b);
+	for (int k = 0; k < K; k++) aff_set(b, k, matrices + 12 * k);
+	switch (K) {
+	case 1: launch_zncc<1>(h, b, st); break;
+	case 2: launch_zncc<2>(h, b, st); break;
+	case 3: launch_zncc<3>(h, b, st); break;
+	case 4: launch_zncc<4>(h, b, st); break;
+	case 5: launch_zncc<5>(h, b, st); break;
+	case 6: launch_zncc<6>(h, b, st); break;
+	case 7: launch_zncc<7>(h, b, st); break;
+	default: launch_zncc<8>(h, b, st); break;
+	}
+	MILB_CUDA_TRY(cudaGetLastError());
+	MILB_CUDA_TRY(cudaMemcpyAsync(h->h_out, h->d_out, sizeof(double) * 2 * K, cudaMemcpyDeviceToHost, st));
+	MILB_CUDA_TRY(cudaStreamSynchronize(st));
+	for (int k = 0; k < K; k++) { ss[k] = h->h_out[2 * k]; st_out[k] = h->h_out[2 * k + 1]; }
+	return MILB_OK;
+}
+
+int milb_reg_cost(milb_reg_t *h, const float *matrices, int K, float *costs, void *stream)
+{
+	double ss[MILB_REG_MAXK], st[MILB_REG_MAXK];
+	MILB_TRY(milb_reg_cost_sums(h, matrices, K, ss, st, stream));
+	for (int k = 0; k < K; k++) {
+		// corrfunc tail + costfunc negation, src/api_subfunc.cu:986-987, 2387
+		if (sqrt(ss[k]) == 0) costs[k] = 2.0f;
+		else costs[k] = -((float)(st[k] / sqrt(ss[k])) / h->sd_t);
+	}
+	return MILB_OK;
+}
+
+int milb_reg_warp_source(milb_reg_t *h, const float *tmx, float *out, int on_device, void *stream)
+{
+	if (!h || !h->have_images || !tmx || !out) return MILB_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	float *dst = on_device ? out : h->tmp;
+	MILB_TRY(launch_warp(dst, h->src_raw, h->sx, h->sy, h->sz, h->sx, h->sy, h->sz, tmx, st));
+	if (!on_device) MILB_CUDA_TRY(cudaMemcpyAsync(out, dst, sizeof(float) * h->n, cudaMemcpyDeviceToHost, st));
+	MILB_CUDA_TRY(cudaStreamSynchronize(st));
+	return MILB_OK;
+}
+
+int milb_affine_warp(float *out, const unsigned int *sizeOut, const float *src, const unsigned int *sizeSrc, const float *tmx,
+	int on_device, void *stream)
+{
+	if (!out || !src || !sizeOut || !sizeSrc || !tmx) return MILB_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	const long long no = (long long)sizeOut[0] * sizeOut[1] * sizeOut[2], ns = (long long)sizeSrc[0] * sizeSrc[1] * sizeSrc[2];
+	if (no <= 0 || ns <= 0) return MILB_ERR_ARG;
+	if (on_device)
+		return launch_warp(out, src, sizeOut[0], sizeOut[1], sizeOut[2], sizeSrc[0], sizeSrc[1], sizeSrc[2], tmx, st);
+	float *d_src = nullptr, *d_out = nullptr;
+	MILB_CUDA_TRY(cudaMalloc(&d_src, sizeof(float) * ns));
+	if (cudaMalloc(&d_out, sizeof(float) * no) != cudaSuccess) { cudaFree(d_src); return MILB_ERR_CUDA; }
+	int rc = MILB_OK;
+	if (cudaMemcpyAsync(d_src, src, sizeof(float) * ns, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = MILB_ERR_CUDA;
+	if (rc == MILB_OK) rc = launch_warp(d_out, d_src, sizeOut[0], sizeOut[1], sizeOut[2], sizeSrc[0], sizeSrc[1], sizeSrc[2], tmx, st);
+	if (rc == MILB_OK && cudaMemcpyAsync(out, d_out, sizeof(float) * no, cudaMemcpyDeviceToHost, st) != cudaSuccess) rc = MILB_ERR_CUDA;
+	if (cudaStreamSynchronize(st) != cudaSuccess) rc = MILB_ERR_CUDA;
+	cudaFree(d_src);
+	cudaFree(d_out);
+	return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Test utility (not on the product path): the same warp through a REAL hardware texture fetch --
+// cudaArray + linear filter + clamp + un-normalised coordinates, i.e. what the reference's
+// tex3D(tex, tx, ty, tz) does (include/cukernel.cuh:517-519, src/api_subfunc.cu:885-895).
+// tests/test_gpu_reg.py uses it to pin the software restatement of the texture filter on hardware.
+__global__ void k_debug_tex3d_warp(float *__restrict__ out, cudaTextureObject_t tex, int sx, int sy, int sz, AffBatch aff)
+{
+	const long long n = (long long)sx * sy * sz;
+	const float *a = aff.m[0];
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		const int x = (int)(i % sx);
+		const long long t = i / sx;
+		const int y = (int)(t % sy), z = (int)(t / sy);
+		const float fx = (float)x, fy = (float)y, fz = (float)z;
+		const float tx = aff_coord(a + 0, fx, fy, fz), ty = aff_coord(a + 4, fx, fy, fz), tz = aff_coord(a + 8, fx, fy, fz);
+		float r = 0.f;
+		if (tx >= 0 && tx < (float)sx && ty >= 0 && ty < (float)sy && tz >= 0 && tz < (float)sz) r = tex3D<float>(tex, tx, ty, tz);
+		out[i] = r;
+	}
+}
+
+extern "C" int milb_debug_tex3d_warp(float *h_out, const float *h_src, const unsigned int *size, const float *tmx)
+{
+	const int sx = size[0], sy = size[1], sz = size[2];
+	const long long n = (long long)sx * sy * sz;
+	cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+	cudaArray_t arr = nullptr;
+	MILB_CUDA_TRY(cudaMalloc3DArray(&arr, &desc, make_cudaExtent(sx, sy, sz)));
+	cudaMemcpy3DParms cp = {0};
+	cp.srcPtr = make_cudaPitchedPtr((void *)h_src, sx * sizeof(float), sx, sy);
+	cp.dstArray = arr;
+	cp.extent = make_cudaExtent(sx, sy, sz);
+	cp.kind = cudaMemcpyHostToDevice;
+	MILB_CUDA_TRY(cudaMemcpy3D(&cp));
+	cudaResourceDesc rd;
+	memset(&rd, 0, sizeof rd);
+	rd.resType = cudaResourceTypeArray;
+	rd.res.array.array = arr;
+	cudaTextureDesc td;
+	memset(&td, 0, sizeof td);
+	td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+	td.filterMode = cudaFilterModeLinear;
+	td.readMode = cudaReadModeElementType;
+	td.normalizedCoords = 0;
+	cudaTextureObject_t tex = 0;
+	MILB_CUDA_TRY(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+	float *d_out = nullptr;
+	MILB_CUDA_TRY(cudaMalloc(&d_out, sizeof(float) * n));
+	AffBatch b;
+	memset(&b, 0, sizeof b);
+	aff_set(b, 0, tmx);
+	k_debug_tex3d_warp<<<reg_grid_for(n), 256>>>(d_out, tex, sx, sy, sz, b);
+	MILB_CUDA_TRY(cudaGetLastError());
+	MILB_CUDA_TRY(cudaMemcpy(h_out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost));
+	cudaFree(d_out);
+	cudaDestroyTextureObject(tex);
+	cudaFreeArray(arr);
+	return MILB_OK;
+}

@@ -1,0 +1,264 @@
+"""Device-resident handles over the milb_* C-ABI (include/milb_capi.h).
+
+Inputs may be numpy arrays (host memory, copied by the library) or torch CUDA tensors (device
+pointers are passed through untouched; torch only provides memory and streams).  Volumes are
+float32 ``(slices, H, W)``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+_F = C.POINTER(C.c_float)
+_D = C.POINTER(C.c_double)
+
+
+class MilbError(RuntimeError):
+    pass
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise MilbError(f"{what} failed with milb status {rc}")
+
+
+def _is_torch(a):
+    return type(a).__module__.startswith("torch")
+
+
+def _ptr(a):
+    """(void* pointer, on_device flag, keepalive) for a numpy array or a torch tensor"""
+    if _is_torch(a):
+        assert a.dtype.is_floating_point and a.element_size() == 4 and a.is_contiguous()
+        return C.c_void_p(a.data_ptr()), (1 if a.is_cuda else 0), a
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    return C.c_void_p(a.ctypes.data), 0, a
+
+
+def _size(shape):
+    return (C.c_uint * 3)(int(shape[2]), int(shape[1]), int(shape[0]))
+
+
+def _stream(stream):
+    if stream is None:
+        return C.c_void_p(0)
+    if hasattr(stream, "cuda_stream"):
+        return C.c_void_p(stream.cuda_stream)
+    return C.c_void_p(int(stream))
+
+
+def launch_count() -> int:
+    return int(_lib.load().milb_launch_count())
+
+
+class Decon:
+    """Richardson-Lucy state for one image size: OTFs, views, estimate (milb_decon_t)."""
+
+    def __init__(self, im_shape, nviews=1):
+        self.lib = _lib.load()
+        self.im_shape = tuple(int(s) for s in im_shape)
+        self.nviews = nviews
+        self._h = C.c_void_p()
+        _check(self.lib.milb_decon_create(C.byref(self._h), nviews, _size(self.im_shape)), "milb_decon_create")
+        fs = (C.c_uint * 3)()
+        self.lib.milb_decon_fft_size(self._h, fs)
+        self.fft_shape = (int(fs[2]), int(fs[1]), int(fs[0]))
+
+    def close(self):
+        if self._h:
+            self.lib.milb_decon_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_psf(self, view, psf, psf_bp=None, stream=None):
+        p, dev, keep = _ptr(psf)
+        if psf_bp is not None:
+            pb, devb, keepb = _ptr(psf_bp)
+            assert devb == dev
+        else:
+            pb, keepb = C.c_void_p(0), None
+        shape = psf.shape
+        _check(self.lib.milb_decon_set_psf(self._h, view, p, pb, _size(shape), 1 if psf_bp is not None else 0, dev, _stream(stream)),
+               "milb_decon_set_psf")
+
+    def set_image(self, view, img, stream=None):
+        p, dev, keep = _ptr(img)
+        assert tuple(img.shape) == self.im_shape
+        _check(self.lib.milb_decon_set_image(self._h, view, p, dev, _stream(stream)), "milb_decon_set_image")
+
+    def run(self, iterations, const_init=False, stream=None):
+        _check(self.lib.milb_decon_run(self._h, int(iterations), 1 if const_init else 0, _stream(stream)), "milb_decon_run")
+
+    def run_cufft_yardstick(self, iterations, const_init=False, stream=None):
+        _check(self.lib.milb_decon_run_cufft_yardstick(self._h, int(iterations), 1 if const_init else 0, _stream(stream)),
+               "milb_decon_run_cufft_yardstick")
+
+    def set_chunk_planes(self, planes):
+        _check(self.lib.milb_decon_set_chunk_planes(self._h, int(planes)), "milb_decon_set_chunk_planes")
+
+    def result(self, out=None, stream=None):
+        if out is None:
+            out = np.empty(self.im_shape, np.float32)
+        p, dev, keep = _ptr(out)
+        _check(self.lib.milb_decon_get_result(self._h, p, dev, _stream(stream)), "milb_decon_get_result")
+        return out
+
+
+class Reg:
+    """Mean-removed target/source pair for ZNCC cost evaluations (milb_reg_t)."""
+
+    def __init__(self, shape):
+        self.lib = _lib.load()
+        self.shape = tuple(int(s) for s in shape)
+        self._h = C.c_void_p()
+        _check(self.lib.milb_reg_create(C.byref(self._h), _size(self.shape)), "milb_reg_create")
+        self.sd_t = None
+
+    def close(self):
+        if self._h:
+            self.lib.milb_reg_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_images(self, target, source, stream=None):
+        pt, dt, k1 = _ptr(target)
+        ps, ds, k2 = _ptr(source)
+        assert dt == ds
+        _check(self.lib.milb_reg_set_images(self._h, pt, ps, dt, _stream(stream)), "milb_reg_set_images")
+
+    def prepare(self, pre_tmx=None, stream=None):
+        sd = C.c_float(0)
+        if pre_tmx is not None:
+            m = np.ascontiguousarray(pre_tmx, np.float32).reshape(12)
+            mp = m.ctypes.data_as(_F)
+        else:
+            mp = C.cast(None, _F)
+        _check(self.lib.milb_reg_prepare(self._h, mp, C.byref(sd), _stream(stream)), "milb_reg_prepare")
+        self.sd_t = np.float32(sd.value)
+        return self.sd_t
+
+    def cost(self, matrices, stream=None):
+        m = np.ascontiguousarray(matrices, np.float32).reshape(-1, 12)
+        out = np.zeros(m.shape[0], np.float32)
+        _check(self.lib.milb_reg_cost(self._h, m.ctypes.data_as(_F), m.shape[0], out.ctypes.data_as(_F), _stream(stream)),
+               "milb_reg_cost")
+        return out
+
+    def cost_sums(self, matrices, stream=None):
+        m = np.ascontiguousarray(matrices, np.float32).reshape(-1, 12)
+        ss = np.zeros(m.shape[0], np.float64)
+        st = np.zeros(m.shape[0], np.float64)
+        _check(self.lib.milb_reg_cost_sums(self._h, m.ctypes.data_as(_F), m.shape[0], ss.ctypes.data_as(_D), st.ctypes.data_as(_D),
+                                           _stream(stream)), "milb_reg_cost_sums")
+        return ss, st
+
+    def warp_source(self, tmx, out=None, stream=None):
+        m = np.ascontiguousarray(tmx, np.float32).reshape(12)
+        if out is None:
+            out = np.empty(self.shape, np.float32)
+        p, dev, keep = _ptr(out)
+        _check(self.lib.milb_reg_warp_source(self._h, m.ctypes.data_as(_F), p, dev, _stream(stream)), "milb_reg_warp_source")
+        return out
+
+
+def affine_warp(src, tmx, out_shape=None, stream=None):
+    lib = _lib.load()
+    out_shape = tuple(out_shape or src.shape)
+    m = np.ascontiguousarray(tmx, np.float32).reshape(12)
+    ps, dev, keep = _ptr(src)
+    if dev:
+        import torch
+        out = torch.empty(out_shape, dtype=torch.float32, device=src.device)
+    else:
+        out = np.empty(out_shape, np.float32)
+    po, _, _ = _ptr(out)
+    _check(lib.milb_affine_warp(po, _size(out_shape), ps, _size(src.shape), m.ctypes.data_as(_F), dev, _stream(stream)),
+           "milb_affine_warp")
+    return out
+
+
+def reg3d_affine(target, source, aff_method, flag_tmx=False, itmx=None, ftol=1e-4, it_limit=3000, verbose=False, stream=None):
+    """milb_reg3d_affine on host arrays or CUDA tensors.  Returns (reg, tmx, records)."""
+    lib = _lib.load()
+    pt, dt, k1 = _ptr(target)
+    ps, ds, k2 = _ptr(source)
+    assert dt == ds
+    if dt:
+        import torch
+        reg = torch.empty_like(target)
+    else:
+        reg = np.empty(tuple(target.shape), np.float32)
+    pr, _, _ = _ptr(reg)
+    tmx = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32) if itmx is None else np.array(itmx, np.float32).reshape(12)
+    rec = np.zeros(11, np.float32)
+    rc = lib.milb_reg3d_affine(pr, tmx.ctypes.data_as(_F), pt, ps, _size(target.shape), int(aff_method), 1 if flag_tmx else 0,
+                               float(ftol), int(it_limit), dt, 1 if verbose else 0, rec.ctypes.data_as(_F), _stream(stream))
+    _check(rc, "milb_reg3d_affine")
+    return reg, tmx, rec
+
+
+# ---- host-side helpers exported for parity tests
+def p2matrix(x):
+    x = np.ascontiguousarray(x, np.float32)
+    m = np.zeros(12, np.float32)
+    _lib.load().milb_p2matrix(m.ctypes.data_as(_F), x.ctypes.data_as(_F))
+    return m
+
+
+def matrix2p(m):
+    m = np.ascontiguousarray(m, np.float32)
+    x = np.zeros(13, np.float32)
+    _lib.load().milb_matrix2p(m.ctypes.data_as(_F), x.ctypes.data_as(_F))
+    return x
+
+
+def matrixmultiply(m1, m2):
+    m1 = np.ascontiguousarray(m1, np.float32)
+    m2 = np.ascontiguousarray(m2, np.float32)
+    m = np.zeros(12, np.float32)
+    _lib.load().milb_matrixmultiply(m.ctypes.data_as(_F), m1.ctypes.data_as(_F), m2.ctypes.data_as(_F))
+    return m
+
+
+def dof9tomatrix(q, dof):
+    q = np.ascontiguousarray(q, np.float32)
+    m = np.zeros(12, np.float32)
+    _lib.load().milb_dof9tomatrix(m.ctypes.data_as(_F), q.ctypes.data_as(_F), int(dof))
+    return m
+
+
+def powell(p, xi, n, ftol, func, it_limit=3000, counter=None):
+    """milb_powell on a Python cost function (host only; used by the optimiser parity tests).
+    p: 1-indexed float32 array (len n+1), xi: (n, n) float32 array, updated in place.
+    `func(x)` gets a 1-indexed numpy copy; `counter` is a ctypes c_int the function may bump.
+    Returns (iter, fret)."""
+    lib = _lib.load()
+    p = np.ascontiguousarray(p, np.float32)
+    xi_c = np.ascontiguousarray(xi, np.float32)
+    counter = counter if counter is not None else C.c_int(0)
+    it = C.c_int(0)
+    fret = C.c_float(0)
+
+    def _cb(ptr, user):
+        x = np.ctypeslib.as_array(ptr, shape=(n + 1,)).copy()
+        return float(func(x))
+
+    cb = _lib.COSTFN(_cb)
+    rc = lib.milb_powell(p.ctypes.data_as(_F), xi_c.ctypes.data_as(_F), n, C.c_float(ftol), C.byref(it), C.byref(fret), cb, None,
+                         C.byref(counter), int(it_limit))
+    _check(rc, "milb_powell")
+    xi[...] = xi_c
+    return it.value, np.float32(fret.value), p

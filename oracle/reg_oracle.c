@@ -1,0 +1,206 @@
+/* CPU restatement of the registration cost path of microImageLib.  TEST INFRASTRUCTURE ONLY.
+ * (see oracle/__init__.py: parity unpinned by the reference; pinned by KATs in tests/ and by a
+ *  hardware tex3D cross-check run on the GPU box.)
+ *
+ * Build: gcc -O2 -fopenmp -ffp-contract=off -shared -fPIC  (oracle/Makefile).
+ * -ffp-contract=off matters: every float expression below is evaluated exactly as written.
+ *
+ * Layout: volumes are x-fastest, idx = x + y*sx + z*sx*sy  (include/cukernel.cuh:549).
+ */
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+/* ---- texture fetch as the reference uses it -------------------------------------------------
+ * include/cukernel.cuh:510-519,539-546 fetch tex3D(tex, tx, ty, tz) with linear filtering,
+ * un-normalised coordinates and (effective) clamp addressing.  CUDA Programming Guide,
+ * "Texture Fetching / Linear Filtering": xB = x - 0.5, i = floor(xB), alpha = frac(xB) stored in
+ * 9-bit fixed point with 8 fractional bits; result = sum over the 8 corners of weight * texel.
+ * Canonical evaluation order (the CUDA product path restates the same order):
+ *   lerp along x, then y, then z, each as  (1-a)*lo + a*hi  with separate roundings.      */
+static inline int clampi(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
+
+static inline void split_coord(float t, int *i0, float *a)
+{
+	float xb = t - 0.5f;
+	float fl = floorf(xb);
+	float fr = xb - fl;                                   /* exact */
+	float q = floorf(fr * 256.0f + 0.5f) * (1.0f / 256.0f); /* 8 fractional bits, round to nearest */
+	*i0 = (int)fl;
+	*a = q;
+}
+
+static inline float tex3d_linear(const float *v, long long sx, long long sy, long long sz,
+	float tx, float ty, float tz)
+{
+	int ix, iy, iz;
+	float ax, ay, az;
+	split_coord(tx, &ix, &ax);
+	split_coord(ty, &iy, &ay);
+	split_coord(tz, &iz, &az);
+	int x0 = clampi(ix, (int)sx - 1), x1 = clampi(ix + 1, (int)sx - 1);
+	int y0 = clampi(iy, (int)sy - 1), y1 = clampi(iy + 1, (int)sy - 1);
+	int z0 = clampi(iz, (int)sz - 1), z1 = clampi(iz + 1, (int)sz - 1);
+	const float *p00 = v + (long long)y0 * sx + (long long)z0 * sx * sy;
+	const float *p10 = v + (long long)y1 * sx + (long long)z0 * sx * sy;
+	const float *p01 = v + (long long)y0 * sx + (long long)z1 * sx * sy;
+	const float *p11 = v + (long long)y1 * sx + (long long)z1 * sx * sy;
+	float bx = 1.0f - ax, by = 1.0f - ay, bz = 1.0f - az;
+	float c00 = bx * p00[x0] + ax * p00[x1];
+	float c10 = bx * p10[x0] + ax * p10[x1];
+	float c01 = bx * p01[x0] + ax * p01[x1];
+	float c11 = bx * p11[x0] + ax * p11[x1];
+	float c0 = by * c00 + ay * c10;
+	float c1 = by * c01 + ay * c11;
+	return bz * c0 + az * c1;
+}
+
+/* Affine coordinate: d_aff[0]*ix + d_aff[1]*iy + d_aff[2]*iz + d_aff[3] + 0.5
+ * (include/cukernel.cuh:510-512).  nvcc's default -fmad=true contracts the float sum
+ * left to right: mul, fma, fma, add; the "+0.5" is a double add narrowed to float, which
+ * equals a correctly rounded float add.  fmaf() restates the contraction.               */
+static inline float aff_coord(const float *a, float ix, float iy, float iz)
+{
+	float t = a[0] * ix;
+	t = fmaf(a[1], iy, t);
+	t = fmaf(a[2], iz, t);
+	t = t + a[3];
+	return (float)((double)t + 0.5);
+}
+
+/* a17: affinetransformkernel, include/cukernel.cuh:500-524.  Output dims (sx,sy,sz),
+ * source dims (sx2,sy2,sz2); 0 outside 0 <= t < dim. */
+void orc_affine_warp(float *out, const float *src, long long sx, long long sy, long long sz,
+	long long sx2, long long sy2, long long sz2, const float *aff)
+{
+#pragma omp parallel for schedule(static)
+	for (long long z = 0; z < sz; z++)
+		for (long long y = 0; y < sy; y++)
+			for (long long x = 0; x < sx; x++) {
+				float tx = aff_coord(aff + 0, (float)x, (float)y, (float)z);
+				float ty = aff_coord(aff + 4, (float)x, (float)y, (float)z);
+				float tz = aff_coord(aff + 8, (float)x, (float)y, (float)z);
+				float r = 0.0f;
+				if (tx >= 0 && tx < (float)sx2 && ty >= 0 && ty < (float)sy2 && tz >= 0 && tz < (float)sz2)
+					r = tex3d_linear(src, sx2, sy2, sz2, tx, ty, tz);
+				out[x + y * sx + z * sx * sy] = r;
+			}
+}
+
+/* a14: corrkernel, include/cukernel.cuh:526-556: sums of s*s and s*t in double, s = warped
+ * source (0 outside 0 < t < dim), t = target.  Column-wise over z like the reference, then the
+ * columns are added in index order (the reference's 5x1024 strided second stage only changes
+ * the double-precision summation order). */
+void orc_zncc_sums(const float *target, const float *src, long long sx, long long sy, long long sz,
+	long long sx2, long long sy2, long long sz2, const float *aff, double *out_ss, double *out_st)
+{
+	long long sxy = sx * sy;
+	double *css = (double *)malloc(sizeof(double) * sxy);
+	double *cst = (double *)malloc(sizeof(double) * sxy);
+#pragma omp parallel for schedule(static)
+	for (long long y = 0; y < sy; y++)
+		for (long long x = 0; x < sx; x++) {
+			double ss = 0, st = 0;
+			for (long long z = 0; z < sz; z++) {
+				float tx = aff_coord(aff + 0, (float)x, (float)y, (float)z);
+				float ty = aff_coord(aff + 4, (float)x, (float)y, (float)z);
+				float tz = aff_coord(aff + 8, (float)x, (float)y, (float)z);
+				float s = 0.0f;
+				if (tx > 0 && tx < (float)sx2 && ty > 0 && ty < (float)sy2 && tz > 0 && tz < (float)sz2)
+					s = tex3d_linear(src, sx2, sy2, sz2, tx, ty, tz);
+				float t = target[x + y * sx + z * sxy];
+				ss += (double)s * s;
+				st += (double)s * t;
+			}
+			css[x + y * sx] = ss;
+			cst[x + y * sx] = st;
+		}
+	double ss = 0, st = 0;
+	for (long long i = 0; i < sxy; i++) { ss += css[i]; st += cst[i]; }
+	free(css); free(cst);
+	*out_ss = ss; *out_st = st;
+}
+
+/* corrfunc tail, src/api_subfunc.cu:986-987, negated as costfunc does (:2387). */
+float orc_cost_from_sums(double ss, double st, float sd_t)
+{
+	if (sqrt(ss) == 0) return 2.0f;
+	return -((float)(st / sqrt(ss)) / sd_t);
+}
+
+/* sum3Dgpu semantics (src/api_subfunc.cu:385-402): double accumulation of float data. */
+double orc_sum(const float *v, long long n)
+{
+	double s = 0;
+	for (long long i = 0; i < n; i++) s += (double)v[i];
+	return s;
+}
+
+/* mean removal + norm, src/api_subfunc.cu:2838-2868:
+ *   out = in + (-float(sum)/float(n));  returns sqrt(sum of float squares in double) as float */
+float orc_demean(float *out, const float *in, long long n)
+{
+	double s = orc_sum(in, n);
+	float shift = -(float)s / (float)n;
+	double sq = 0;
+	for (long long i = 0; i < n; i++) {
+		float d = in[i] + shift;
+		out[i] = d;
+		float d2 = d * d;
+		sq += (double)d2;
+	}
+	return (float)sqrt(sq);
+}
+
+/* ---- parameter <-> matrix, src/api_subfunc.cu:557-623, 715-824 (x is NR 1-indexed) ---------- */
+void orc_p2matrix(float *m, const float *x)
+{
+	m[0] = x[4]; m[1] = x[5]; m[2] = x[6]; m[3] = x[1];
+	m[4] = x[7]; m[5] = x[8]; m[6] = x[9]; m[7] = x[2];
+	m[8] = x[10]; m[9] = x[11]; m[10] = x[12]; m[11] = x[3];
+}
+
+void orc_matrix2p(const float *m, float *x)
+{
+	x[0] = 0;
+	x[1] = m[3]; x[2] = m[7]; x[3] = m[11]; x[4] = m[0];
+	x[5] = m[1]; x[6] = m[2]; x[7] = m[4]; x[8] = m[5];
+	x[9] = m[6]; x[10] = m[8]; x[11] = m[9]; x[12] = m[10];
+}
+
+void orc_matrixmultiply(float *m, const float *m1, const float *m2)
+{
+	for (int r = 0; r < 3; r++) {
+		const float *a = m1 + 4 * r;
+		m[4 * r + 0] = a[0] * m2[0] + a[1] * m2[4] + a[2] * m2[8];
+		m[4 * r + 1] = a[0] * m2[1] + a[1] * m2[5] + a[2] * m2[9];
+		m[4 * r + 2] = a[0] * m2[2] + a[1] * m2[6] + a[2] * m2[10];
+		m[4 * r + 3] = a[0] * m2[3] + a[1] * m2[7] + a[2] * m2[11] + a[3];
+	}
+}
+
+void orc_dof9tomatrix(float *p_out, const float *p_dof, int dofNum)
+{
+	float t1[12], t2[12], t3[12];
+	float x = p_dof[1], y = p_dof[2], z = p_dof[3];
+	float alpha = 0, beta = 0, theta = 0, a = 1, b = 1, c = 1;
+	if (dofNum >= 6) {
+		alpha = (float)(p_dof[4] / 57.3);   /* double divide narrowed to float, :744-746 */
+		beta = (float)(p_dof[5] / 57.3);
+		theta = (float)(p_dof[6] / 57.3);
+	}
+	if (dofNum == 7) { a = b = c = p_dof[7]; }
+	if (dofNum == 9) { a = p_dof[7]; b = p_dof[8]; c = p_dof[9]; }
+	memset(t2, 0, sizeof t2);
+	t2[3] = x; t2[7] = y; t2[11] = z;
+	t2[0] = a; t2[5] = b; t2[10] = c;
+	memset(t3, 0, sizeof t3);
+	t3[0] = cosf(alpha); t3[1] = sinf(alpha); t3[4] = -sinf(alpha); t3[5] = cosf(alpha); t3[10] = 1;
+	orc_matrixmultiply(t1, t2, t3);
+	memset(t3, 0, sizeof t3);
+	t3[0] = 1; t3[5] = cosf(beta); t3[6] = sinf(beta); t3[9] = -sinf(beta); t3[10] = cosf(beta);
+	orc_matrixmultiply(t2, t1, t3);
+	memset(t3, 0, sizeof t3);
+	t3[0] = cosf(theta); t3[2] = -sinf(theta); t3[5] = 1; t3[8] = sinf(theta); t3[10] = cosf(theta);
+	orc_matrixmultiply(p_out, t2, t3);
+}

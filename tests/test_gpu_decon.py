@@ -1,0 +1,135 @@
+"""GPU parity of the Richardson-Lucy path against the CPU oracle (oracle/decon_oracle.py),
+called through the C-ABI (libapi.so).  Tolerance from BASELINE.json north_star:
+relative L2 error <= 1e-4 after the stated iteration count."""
+import numpy as np
+import pytest
+
+from microimagelib_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4  # north_star: "deconvolved volumes within a relative L2 error of 1e-4"
+
+
+def rel_l2(a, b):
+    a = a.astype(np.float64)
+    b = b.astype(np.float64)
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))
+
+
+def _case(shape, psf_shape, sigma, seed=synth.SEED_A):
+    psf = synth.gaussian_psf(psf_shape, sigma)
+    img = synth.bead_image(shape, psf, seed=seed)
+    return img, psf
+
+
+def test_config1_singleview_128cube_10it():
+    """BASELINE config 1: 128x128x128 beads + Gaussian PSF, 10 iterations."""
+    from microimagelib_b200 import libapi
+    from oracle import decon_oracle as do
+    img, psf = _case((128, 128, 128), (65, 65, 65), (4, 2, 2))
+    got, st, rec = libapi.decon_singleview(img, psf, 10)
+    assert st == 0 and rec[0] == 1
+    ref = do.decon_singleview(img, psf, 10)
+    assert rel_l2(got, ref) <= TOL
+    # flux is conserved by RL with a unit-DC OTF (SURVEY 8(c) KAT 2)
+    assert abs(got.sum(dtype=np.float64) / np.maximum(img, 0.01).sum(dtype=np.float64) - 1) < 1e-3
+
+
+@pytest.mark.parametrize("shape,psf_shape", [
+    ((64, 64, 64), (33, 33, 33)),          # pow2 box, odd PSF
+    ((40, 100, 150), (31, 33, 35)),        # box 64 x 128 x 192: padding + radix-3 axis
+    ((96, 140, 90), (32, 32, 32)),         # even PSF (flip quirk), box 128 x 192 x 128
+    ((20, 300, 36), (21, 21, 21)),         # box 32 x 320 x 64: radix-5 axis
+    ((16, 16, 16), (33, 17, 9)),           # PSF larger than the box in one axis
+])
+def test_singleview_shapes(shape, psf_shape):
+    from microimagelib_b200 import libapi
+    from oracle import decon_oracle as do
+    img, psf = _case(shape, psf_shape, (2.5, 2.0, 1.5))
+    got, st, _ = libapi.decon_singleview(img, psf, 5)
+    assert st == 0
+    ref = do.decon_singleview(img, psf, 5)
+    assert got.shape == ref.shape
+    assert rel_l2(got, ref) <= TOL
+
+
+def test_singleview_const_init_and_unmatched():
+    from microimagelib_b200 import libapi
+    from oracle import decon_oracle as do
+    img, psf = _case((48, 64, 80), (25, 25, 25), (3, 2, 2))
+    bp = synth.gaussian_psf((25, 25, 25), (1.5, 1.0, 1.0))
+    got, st, _ = libapi.decon_singleview(img, psf, 4, initialFlag=True)
+    ref = do.decon_singleview(img, psf, 4, const_init=True)
+    assert rel_l2(got, ref) <= TOL
+    got, st, _ = libapi.decon_singleview(img, psf, 4, flagUnmatch=True, psf_bp=bp)
+    ref = do.decon_singleview(img, psf, 4, unmatch=True, psf_bp=bp)
+    assert rel_l2(got, ref) <= TOL
+
+
+def test_dualview():
+    from microimagelib_b200 import libapi
+    from oracle import decon_oracle as do
+    shape = (64, 96, 128)
+    psf_a = synth.gaussian_psf((33, 33, 33), (4, 2, 2))
+    psf_b = synth.gaussian_psf((33, 33, 33), (2, 2, 4))
+    a = synth.bead_image(shape, psf_a, seed=synth.SEED_A, noise_seed=synth.SEED_NOISE)
+    b = synth.bead_image(shape, psf_b, seed=synth.SEED_A, noise_seed=synth.SEED_NOISE + 1)
+    got, st, rec = libapi.decon_dualview(a, b, psf_a, psf_b, 6)
+    assert st == 0
+    ref = do.decon_dualview(a, b, psf_a, psf_b, 6)
+    assert rel_l2(got, ref) <= TOL
+    got, st, rec = libapi.decon_dualview(a, b, psf_a, psf_b, 3, initialFlag=True)
+    ref = do.decon_dualview(a, b, psf_a, psf_b, 3, const_init=True)
+    assert rel_l2(got, ref) <= TOL
+
+
+def test_delta_image_closed_form():
+    """KAT: a constant image is a fixed point; a delta image after one iteration has the closed
+    form E1 = max(A * (h_bp conv (A / (h conv A))), .01) -- checked against float64 numpy."""
+    from microimagelib_b200 import libapi
+    import scipy.fft as sfft
+    shape = (32, 32, 32)
+    psf = synth.gaussian_psf((15, 15, 15), (2, 2, 2))
+    const = np.full(shape, 7.0, np.float32)
+    got, st, _ = libapi.decon_singleview(const, psf, 3)
+    assert np.allclose(got, 7.0, rtol=1e-5)
+    img = np.full(shape, 1.0, np.float32)
+    img[16, 16, 16] = 1000.0
+    got, st, _ = libapi.decon_singleview(img, psf, 1)
+    box = np.zeros(shape)
+    idx = [(np.arange(15) - 7) % 32] * 3
+    box[np.ix_(*idx)] = psf.astype(np.float64) / psf.astype(np.float64).sum()
+    H = sfft.fftn(box)
+    A = img.astype(np.float64)
+    conv = sfft.ifftn(sfft.fftn(A) * H).real
+    ratio = A / conv
+    back = sfft.ifftn(sfft.fftn(ratio) * np.conj(H)).real  # odd symmetric PSF: flipped == conj
+    want = np.maximum(A * back, 0.01)
+    assert rel_l2(got, want) <= TOL
+
+
+def test_bad_mode_returns_like_reference():
+    from microimagelib_b200 import libapi
+    img, psf = _case((16, 16, 16), (9, 9, 9), (1, 1, 1))
+    _, st, _ = libapi.decon_singleview(img, psf, 1, gpuMemMode=7)
+    assert st == 1      # src/api_decon.cpp:318
+    _, st, _ = libapi.decon_dualview(img, img, psf, psf, 1, gpuMemMode=7)
+    assert st == -1     # src/api_decon.cpp:687
+    assert libapi.fusion_dualview_status() == 1   # src/api_decon.cpp:1133-1136
+
+
+def test_device_resident_handle_matches_host_api():
+    import torch
+    from microimagelib_b200 import device, libapi
+    img, psf = _case((64, 64, 64), (17, 17, 17), (2, 2, 2))
+    ref, _, _ = libapi.decon_singleview(img, psf, 3)
+    d = device.Decon(img.shape, 1)
+    d.set_psf(0, psf)
+    d.set_image(0, torch.from_numpy(img).cuda())
+    d.run(3)
+    out = torch.empty(img.shape, dtype=torch.float32, device="cuda")
+    d.result(out)
+    torch.cuda.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref)
+    d.close()
