@@ -77,3 +77,9 @@ def warp_exact(vol: np.ndarray, m12: np.ndarray, out_shape=None) -> np.ndarray:
         cz = M[2, 0] * x + M[2, 1] * y + M[2, 2] * z + M[2, 3]
         out[z] = map_coordinates(vol, [cz, cy, cx], order=1, mode="constant", cval=0.0)
     return out
+
+
+def invert_affine(m12) -> np.ndarray:
+    """Inverse of a 3x4 affine (implicit last row 0 0 0 1), float64 -> float32."""
+    M = np.vstack([np.asarray(m12, np.float64).reshape(3, 4), [0, 0, 0, 1]])
+    return np.linalg.inv(M)[:3].astype(np.float32).reshape(12)

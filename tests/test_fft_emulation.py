@@ -1,0 +1,64 @@
+"""CPU emulation of the device FFT stages (csrc/fft_core.h + fft_plan.h compiled with g++):
+the mixed-radix butterflies, twiddles, position tables and the two-real-pencils-in-one-complex
+split/merge are checked against numpy's float64 FFT for every size class snapTransformSize yields."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SO = os.path.join(HERE, "emul", "libfft_emul.so")
+F = C.POINTER(C.c_float)
+I = C.POINTER(C.c_int)
+
+
+@pytest.fixture(scope="module")
+def lib():
+    src = os.path.join(HERE, "emul", "fft_emul.cpp")
+    if not os.path.exists(SO) or os.path.getmtime(SO) < os.path.getmtime(src):
+        subprocess.run(["g++", "-O2", "-shared", "-fPIC", "-o", SO, src], check=True)
+    return C.CDLL(SO)
+
+
+SIZES = [16, 32, 64, 128, 192, 256, 320, 384, 448, 512, 576, 640, 704, 768, 832, 896, 960, 1024, 1088, 1216, 2048]
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_forward_inverse_and_positions(lib, n):
+    rng = np.random.default_rng(n)
+    radix = (C.c_int * 8)()
+    pos = np.zeros(n, np.int32)
+    ns = lib.emul_plan(n, radix, pos.ctypes.data_as(I))
+    assert ns > 0 and int(np.prod([radix[i] for i in range(ns)])) == n
+    assert sorted(pos.tolist()) == list(range(n))
+    x = (rng.standard_normal((n, 4)) + 1j * rng.standard_normal((n, 4))).astype(np.complex64)
+    d = x.copy()
+    assert lib.emul_fft(n, 4, d.ctypes.data_as(F), 0) == 0
+    ref = np.fft.fft(x.astype(np.complex128), axis=0)
+    assert np.linalg.norm(d[pos] - ref) / np.linalg.norm(ref) < 5e-7
+    assert lib.emul_fft(n, 4, d.ctypes.data_as(F), 1) == 0
+    assert np.linalg.norm(d / n - x) / np.linalg.norm(x) < 5e-7
+
+
+@pytest.mark.parametrize("n", SIZES)
+def test_two_real_pencils_in_one_complex(lib, n):
+    rng = np.random.default_rng(n + 1)
+    a = rng.standard_normal(n).astype(np.float32)
+    b = rng.standard_normal(n).astype(np.float32)
+    A = np.zeros(n // 2 + 1, np.complex64)
+    B = np.zeros(n // 2 + 1, np.complex64)
+    lib.emul_r2c_pair(n, a.ctypes.data_as(F), b.ctypes.data_as(F), A.ctypes.data_as(F), B.ctypes.data_as(F))
+    for got, src in ((A, a), (B, b)):
+        ref = np.fft.rfft(src.astype(np.float64))
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 5e-7
+    a2 = np.zeros(n, np.float32)
+    b2 = np.zeros(n, np.float32)
+    lib.emul_c2r_pair(n, A.ctypes.data_as(F), B.ctypes.data_as(F), a2.ctypes.data_as(F), b2.ctypes.data_as(F))
+    assert np.abs(a2 / n - a).max() < 5e-6 and np.abs(b2 / n - b).max() < 5e-6
+
+
+def test_unsupported_prime_factor_is_rejected(lib):
+    radix = (C.c_int * 8)()
+    assert lib.emul_plan(64 * 67, radix, None) == -1

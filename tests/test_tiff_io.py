@@ -1,0 +1,50 @@
+"""TIFF stack I/O of libapi (csrc/tiff_io.cpp, host only): round trips, the reference's pixel
+conversion rules (src/apifunc.cpp:171-175, :255) and interoperability with libtiff via Pillow."""
+import numpy as np
+import pytest
+
+from microimagelib_b200 import libapi
+
+
+def test_roundtrip_16_and_32_bit(tmp_path):
+    rng = np.random.default_rng(0)
+    vol = (rng.random((5, 7, 9)) * 4000).astype(np.float32)
+    p16, p32 = tmp_path / "a16.tif", tmp_path / "a32.tif"
+    libapi.writetifstack(p16, vol, 16)
+    libapi.writetifstack(p32, vol, 32)
+    assert libapi.gettifinfo(p16) == (16, (9, 7, 5))
+    assert libapi.gettifinfo(p32) == (32, (9, 7, 5))
+    assert np.array_equal(libapi.readtifstack(p32), vol)                      # float32: bit exact
+    assert np.array_equal(libapi.readtifstack(p16), np.trunc(vol))            # (uint16) truncation
+
+
+def test_uint16_conversion_truncates_and_wraps_like_x86(tmp_path):
+    vol = np.array([[[0.9, 1.5, 65535.7, 65536.0, 70000.2, -1.5, -0.4]]], np.float32)
+    p = tmp_path / "w.tif"
+    libapi.writetifstack(p, vol, 16)
+    got = libapi.readtifstack(p)
+    assert got.ravel().tolist() == [0, 1, 65535, 0, 4464, 65535, 0]
+
+
+def test_pillow_reads_what_we_write_and_vice_versa(tmp_path):
+    Image = pytest.importorskip("PIL.Image")
+    rng = np.random.default_rng(1)
+    vol = (rng.random((4, 6, 8)) * 1000).astype(np.float32)
+    p = tmp_path / "ours.tif"
+    libapi.writetifstack(p, vol, 16)
+    im = Image.open(p)
+    assert getattr(im, "n_frames", 1) == 4
+    for k in range(4):
+        im.seek(k)
+        assert np.array_equal(np.array(im), np.trunc(vol[k]).astype(np.uint16))
+    p = tmp_path / "ours32.tif"
+    libapi.writetifstack(p, vol, 32)
+    im = Image.open(p)
+    im.seek(2)
+    assert np.array_equal(np.array(im), vol[2])
+    # a stack written by libtiff (through Pillow), uncompressed, possibly several strips per page
+    pages = [Image.fromarray((vol[k]).astype(np.uint16)) for k in range(4)]
+    q = tmp_path / "theirs.tif"
+    pages[0].save(q, save_all=True, append_images=pages[1:], compression=None)
+    assert libapi.gettifinfo(q) == (16, (8, 6, 4))
+    assert np.array_equal(libapi.readtifstack(q), vol.astype(np.uint16).astype(np.float32))
