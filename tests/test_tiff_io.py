@@ -26,6 +26,20 @@ def test_uint16_conversion_truncates_and_wraps_like_x86(tmp_path):
     assert got.ravel().tolist() == [0, 1, 65535, 0, 4464, 65535, 0]
 
 
+def _as_contig_planar(path, out):
+    """Pillow cannot decode PLANARCONFIG_SEPARATE (which the reference sets, src/apifunc.cpp:266, and
+    which is meaningless for one sample per pixel); flip tag 284 to CONTIG in a copy for the pixel check."""
+    import struct
+    b = bytearray(open(path, "rb").read())
+    key = struct.pack("<HHI", 284, 3, 1)
+    i = b.find(key)
+    while i >= 0:
+        b[i + 8:i + 10] = struct.pack("<H", 1)
+        i = b.find(key, i + 12)
+    open(out, "wb").write(b)
+    return out
+
+
 def test_pillow_reads_what_we_write_and_vice_versa(tmp_path):
     Image = pytest.importorskip("PIL.Image")
     rng = np.random.default_rng(1)
@@ -33,13 +47,19 @@ def test_pillow_reads_what_we_write_and_vice_versa(tmp_path):
     p = tmp_path / "ours.tif"
     libapi.writetifstack(p, vol, 16)
     im = Image.open(p)
-    assert getattr(im, "n_frames", 1) == 4
+    assert getattr(im, "n_frames", 1) == 4 and im.mode == "I;16"
+    tags = dict(im.tag_v2)
+    # the reference's tag set, src/apifunc.cpp:260-271
+    assert tags[256] == 8 and tags[257] == 6 and tags[258] == (16,) and tags[259] == 1 and tags[262] == 1
+    assert tags[274] == 1 and tags[277] == 1 and tags[278] == 6 and tags[279] == (96,) and tags[284] == 2
+    im = Image.open(_as_contig_planar(p, tmp_path / "ours_c.tif"))
     for k in range(4):
         im.seek(k)
         assert np.array_equal(np.array(im), np.trunc(vol[k]).astype(np.uint16))
     p = tmp_path / "ours32.tif"
     libapi.writetifstack(p, vol, 32)
-    im = Image.open(p)
+    assert dict(Image.open(p).tag_v2)[339] in (3, (3,))          # SAMPLEFORMAT_IEEEFP
+    im = Image.open(_as_contig_planar(p, tmp_path / "ours32_c.tif"))
     im.seek(2)
     assert np.array_equal(np.array(im), vol[2])
     # a stack written by libtiff (through Pillow), uncompressed, possibly several strips per page
