@@ -413,3 +413,62 @@ extern "C" int milb_debug_tex3d_warp(float *h_out, const float *h_src, const uns
 	cudaFreeArray(arr);
 	return MILB_OK;
 }
+
+// Test utility: sample a volume at explicit texture coordinates, through the hardware texture unit
+// (use_hw != 0) or through the software restatement used by the product kernels.
+__global__ void k_debug_sample_hw(float *__restrict__ out, cudaTextureObject_t tex, const float *__restrict__ c, int n)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = tex3D<float>(tex, c[3 * i], c[3 * i + 1], c[3 * i + 2]);
+}
+__global__ void k_debug_sample_sw(float *__restrict__ out, const float *__restrict__ src, int sx, int sy, int sz, const float *__restrict__ c, int n)
+{
+	const int i = blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) out[i] = tex3d_linear(src, sx, sy, sz, c[3 * i], c[3 * i + 1], c[3 * i + 2]);
+}
+
+extern "C" int milb_debug_tex3d_sample(float *h_out, const float *h_src, const unsigned int *size, const float *h_coords, int n, int use_hw)
+{
+	const int sx = size[0], sy = size[1], sz = size[2];
+	const long long nv = (long long)sx * sy * sz;
+	float *d_out = nullptr, *d_c = nullptr, *d_src = nullptr;
+	MILB_CUDA_TRY(cudaMalloc(&d_out, sizeof(float) * n));
+	MILB_CUDA_TRY(cudaMalloc(&d_c, sizeof(float) * 3 * n));
+	MILB_CUDA_TRY(cudaMemcpy(d_c, h_coords, sizeof(float) * 3 * n, cudaMemcpyHostToDevice));
+	if (use_hw) {
+		cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+		cudaArray_t arr = nullptr;
+		MILB_CUDA_TRY(cudaMalloc3DArray(&arr, &desc, make_cudaExtent(sx, sy, sz)));
+		cudaMemcpy3DParms cp = {0};
+		cp.srcPtr = make_cudaPitchedPtr((void *)h_src, sx * sizeof(float), sx, sy);
+		cp.dstArray = arr;
+		cp.extent = make_cudaExtent(sx, sy, sz);
+		cp.kind = cudaMemcpyHostToDevice;
+		MILB_CUDA_TRY(cudaMemcpy3D(&cp));
+		cudaResourceDesc rd;
+		memset(&rd, 0, sizeof rd);
+		rd.resType = cudaResourceTypeArray;
+		rd.res.array.array = arr;
+		cudaTextureDesc td;
+		memset(&td, 0, sizeof td);
+		td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+		td.filterMode = cudaFilterModeLinear;
+		td.readMode = cudaReadModeElementType;
+		cudaTextureObject_t tex = 0;
+		MILB_CUDA_TRY(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+		k_debug_sample_hw<<<(n + 255) / 256, 256>>>(d_out, tex, d_c, n);
+		MILB_CUDA_TRY(cudaDeviceSynchronize());
+		cudaDestroyTextureObject(tex);
+		cudaFreeArray(arr);
+	} else {
+		MILB_CUDA_TRY(cudaMalloc(&d_src, sizeof(float) * nv));
+		MILB_CUDA_TRY(cudaMemcpy(d_src, h_src, sizeof(float) * nv, cudaMemcpyHostToDevice));
+		k_debug_sample_sw<<<(n + 255) / 256, 256>>>(d_out, d_src, sx, sy, sz, d_c, n);
+		MILB_CUDA_TRY(cudaDeviceSynchronize());
+		cudaFree(d_src);
+	}
+	MILB_CUDA_TRY(cudaMemcpy(h_out, d_out, sizeof(float) * n, cudaMemcpyDeviceToHost));
+	cudaFree(d_out);
+	cudaFree(d_c);
+	return MILB_OK;
+}

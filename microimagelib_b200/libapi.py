@@ -36,11 +36,12 @@ def snap_transform_size(n: int) -> int:
 
 
 def decon_singleview(img, psf, itNumForDecon, initialFlag=False, deviceNum=0, gpuMemMode=1, verbose=False,
-                     flagUnmatch=False, psf_bp=None):
-    """decon_singleview (include/libapi.h:42-43).  Returns (h_decon, status, deconRecords)."""
+                     flagUnmatch=False, psf_bp=None, out=None):
+    """decon_singleview (include/libapi.h:42-43).  Returns (h_decon, status, deconRecords).
+    `out` may be a caller-owned float32 buffer (e.g. pinned memory), as in the C API."""
     lib = _lib.load()
     img, psf = _f32(img), _f32(psf)
-    out = np.empty_like(img)
+    out = np.empty_like(img) if out is None else out
     rec = np.zeros(10, np.float32)
     bp = _f32(psf_bp) if psf_bp is not None else psf
     st = lib.decon_singleview(_fp(out), _fp(img), _size(img.shape), _fp(psf), _size(psf.shape), bool(initialFlag),
