@@ -260,26 +260,13 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "launch": "one single-view RL iteration (8 plane-stage launches x chunks + 2 X-pass launches)",
+                "peak_source": peak_src, "launch": "one single-view RL iteration = 6 plane-pass launches + 2 fused X-pass launches",
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_VOXEL_ITER * n_fft, "ms_per_launch": ms_iter}
     yard = None
     if world == 1 and not args.no_yardstick:
         try:
-            d.run_cufft_yardstick(2, stream=stream)
-            torch.cuda.synchronize()
-            y0, y1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             yi = max(5, args.iters // 5)
-            y0.record(stream)
-            d.run_cufft_yardstick(yi, stream=stream)
-            y1.record(stream)
-            torch.cuda.synchronize()
-            # includes the yardstick's own OTF preparation (4 transforms) -> subtract a 0-iteration run
-            z0, z1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            z0.record(stream)
-            d.run_cufft_yardstick(0, stream=stream)
-            z1.record(stream)
-            torch.cuda.synchronize()
-            yms = (y0.elapsed_time(y1) - z0.elapsed_time(z1)) / yi
+            yms = d.run_cufft_yardstick(yi, stream=stream) / yi     # CUDA events around the loop only
             yard = {"what": "cuFFT R2C/C2R + unfused element-wise kernels (the reference's launch structure)", "ms_per_iteration": yms,
                     "voxel_iters_per_s": n_fft / (yms * 1e-3), "speedup_vs_yardstick": yms / ms_iter}
         except Exception as e:  # the yardstick is informative only

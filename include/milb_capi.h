@@ -64,7 +64,8 @@ int milb_decon_set_chunk_planes(milb_decon_t *h, int planes);
 
 /* yardstick: the same loop through cuFFT + unfused element-wise kernels, i.e. the reference's own
  * launch structure (src/api_subfunc.cu:3404-3416) on this GPU.  Used by bench.py only. */
-int milb_decon_run_cufft_yardstick(milb_decon_t *h, int iterations, int const_init, void *stream);
+int milb_decon_run_cufft_yardstick(milb_decon_t *h, int iterations, int const_init, void *stream,
+	float *loop_ms /* out: CUDA-event time of the iteration loop only */);
 
 /* Registration ----------------------------------------------------------------------------------
  * A handle owns the mean-removed target and source volumes of one reg3d_affine1 call

@@ -11,6 +11,7 @@
 #include "fft_kernels.cuh"
 #include "fft_plan.h"
 #include "decon_internal.h"
+#include "decon_fast.h"
 #include "launch_count.h"
 
 // ------------------------------------------------------------------------------------------------
@@ -241,7 +242,22 @@ int milb_decon_create(milb_decon_t **out, int nviews, const unsigned int *imSize
 		milb_decon_destroy(h);
 		return rc;
 	}
+	{
+		const char *env = getenv("MILB_FORCE_GENERIC");
+		const FastAxisOps *fx = milb_fast_ops(h->X), *fy = milb_fast_ops(h->Y), *fz = milb_fast_ops(h->Z);
+		h->fast = fx && fy && fz && !(env && env[0] == '1');
+		if (h->fast && (fx->setup() || fy->setup() || fz->setup())) h->fast = false;
+		if (h->fast) {
+			// planes of the half spectrum per launch of the plane passes; 0 = all planes at once.
+			// (Chunks small enough to stay L2-resident between the three passes were measured
+			// slower than whole-volume launches on B200 -- see DESIGN.md -- so 0 is the default.)
+			const char *ce = getenv("MILB_CHUNK_PLANES");
+			const long long c = ce ? atoll(ce) : 0;
+			h->chunk_planes = (int)(c < 0 ? 0 : c);
+		}
+	}
 	cudaError_t e = cudaSuccess;
+	if (h->fast) e = cudaMalloc(&h->S2, sizeof(float2) * h->nspec);
 	for (int v = 0; v < nviews && e == cudaSuccess; v++) {
 		e = cudaMalloc(&h->A[v], sizeof(float) * h->nreal);
 		if (e == cudaSuccess) e = cudaMalloc(&h->otf[v], sizeof(float2) * h->nspec);
@@ -271,6 +287,7 @@ void milb_decon_destroy(milb_decon_t *h)
 	if (h->E) cudaFree(h->E);
 	if (h->stage) cudaFree(h->stage);
 	if (h->S) cudaFree(h->S);
+	if (h->S2) cudaFree(h->S2);
 	if (h->d_sums) cudaFree(h->d_sums);
 	free_axis_plan(h->px);
 	free_axis_plan(h->py);
@@ -301,6 +318,12 @@ template <int MODE>
 static void launch_xpass(milb_decon *h, float *vol_io, const float *aux, cudaStream_t st)
 {
 	const long long M = (long long)h->Y * h->Z / 2;
+	if (h->fast) {
+		static_assert(X_FWD_REAL == 0 && X_RATIO == 1 && X_UPDATE == 2 && X_UPDATE_LAST == 3, "mode numbering shared with fft_fast.cuh");
+		milb_fast_ops(h->X)->xpass(MODE, (float2 *)vol_io, (const float2 *)aux, (float4 *)h->S, h->px.d_tw, M, st);
+		milb_count_launches(1);
+		return;
+	}
 	k_xpass<MODE><<<(unsigned)(M / h->Lx), kThreads, h->smx, st>>>(h->px.dev, M, h->Lx, (float2 *)vol_io, (const float2 *)aux,
 		(float4 *)h->S, 1.0f);
 	milb_count_launches(1);
@@ -312,6 +335,23 @@ static void plane_stage(milb_decon *h, const float2 *otf, float scale, cudaStrea
 {
 	const int planes = h->X / 2 + 1;
 	int chunk = h->chunk_planes > 0 ? h->chunk_planes : planes;
+	if (h->fast) {
+		// S [y][z] -Y fwd-> S2 [z][ky'] -Z fwd * otf Z inv-> S [ky'][z] -Y inv-> S [y][z], chunk by chunk in L2
+		const FastAxisOps *oy = milb_fast_ops(h->Y), *oz = milb_fast_ops(h->Z);
+		for (int p0 = 0; p0 < planes; p0 += chunk) {
+			const int np = (p0 + chunk <= planes) ? chunk : planes - p0;
+			oy->passT(h->S, h->S2, h->py.d_tw, h->Z, p0, np, st);
+			if (otf) {
+				oz->convT(h->S2, h->S, otf, h->pz.d_tw, h->Y, p0, np, st);
+				oy->pass_inv(h->S, h->py.d_tw, h->Z, p0, np, st);
+				milb_count_launches(3);
+			} else {
+				oz->fwd_scaled(h->S2, h->pz.d_tw, h->Y, p0, np, scale, st); // spectrum stays in S2
+				milb_count_launches(2);
+			}
+		}
+		return;
+	}
 	for (int p0 = 0; p0 < planes; p0 += chunk) {
 		const int np = (p0 + chunk <= planes) ? chunk : planes - p0;
 		dim3 gy(h->Z / h->Ly, np);
@@ -351,7 +391,7 @@ static int gen_otf(milb_decon *h, float2 *dst, const float *d_psf, int px, int p
 	milb_count_launches(1);
 	launch_xpass<X_FWD_REAL>(h, h->E, nullptr, st);
 	plane_stage(h, nullptr, (float)(1.0 / (double)h->nreal), st);
-	MILB_CUDA_TRY(cudaMemcpyAsync(dst, h->S, sizeof(float2) * h->nspec, cudaMemcpyDeviceToDevice, st));
+	MILB_CUDA_TRY(cudaMemcpyAsync(dst, h->fast ? h->S2 : h->S, sizeof(float2) * h->nspec, cudaMemcpyDeviceToDevice, st));
 	MILB_CUDA_TRY(cudaGetLastError());
 	return MILB_OK;
 }

@@ -1,0 +1,20 @@
+// Dispatch table of the power-of-two fast kernels.
+#include "decon_fast.h"
+
+const FastAxisOps *milb_fast_ops_64();
+const FastAxisOps *milb_fast_ops_128();
+const FastAxisOps *milb_fast_ops_256();
+const FastAxisOps *milb_fast_ops_512();
+const FastAxisOps *milb_fast_ops_1024();
+
+const FastAxisOps *milb_fast_ops(int n)
+{
+	switch (n) {
+	case 64: return milb_fast_ops_64();
+	case 128: return milb_fast_ops_128();
+	case 256: return milb_fast_ops_256();
+	case 512: return milb_fast_ops_512();
+	case 1024: return milb_fast_ops_1024();
+	default: return nullptr;
+	}
+}

@@ -1,0 +1,82 @@
+// Instantiates the fast kernels for one length MILB_FAST_N and registers their launchers.
+#include "common.h"
+#include "decon_fast.h"
+#include "fft_fast.cuh"
+
+namespace {
+constexpr int N = MILB_FAST_N;
+constexpr int T = 512;
+constexpr int L = 4096 / N;
+constexpr size_t SM1 = (size_t)(N * L + N) * sizeof(float2);                                  // X pass: one tile
+constexpr size_t SMP2 = (size_t)(2 * TileGeom<N, L>::elems + N) * sizeof(float2);           // plane pass: 2 landing buffers
+constexpr size_t SMP3 = (size_t)(3 * TileGeom<N, L>::elems + N) * sizeof(float2);           // + transposition / OTF buffer
+int g_ctas = 0; // persistent grid: 2 CTAs per SM
+
+template <typename K> int optin(K k, size_t bytes)
+{
+	return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess ? 0 : 1;
+}
+
+int setup()
+{
+	int bad = 0;
+	bad |= optin(k_xpassF<N, L, T, XF_FWD_REAL>, SM1);
+	bad |= optin(k_xpassF<N, L, T, XF_RATIO>, SM1);
+	bad |= optin(k_xpassF<N, L, T, XF_UPDATE>, SM1);
+	bad |= optin(k_xpassF<N, L, T, XF_UPDATE_LAST>, SM1);
+	bad |= optin(k_ypassT<N, L, T>, SMP3);
+	bad |= optin(k_ypassF<N, L, T, true>, SMP2);
+	bad |= optin(k_zconvT<N, L, T, true>, SMP3);
+	bad |= optin(k_zconvT<N, L, T, false>, SMP3);
+	int dev = 0, sms = 148;
+	cudaGetDevice(&dev);
+	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	g_ctas = 2 * sms;
+	return bad;
+}
+
+void xpass(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const float2 *tw, long long M, cudaStream_t st)
+{
+	const unsigned grid = (unsigned)(M / L);
+	switch (mode) {
+	case XF_FWD_REAL: k_xpassF<N, L, T, XF_FWD_REAL><<<grid, T, SM1, st>>>(vol_io, aux, spec, tw, M); break;
+	case XF_RATIO: k_xpassF<N, L, T, XF_RATIO><<<grid, T, SM1, st>>>(vol_io, aux, spec, tw, M); break;
+	case XF_UPDATE: k_xpassF<N, L, T, XF_UPDATE><<<grid, T, SM1, st>>>(vol_io, aux, spec, tw, M); break;
+	default: k_xpassF<N, L, T, XF_UPDATE_LAST><<<grid, T, SM1, st>>>(vol_io, aux, spec, tw, M); break;
+	}
+}
+
+void passT(const float2 *in, float2 *out, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
+{
+	const int tiles = (cols / L) * nplanes;
+	k_ypassT<N, L, T><<<tiles < g_ctas ? tiles : g_ctas, T, SMP3, st>>>(in, out, tw, cols, plane0, nplanes);
+}
+
+void pass_inv(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
+{
+	const int tiles = (cols / L) * nplanes;
+	k_ypassF<N, L, T, true><<<tiles < g_ctas ? tiles : g_ctas, T, SMP2, st>>>(spec, tw, cols, plane0, nplanes);
+}
+
+void convT(float2 *in, float2 *out, const float2 *otf, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
+{
+	const int tiles = (cols / L) * nplanes;
+	k_zconvT<N, L, T, true><<<tiles < g_ctas ? tiles : g_ctas, T, SMP3, st>>>(in, out, otf, tw, cols, plane0, nplanes, 1.0f);
+}
+
+void fwd_scaled(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, float scale, cudaStream_t st)
+{
+	const int tiles = (cols / L) * nplanes;
+	k_zconvT<N, L, T, false><<<tiles < g_ctas ? tiles : g_ctas, T, SMP3, st>>>(spec, nullptr, nullptr, tw, cols, plane0, nplanes, scale);
+}
+} // namespace
+
+#define MILB_CAT2(a, b) a##b
+#define MILB_CAT(a, b) MILB_CAT2(a, b)
+const FastAxisOps *MILB_CAT(milb_fast_ops_, MILB_FAST_N)()
+{
+	static FastAxisOps ops;
+	ops.n = N; ops.lanes = L; ops.setup = setup; ops.xpass = xpass; ops.passT = passT; ops.pass_inv = pass_inv;
+	ops.convT = convT; ops.fwd_scaled = fwd_scaled;
+	return &ops;
+}

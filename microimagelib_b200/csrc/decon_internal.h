@@ -27,6 +27,7 @@ struct milb_decon {
 	float *E = nullptr;
 	float *stage = nullptr;        // staging for host uploads / crop output (nreal floats)
 	float2 *S = nullptr;
+	float2 *S2 = nullptr;          // fast path: transposed planes [kx][z][ky']
 	float2 *otf[2] = {nullptr, nullptr}, *otf_bp[2] = {nullptr, nullptr};
 	double *d_sums = nullptr;      // [0..1] sums, [2..] reduction scratch
 	bool have_psf[2] = {false, false}, have_img[2] = {false, false};

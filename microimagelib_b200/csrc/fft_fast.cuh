@@ -1,0 +1,491 @@
+// Power-of-two fast path of the pencil FFT passes (N in {64,128,256,512,1024} per axis).
+//
+// Same algorithm and the same position-order spectrum as the generic engine (fft_core.h), but
+// with compile-time lengths and radices: every butterfly lives in registers, the first stage
+// of a pass reads global memory directly and the last one writes it directly, stages exchange
+// through one shared-memory tile, and all three passes are "column" passes whose lanes run
+// along the contiguous axis, so twiddles depend only on the butterfly row.
+//
+// Data flow of one convolution  S <- F^-1( F(S) * OTF )  on the kx-planes (Y x Z complex each):
+//   k_ypassT  : S [y][z]   --Y forward-->  S2 [z][ky']     (transposed through shared memory)
+//   k_zconvT  : S2 [z][ky'] --Z forward, * OTF, Z inverse--> S [ky'][z]   (transposed back)
+//   k_ypass<INV>: S [ky'][z] --Y inverse--> S [y][z]        (in place)
+// so no pass ever transforms along the contiguous axis, and the OTF (kept in the [z'][ky'] layout
+// the data has at the multiply) is read with fully coalesced loads.
+//   k_xpassF  : the fused X pencils: C2R inverse -> ratio | update+clamp -> R2C forward.
+// Run plane-chunk by plane-chunk the three plane passes keep their intermediates in the 126 MB L2.
+#pragma once
+#include "fft_core.h"
+
+#define SMALLVALUE_FAST 0.01f // src/api_subfunc.cu:24
+
+template <int N> struct FastPlan;
+#define MILB_FAST_PLAN(N_, S_, A, B, C, D)                    \
+	template <> struct FastPlan<N_> {                         \
+		static constexpr int S = S_;                          \
+		static constexpr int r0 = A, r1 = B, r2 = C, r3 = D;  \
+	};
+MILB_FAST_PLAN(64, 2, 8, 8, 1, 1)
+MILB_FAST_PLAN(128, 3, 8, 4, 4, 1)
+MILB_FAST_PLAN(256, 3, 8, 8, 4, 1)
+MILB_FAST_PLAN(512, 3, 8, 8, 8, 1)
+MILB_FAST_PLAN(1024, 4, 8, 8, 4, 4)
+
+// position of frequency k after the forward stages (same rule as AxisPlanTables::pos)
+template <int N> __device__ __forceinline__ int fast_pos(int k)
+{
+	using P = FastPlan<N>;
+	const int d0 = k % P::r0;
+	k /= P::r0;
+	const int d1 = k % P::r1;
+	k /= P::r1;
+	const int d2 = k % P::r2;
+	const int d3 = k / P::r2;
+	return d0 * (N / P::r0) + d1 * (N / (P::r0 * P::r1)) + d2 * (N / (P::r0 * P::r1 * P::r2)) + d3;
+}
+
+template <int R, bool INV> __device__ __forceinline__ void fbfly(float2 (&v)[R])
+{
+	if (R == 2) bfly2<INV>(v[0], v[1]);
+	else if (R == 4) bfly4<INV>(v[0], v[1], v[2], v[3]);
+	else bfly8<INV>(v);
+}
+
+// One stage of radix R on sub-transforms of length NS for the whole tile (N rows x L lanes),
+// T threads.  ld(row, lane) / st(row, lane, v) abstract where the rows live (global or shared).
+template <int N, int L, int T, int R, int NS, bool INV, class LD, class ST>
+__device__ __forceinline__ void fstage(const float2 *__restrict__ tw, LD ld, ST st)
+{
+	constexpr int M = NS / R;
+	constexpr int NB = (N / R) * L;
+	constexpr int IT = (NB + T - 1) / T;
+#pragma unroll
+	for (int it = 0; it < IT; it++) {
+		const int bl = threadIdx.x + it * T;
+		if ((NB % T) != 0 && bl >= NB) break;
+		const int lane = bl % L, b = bl / L;
+		const int blk = b / M, q = b % M;
+		const int base = blk * NS + q;
+		float2 v[R];
+#pragma unroll
+		for (int j = 0; j < R; j++) v[j] = ld(base + j * M, lane);
+		if (INV && M > 1) {
+#pragma unroll
+			for (int j = 1; j < R; j++) v[j] = cmulc(v[j], tw[q * (N / NS) * j]);
+		}
+		fbfly<R, INV>(v);
+		if (!INV && M > 1) {
+#pragma unroll
+			for (int j = 1; j < R; j++) v[j] = cmul(v[j], tw[q * (N / NS) * j]);
+		}
+#pragma unroll
+		for (int j = 0; j < R; j++) st(base + j * M, lane, v[j]);
+	}
+}
+
+// forward: stage 0 reads through ld0, the last stage writes through stl, the rest is in `tile`
+template <int N, int L, int T, class LD, class ST>
+__device__ __forceinline__ void fwd_stages(float2 *tile, const float2 *tw, LD ld0, ST stl)
+{
+	using P = FastPlan<N>;
+	auto sl = [tile](int r, int l) { return tile[r * L + l]; };
+	auto ss = [tile](int r, int l, float2 v) { tile[r * L + l] = v; };
+	constexpr int ns1 = N / P::r0, ns2 = ns1 / P::r1, ns3 = ns2 / P::r2;
+	fstage<N, L, T, P::r0, N, false>(tw, ld0, ss);
+	__syncthreads();
+	if (P::S == 2) {
+		fstage<N, L, T, P::r1, ns1, false>(tw, sl, stl);
+	} else if (P::S == 3) {
+		fstage<N, L, T, P::r1, ns1, false>(tw, sl, ss);
+		__syncthreads();
+		fstage<N, L, T, P::r2, ns2, false>(tw, sl, stl);
+	} else {
+		fstage<N, L, T, P::r1, ns1, false>(tw, sl, ss);
+		__syncthreads();
+		fstage<N, L, T, P::r2, ns2, false>(tw, sl, ss);
+		__syncthreads();
+		fstage<N, L, T, P::r3, ns3, false>(tw, sl, stl);
+	}
+}
+
+// forward stages 1..S-1 only, all in `tile` (stage 0 was done by the caller)
+template <int N, int L, int T> __device__ __forceinline__ void fwd_tail_smem(float2 *tile, const float2 *tw)
+{
+	using P = FastPlan<N>;
+	auto sl = [tile](int r, int l) { return tile[r * L + l]; };
+	auto ss = [tile](int r, int l, float2 v) { tile[r * L + l] = v; };
+	constexpr int ns1 = N / P::r0, ns2 = ns1 / P::r1, ns3 = ns2 / P::r2;
+	fstage<N, L, T, P::r1, ns1, false>(tw, sl, ss);
+	__syncthreads();
+	if (P::S >= 3) {
+		fstage<N, L, T, P::r2, ns2, false>(tw, sl, ss);
+		__syncthreads();
+	}
+	if (P::S >= 4) {
+		fstage<N, L, T, P::r3, ns3, false>(tw, sl, ss);
+		__syncthreads();
+	}
+}
+
+// inverse stages S-1..1, all in `tile` (stage 0 is done by the caller)
+template <int N, int L, int T> __device__ __forceinline__ void inv_head_smem(float2 *tile, const float2 *tw)
+{
+	using P = FastPlan<N>;
+	auto sl = [tile](int r, int l) { return tile[r * L + l]; };
+	auto ss = [tile](int r, int l, float2 v) { tile[r * L + l] = v; };
+	constexpr int ns1 = N / P::r0, ns2 = ns1 / P::r1, ns3 = ns2 / P::r2;
+	if (P::S >= 4) {
+		fstage<N, L, T, P::r3, ns3, true>(tw, sl, ss);
+		__syncthreads();
+	}
+	if (P::S >= 3) {
+		fstage<N, L, T, P::r2, ns2, true>(tw, sl, ss);
+		__syncthreads();
+	}
+	fstage<N, L, T, P::r1, ns1, true>(tw, sl, ss);
+	__syncthreads();
+}
+
+// inverse: the first stage (S-1) reads through ldf, stage 0 writes through st0
+template <int N, int L, int T, class LD, class ST>
+__device__ __forceinline__ void inv_stages(float2 *tile, const float2 *tw, LD ldf, ST st0)
+{
+	using P = FastPlan<N>;
+	auto sl = [tile](int r, int l) { return tile[r * L + l]; };
+	auto ss = [tile](int r, int l, float2 v) { tile[r * L + l] = v; };
+	constexpr int ns1 = N / P::r0, ns2 = ns1 / P::r1, ns3 = ns2 / P::r2;
+	if (P::S == 2) {
+		fstage<N, L, T, P::r1, ns1, true>(tw, ldf, ss);
+	} else if (P::S == 3) {
+		fstage<N, L, T, P::r2, ns2, true>(tw, ldf, ss);
+		__syncthreads();
+		fstage<N, L, T, P::r1, ns1, true>(tw, sl, ss);
+	} else {
+		fstage<N, L, T, P::r3, ns3, true>(tw, ldf, ss);
+		__syncthreads();
+		fstage<N, L, T, P::r2, ns2, true>(tw, sl, ss);
+		__syncthreads();
+		fstage<N, L, T, P::r1, ns1, true>(tw, sl, ss);
+	}
+	__syncthreads();
+	fstage<N, L, T, P::r0, N, true>(tw, sl, st0);
+}
+
+template <int N> __device__ __forceinline__ void load_tw(float2 *s_tw, const float2 *__restrict__ g_tw)
+{
+	for (int i = threadIdx.x; i < N; i += blockDim.x) s_tw[i] = g_tw[i];
+}
+
+// ---- persistent, double-buffered plane passes ----------------------------------------------------
+// A CTA walks tiles t = blockIdx.x, +gridDim.x, ...; while it transforms tile t out of one landing
+// buffer, cp.async (LDGSTS) is already filling the other with tile t + gridDim.x, so the global-load
+// latency is off the critical path and every SM always has loads in flight.
+//
+// Shared-memory rows are L pencils (L * 8 bytes) wide.  For L <= 8 a row is at most 64 B, and the
+// stride-1 butterflies of the last stage would put a warp's four rows on the same banks; rows are
+// therefore skewed by one row every eight (prow).
+template <int L> __device__ __forceinline__ int prow(int r) { return (L <= 8) ? r + (r >> 3) : r; }
+template <int N, int L> struct TileGeom {
+	static constexpr int rows = (L <= 8) ? N + N / 8 : N;
+	static constexpr int elems = rows * L;
+};
+
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
+{
+	const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+	asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K) : "memory"); }
+
+// N rows of L pencils (row pitch `pitch` float2 in global memory) -> skewed shared tile
+template <int N, int L, int T> __device__ __forceinline__ void tile_load_async(float2 *buf, const float2 *__restrict__ src, long long pitch)
+{
+	constexpr int CPR = L / 2, NC = N * CPR; // 16-byte chunks per row / per tile
+#pragma unroll 4
+	for (int c = threadIdx.x; c < NC; c += T) {
+		const int r = c / CPR, p = c % CPR;
+		cp_async16(buf + prow<L>(r) * L + 2 * p, src + (long long)r * pitch + 2 * p);
+	}
+}
+
+// swizzle of the transposition buffer (on top of the row skew): for a fixed lane, 16 consecutive
+// rows hit 16 distinct 8-byte bank pairs; for a fixed row the lanes are only permuted
+template <int L> __device__ __forceinline__ int swz(int row, int lane)
+{
+	const int f = (L >= 16) ? (row & 15) : (L == 8) ? ((row >> 1) & 7) : ((row >> 2) & 3);
+	return prow<L>(row) * L + (lane ^ f);
+}
+
+// coalesced transposed copy-out of a swizzled N x L tile: out[lane * out_pitch + row]
+template <int N, int L, int T> __device__ __forceinline__ void store_transposed(const float2 *tile2, float2 *__restrict__ out, long long out_pitch)
+{
+#pragma unroll 4
+	for (int idx = threadIdx.x; idx < N * L; idx += T) {
+		const int row = idx % N, lane = idx / N;
+		out[(long long)lane * out_pitch + row] = tile2[swz<L>(row, lane)];
+	}
+}
+
+// all-shared-memory stage helpers on a skewed tile
+template <int N, int L, int T, int R, int NS, bool INV, class ST>
+__device__ __forceinline__ void sstage_to(float2 *tile, const float2 *tw, ST st)
+{
+	fstage<N, L, T, R, NS, INV>(tw, [tile](int r, int l) { return tile[prow<L>(r) * L + l]; }, st);
+}
+template <int N, int L, int T, int R, int NS, bool INV> __device__ __forceinline__ void sstage(float2 *tile, const float2 *tw)
+{
+	sstage_to<N, L, T, R, NS, INV>(tile, tw, [tile](int r, int l, float2 v) { tile[prow<L>(r) * L + l] = v; });
+}
+
+// forward stages 0..S-2 in place in `tile` (each followed by a barrier); returns nothing
+template <int N, int L, int T> __device__ __forceinline__ void fwd_but_last(float2 *tile, const float2 *tw)
+{
+	using P = FastPlan<N>;
+	constexpr int ns1 = N / P::r0, ns2 = ns1 / P::r1;
+	sstage<N, L, T, P::r0, N, false>(tile, tw);
+	__syncthreads();
+	if (P::S >= 3) {
+		sstage<N, L, T, P::r1, ns1, false>(tile, tw);
+		__syncthreads();
+	}
+	if (P::S >= 4) {
+		sstage<N, L, T, P::r2, ns2, false>(tile, tw);
+		__syncthreads();
+	}
+}
+// last forward stage (stride-1 butterflies) out of `tile` through st
+template <int N, int L, int T, class ST> __device__ __forceinline__ void fwd_last(float2 *tile, const float2 *tw, ST st)
+{
+	using P = FastPlan<N>;
+	constexpr int ns1 = N / P::r0, ns2 = ns1 / P::r1, ns3 = ns2 / P::r2;
+	if (P::S == 2) sstage_to<N, L, T, P::r1, ns1, false>(tile, tw, st);
+	else if (P::S == 3) sstage_to<N, L, T, P::r2, ns2, false>(tile, tw, st);
+	else sstage_to<N, L, T, P::r3, ns3, false>(tile, tw, st);
+}
+// inverse stages S-1..1 in place in `tile`, each followed by a barrier
+template <int N, int L, int T, bool SKIP_FIRST> __device__ __forceinline__ void inv_but_last(float2 *tile, const float2 *tw)
+{
+	using P = FastPlan<N>;
+	constexpr int ns1 = N / P::r0, ns2 = ns1 / P::r1, ns3 = ns2 / P::r2;
+	// SKIP_FIRST: stage S-1 was already done by the caller (fused with the OTF product)
+	if (P::S >= 4) {
+		if (!SKIP_FIRST) { sstage<N, L, T, P::r3, ns3, true>(tile, tw); __syncthreads(); }
+		sstage<N, L, T, P::r2, ns2, true>(tile, tw);
+		__syncthreads();
+		sstage<N, L, T, P::r1, ns1, true>(tile, tw);
+		__syncthreads();
+	} else if (P::S == 3) {
+		if (!SKIP_FIRST) { sstage<N, L, T, P::r2, ns2, true>(tile, tw); __syncthreads(); }
+		sstage<N, L, T, P::r1, ns1, true>(tile, tw);
+		__syncthreads();
+	} else {
+		if (!SKIP_FIRST) { sstage<N, L, T, P::r1, ns1, true>(tile, tw); __syncthreads(); }
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Y forward, transposing:  in plane [N = Y rows][Z]  ->  out plane [Z rows][N = Y]
+template <int N, int L, int T>
+__global__ void __launch_bounds__(T, 2)
+k_ypassT(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes)
+{
+	using G = TileGeom<N, L>;
+	extern __shared__ float2 sm[];
+	float2 *tile2 = sm + 2 * G::elems, *tw = sm + 3 * G::elems;
+	load_tw<N>(tw, g_tw);
+	const int tpp = Z / L, ntiles = nplanes * tpp;
+	auto src_of = [&](int t) { return in + (long long)(t / tpp + plane0) * N * Z + (long long)(t % tpp) * L; };
+	int t = blockIdx.x, cur = 0;
+	if (t < ntiles) tile_load_async<N, L, T>(sm, src_of(t), Z);
+	cp_async_commit();
+	for (; t < ntiles; t += gridDim.x, cur ^= 1) {
+		cp_async_wait<0>();
+		__syncthreads();
+		const int tn = t + gridDim.x;
+		if (tn < ntiles) tile_load_async<N, L, T>(sm + (cur ^ 1) * G::elems, src_of(tn), Z);
+		cp_async_commit();
+		float2 *tile = sm + cur * G::elems;
+		fwd_but_last<N, L, T>(tile, tw);
+		fwd_last<N, L, T>(tile, tw, [tile2](int r, int l, float2 v) { tile2[swz<L>(r, l)] = v; });
+		__syncthreads();
+		store_transposed<N, L, T>(tile2, out + (long long)(t / tpp + plane0) * N * Z + (long long)(t % tpp) * L * N, N);
+	}
+}
+
+// Y pass, in place, plain: plane [N rows][Z], lanes along z
+template <int N, int L, int T, bool INV>
+__global__ void __launch_bounds__(T, 2)
+k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes)
+{
+	using P = FastPlan<N>;
+	using G = TileGeom<N, L>;
+	extern __shared__ float2 sm[];
+	float2 *tw = sm + 2 * G::elems;
+	load_tw<N>(tw, g_tw);
+	const int tpp = Z / L, ntiles = nplanes * tpp;
+	auto ptr_of = [&](int t) { return spec + (long long)(t / tpp + plane0) * N * Z + (long long)(t % tpp) * L; };
+	int t = blockIdx.x, cur = 0;
+	if (t < ntiles) tile_load_async<N, L, T>(sm, ptr_of(t), Z);
+	cp_async_commit();
+	for (; t < ntiles; t += gridDim.x, cur ^= 1) {
+		cp_async_wait<0>();
+		__syncthreads();
+		const int tn = t + gridDim.x;
+		if (tn < ntiles) tile_load_async<N, L, T>(sm + (cur ^ 1) * G::elems, ptr_of(tn), Z);
+		cp_async_commit();
+		float2 *tile = sm + cur * G::elems;
+		float2 *p = ptr_of(t);
+		auto gs = [p, Z](int r, int l, float2 v) { p[(long long)r * Z + l] = v; };
+		if (INV) {
+			inv_but_last<N, L, T, false>(tile, tw);
+			sstage_to<N, L, T, P::r0, N, true>(tile, tw, gs);
+		} else {
+			fwd_but_last<N, L, T>(tile, tw);
+			fwd_last<N, L, T>(tile, tw, gs);
+		}
+	}
+}
+
+// Z pass on the transposed planes: in [N = Z rows][Yc], lanes along ky'.
+//   CONV : forward, * otf (same layout as `in`), inverse, transposed out [Yc rows][N = Z]
+//   !CONV: forward only, in place, scaled (OTF generation)
+template <int N, int L, int T, bool CONV>
+__global__ void __launch_bounds__(T, 2)
+k_zconvT(float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ otf, const float2 *__restrict__ g_tw, int Yc,
+	int plane0, int nplanes, float scale)
+{
+	using P = FastPlan<N>;
+	using G = TileGeom<N, L>;
+	extern __shared__ float2 sm[];
+	float2 *tile2 = sm + 2 * G::elems, *tw = sm + 3 * G::elems; // tile2 doubles as the OTF landing buffer
+	load_tw<N>(tw, g_tw);
+	const int tpp = Yc / L, ntiles = nplanes * tpp;
+	auto off_of = [&](int t) { return (long long)(t / tpp + plane0) * N * Yc + (long long)(t % tpp) * L; };
+	int t = blockIdx.x, cur = 0;
+	if (t < ntiles) tile_load_async<N, L, T>(sm, in + off_of(t), Yc);
+	cp_async_commit();
+	for (; t < ntiles; t += gridDim.x, cur ^= 1) {
+		cp_async_wait<0>();
+		__syncthreads();
+		if (CONV) tile_load_async<N, L, T>(tile2, otf + off_of(t), Yc);
+		cp_async_commit();
+		const int tn = t + gridDim.x;
+		if (tn < ntiles) tile_load_async<N, L, T>(sm + (cur ^ 1) * G::elems, in + off_of(tn), Yc);
+		cp_async_commit();
+		float2 *tile = sm + cur * G::elems;
+		fwd_but_last<N, L, T>(tile, tw);
+		if (!CONV) {
+			float2 *p = in + off_of(t);
+			fwd_last<N, L, T>(tile, tw, [p, Yc, scale](int r, int l, float2 v) { p[(long long)r * Yc + l] = make_float2(v.x * scale, v.y * scale); });
+			continue;
+		}
+		cp_async_wait<1>(); // the OTF tile (older group) has landed; the next data tile may still fly
+		__syncthreads();
+		{ // last forward stage, OTF product and first inverse stage share one register butterfly
+			constexpr int R = (P::S == 2) ? P::r1 : (P::S == 3) ? P::r2 : P::r3;
+			constexpr int NB = (N / R) * L, IT = (NB + T - 1) / T;
+#pragma unroll
+			for (int it = 0; it < IT; it++) {
+				const int bl = threadIdx.x + it * T;
+				if ((NB % T) != 0 && bl >= NB) break;
+				const int lane = bl % L, base = (bl / L) * R;
+				float2 v[R];
+#pragma unroll
+				for (int j = 0; j < R; j++) v[j] = tile[prow<L>(base + j) * L + lane];
+				fbfly<R, false>(v);
+#pragma unroll
+				for (int j = 0; j < R; j++) v[j] = cmul(v[j], tile2[prow<L>(base + j) * L + lane]); // multicomplex3Dkernel
+				fbfly<R, true>(v);
+#pragma unroll
+				for (int j = 0; j < R; j++) tile[prow<L>(base + j) * L + lane] = v[j];
+			}
+			__syncthreads();
+		}
+		inv_but_last<N, L, T, true>(tile, tw);
+		sstage_to<N, L, T, P::r0, N, true>(tile, tw, [tile2](int r, int l, float2 v) { tile2[swz<L>(r, l)] = v; });
+		__syncthreads();
+		store_transposed<N, L, T>(tile2, out + (long long)(t / tpp + plane0) * N * Yc + (long long)(t % tpp) * L * N, N);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused X pencils (see fft_kernels.cuh k_xpass for the mode semantics).
+enum { XF_FWD_REAL = 0, XF_RATIO = 1, XF_UPDATE = 2, XF_UPDATE_LAST = 3 };
+
+template <int N, int L, int T, int MODE>
+__global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
+k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M)
+{
+	using P = FastPlan<N>;
+	static_assert(P::r0 == 8 && (N / 8) * L == T, "stage 0 must be one radix-8 butterfly per thread");
+	extern __shared__ float2 sm[];
+	float2 *tile = sm, *tw = sm + N * L;
+	load_tw<N>(tw, g_tw);
+	__syncthreads();
+	const long long col0 = (long long)blockIdx.x * L;
+	constexpr int half = N / 2;
+	constexpr int M0 = N / 8;
+	const int lane = threadIdx.x % L, q = threadIdx.x / L;
+	float2 v[8];
+
+	if (MODE != XF_FWD_REAL) {
+		// half spectrum -> packed complex pencil in position order
+		for (int idx = threadIdx.x; idx < (half + 1) * L; idx += T) {
+			const int k = idx / L, l = idx % L;
+			float4 ab = spec[(long long)k * M + col0 + l];
+			const bool self = (k == 0) || (k == half);
+			if (self) { ab.y = 0.f; ab.w = 0.f; }
+			float2 ck, cn;
+			merge_pair(ab, ck, cn);
+			tile[fast_pos<N>(k) * L + l] = ck;
+			if (!self) tile[fast_pos<N>(N - k) * L + l] = cn;
+		}
+		__syncthreads();
+		inv_head_smem<N, L, T>(tile, tw);
+		// inverse stage 0 in registers -> natural-order samples x = q + j*M0
+#pragma unroll
+		for (int j = 0; j < 8; j++) v[j] = tile[(q + j * M0) * L + lane];
+#pragma unroll
+		for (int j = 1; j < 8; j++) v[j] = cmulc(v[j], tw[q * j]);
+		bfly8<true>(v);
+		if (MODE == XF_RATIO) {
+			float2 a[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++) a[j] = aux[(long long)(q + j * M0) * M + col0 + lane];
+#pragma unroll
+			for (int j = 0; j < 8; j++) { v[j].x = a[j].x / v[j].x; v[j].y = a[j].y / v[j].y; } // div3Dkernel
+		} else {
+			float2 e[8];
+#pragma unroll
+			for (int j = 0; j < 8; j++) e[j] = vol_io[(long long)(q + j * M0) * M + col0 + lane];
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				e[j].x *= v[j].x; e[j].y *= v[j].y;                                   // multi3Dkernel
+				e[j].x = (e[j].x > SMALLVALUE_FAST) ? e[j].x : SMALLVALUE_FAST;       // maxvalue3Dgpukernel
+				e[j].y = (e[j].y > SMALLVALUE_FAST) ? e[j].y : SMALLVALUE_FAST;
+				vol_io[(long long)(q + j * M0) * M + col0 + lane] = e[j];
+				v[j] = e[j];
+			}
+			if (MODE == XF_UPDATE_LAST) return;
+		}
+	} else {
+#pragma unroll
+		for (int j = 0; j < 8; j++) v[j] = vol_io[(long long)(q + j * M0) * M + col0 + lane];
+	}
+	// forward stage 0 in the same registers
+	bfly8<false>(v);
+#pragma unroll
+	for (int j = 1; j < 8; j++) v[j] = cmul(v[j], tw[q * j]);
+#pragma unroll
+	for (int j = 0; j < 8; j++) tile[(q + j * M0) * L + lane] = v[j];
+	__syncthreads();
+	fwd_tail_smem<N, L, T>(tile, tw);
+	// packed pencil -> two half spectra (even / odd z column of the pair)
+	for (int idx = threadIdx.x; idx < (half + 1) * L; idx += T) {
+		const int k = idx / L, l = idx % L;
+		const float2 ck = tile[fast_pos<N>(k) * L + l];
+		const float2 cn = tile[fast_pos<N>((N - k) % N) * L + l];
+		spec[(long long)k * M + col0 + l] = split_pair(ck, cn);
+	}
+}

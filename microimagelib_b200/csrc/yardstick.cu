@@ -53,7 +53,7 @@ int ygrid(long long n) { long long b = cdiv_ll(n, 256); return (int)(b > 148 * 1
 
 } // namespace
 
-extern "C" int milb_decon_run_cufft_yardstick(milb_decon_t *h, int iterations, int const_init, void *stream)
+extern "C" int milb_decon_run_cufft_yardstick(milb_decon_t *h, int iterations, int const_init, void *stream, float *loop_ms)
 {
 	if (!h || iterations < 0) return MILB_ERR_ARG;
 	for (int v = 0; v < h->nviews; v++)
@@ -93,7 +93,14 @@ extern "C" int milb_decon_run_cufft_yardstick(milb_decon_t *h, int iterations, i
 				if ((rc = milb_sum_f64_async(h->A[v], n, h->d_sums + 2, h->d_sums + v, st)) != MILB_OK) goto done;
 		}
 		const int g = ygrid(n), gs = ygrid(nsc);
+		// warm-up: cuFFT loads its kernels lazily on first execution of each plan
+		CUFFT_TRY(cufftExecR2C(fwd, T, Sp));
+		CUFFT_TRY(cufftExecC2R(inv, Sp, T));
+		cudaEvent_t e0, e1;
+		cudaEventCreate(&e0);
+		cudaEventCreate(&e1);
 		y_init<<<g, 256, 0, st>>>(h->E, h->A[0], h->A[1], h->d_sums, n, mode);
+		cudaEventRecord(e0, st);
 		for (int it = 0; it < iterations; it++)
 			for (int v = 0; v < nv; v++) {
 				CUFFT_TRY(cufftExecR2C(fwd, h->E, Sp));
@@ -106,6 +113,13 @@ extern "C" int milb_decon_run_cufft_yardstick(milb_decon_t *h, int iterations, i
 				y_mul<<<g, 256, 0, st>>>(h->E, T, n);
 				y_max<<<g, 256, 0, st>>>(h->E, SMALLVALUE_F, n);
 			}
+		cudaEventRecord(e1, st);
+		cudaEventSynchronize(e1);
+		float ms = 0;
+		cudaEventElapsedTime(&ms, e0, e1);
+		if (loop_ms) *loop_ms = ms;
+		cudaEventDestroy(e0);
+		cudaEventDestroy(e1);
 		if (cudaGetLastError() != cudaSuccess) rc = MILB_ERR_CUDA;
 	}
 done:

@@ -98,8 +98,10 @@ class Decon:
         _check(self.lib.milb_decon_run(self._h, int(iterations), 1 if const_init else 0, _stream(stream)), "milb_decon_run")
 
     def run_cufft_yardstick(self, iterations, const_init=False, stream=None):
-        _check(self.lib.milb_decon_run_cufft_yardstick(self._h, int(iterations), 1 if const_init else 0, _stream(stream)),
+        ms = C.c_float(0)
+        _check(self.lib.milb_decon_run_cufft_yardstick(self._h, int(iterations), 1 if const_init else 0, _stream(stream), C.byref(ms)),
                "milb_decon_run_cufft_yardstick")
+        return float(ms.value)
 
     def set_chunk_planes(self, planes):
         _check(self.lib.milb_decon_set_chunk_planes(self._h, int(planes)), "milb_decon_set_chunk_planes")
