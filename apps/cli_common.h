@@ -1,0 +1,92 @@
+// Shared helpers of the command-line apps: dash-flag lookup, .tmx matrix files, wall-clock timer.
+// The apps keep the reference's flags, defaults and output files (src/decon_sv.cpp, src/decon_dv.cpp,
+// src/reg3D.cpp, src/spim_fusion.cpp, src/spim_fusion_batch.cpp) and only call include/libapi.h.
+#pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../include/libapi.h"
+
+struct Args {
+	int argc;
+	char **argv;
+	bool has(const char *flag) const
+	{
+		for (int i = 1; i < argc; i++)
+			if (!strcmp(argv[i], flag)) return true;
+		return false;
+	}
+	// value following the LAST occurrence of `flag` (later flags override, as in a left-to-right scan)
+	const char *value(const char *flag) const
+	{
+		const char *v = nullptr;
+		for (int i = 1; i + 1 < argc; i++)
+			if (!strcmp(argv[i], flag)) v = argv[i + 1];
+		return v;
+	}
+	std::string str(const char *flag, const char *dflt) const { const char *v = value(flag); return v ? v : dflt; }
+	int integer(const char *flag, int dflt) const { const char *v = value(flag); return v ? atoi(v) : dflt; }
+	float real(const char *flag, float dflt) const { const char *v = value(flag); return v ? (float)atof(v) : dflt; }
+	// -xON / -xOFF pairs: the last one on the command line wins
+	bool onoff(const char *on, const char *off, bool dflt) const
+	{
+		bool r = dflt;
+		for (int i = 1; i < argc; i++) {
+			if (!strcmp(argv[i], on)) r = true;
+			if (!strcmp(argv[i], off)) r = false;
+		}
+		return r;
+	}
+};
+
+struct WallTimer {
+	std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+	double s() const { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); }
+};
+
+// 12 values, "%f\t", newline after every 4th, then "0 0 0 1" (src/reg3D.cpp:316-326)
+inline bool write_tmx(const char *path, const float *m)
+{
+	FILE *f = fopen(path, "w");
+	if (!f) return false;
+	for (int j = 0; j < 12; j++) {
+		fprintf(f, "%f\t", m[j]);
+		if ((j + 1) % 4 == 0) fprintf(f, "\n");
+	}
+	fprintf(f, "%f\t%f\t%f\t%f\n", 0.0, 0.0, 0.0, 1.0);
+	fclose(f);
+	return true;
+}
+
+inline bool read_tmx(const char *path, float *m)
+{
+	FILE *f = fopen(path, "r");
+	if (!f) return false;
+	int got = 0;
+	for (int j = 0; j < 12; j++) got += fscanf(f, "%f", &m[j]) == 1;
+	fclose(f);
+	return got == 12;
+}
+
+inline void identity_tmx(float *m)
+{
+	for (int j = 0; j < 12; j++) m[j] = 0;
+	m[0] = m[5] = m[10] = 1;
+}
+
+inline const char *gpu_mode_text(int gm)
+{
+	switch (gm) {
+	case -1: return "automatically setting";
+	case 0: return "CPU";
+	case 1: return "efficient GPU";
+	case 2: return "memory-saved GPU";
+	default: return nullptr;
+	}
+}
+
+inline size_t voxels(const unsigned int *s) { return (size_t)s[0] * s[1] * s[2]; }

@@ -1,0 +1,85 @@
+// Shared pieces of spimFusion / spimFusionBatch: isotropic output geometry, view-B rotation and
+// resampling, the registration retry ladder.  Behaviour follows src/spim_fusion.cpp:330-600 and
+// src/spim_fusion_batch.cpp:400-940; only include/libapi.h is called.
+#pragma once
+#include <cmath>
+
+#include "cli_common.h"
+
+struct FusionGeometry {
+	unsigned int in1[3], in2[3];   // sizes on disk
+	unsigned int s1[3], s2[3];     // after resampling to view A's x pixel size (and rotating view B)
+	int opChoice = 0;              // imoperation3D choice: 0 none, 1 +90 deg about Y, 2 -90 deg
+};
+
+// output sizes (src/spim_fusion.cpp:330-357): everything is resampled to pixelSizex1
+inline void fusion_geometry(FusionGeometry &g, const float px1[3], const float px2[3], int imRotation)
+{
+	g.s1[0] = g.in1[0];
+	g.s1[1] = (unsigned)round(float(g.in1[1]) * px1[1] / px1[0]);
+	g.s1[2] = (unsigned)round(float(g.in1[2]) * px1[2] / px1[0]);
+	unsigned int t[3];
+	for (int k = 0; k < 3; k++) t[k] = (unsigned)round(float(g.in2[k]) * px2[k] / px1[0]);
+	if (imRotation == 1 || imRotation == -1) {
+		g.opChoice = (imRotation == 1) ? 1 : 2;
+		g.s2[0] = t[2]; g.s2[1] = t[1]; g.s2[2] = t[0];
+	} else {
+		// the reference leaves the view-B size unset without rotation (src/spim_fusion.cpp:343-357);
+		// the evident intent is the resampled size
+		g.opChoice = 0;
+		g.s2[0] = t[0]; g.s2[1] = t[1]; g.s2[2] = t[2];
+	}
+}
+
+// view A: resample; view B: rotate about Y then resample (src/spim_fusion.cpp:560-590)
+inline void fusion_preprocess(const FusionGeometry &g, const std::vector<float> &raw1, const std::vector<float> &raw2, std::vector<float> &img1,
+	std::vector<float> &img2, int deviceNum)
+{
+	img1.assign(voxels(g.s1), 0.f);
+	img2.assign(voxels(g.s2), 0.f);
+	if (!memcmp(g.in1, g.s1, sizeof g.s1)) img1 = raw1;
+	else (void)imresize3d(img1.data(), (float *)raw1.data(), g.s1[0], g.s1[1], g.s1[2], g.in1[0], g.in1[1], g.in1[2], deviceNum);
+	std::vector<float> rot;
+	unsigned int rs[3] = {g.in2[0], g.in2[1], g.in2[2]};
+	const std::vector<float> *src = &raw2;
+	if (g.opChoice) {
+		rot.assign(raw2.size(), 0.f);
+		(void)imoperation3D(rot.data(), rs, (float *)raw2.data(), (unsigned int *)g.in2, g.opChoice, deviceNum);
+		src = &rot;
+	}
+	if (!memcmp(rs, g.s2, sizeof rs)) img2 = *src;
+	else (void)imresize3d(img2.data(), (float *)src->data(), g.s2[0], g.s2[1], g.s2[2], rs[0], rs[1], rs[2], deviceNum);
+}
+
+struct RegSettings {
+	int regChoice = 2, affMethod = 6, itLimit = 3000, deviceNum = 0, gpuMemMode = -1;
+	float ftol = 0.0001f;
+	bool verbose = true;
+};
+
+// reg3d, then the reference's fallback ladder when the matrix is implausible or ZNCC < 0.1
+// (src/spim_fusion_batch.cpp:559,722-746): other pre-alignment scheme, then the initial matrix.
+// `recheck` re-evaluates checkmatrix after the second attempt (the reference does so only in its
+// regMode-2 branch, :764).
+inline void register_with_ladder(std::vector<float> &reg, float *tmx, std::vector<float> &img1, std::vector<float> &img2, const FusionGeometry &g,
+	const RegSettings &rs, bool flagTmx, const float *tmxInitial, bool recheck, float *rec)
+{
+	const float costBar = 0.1f;
+	(void)reg3d(reg.data(), tmx, img1.data(), img2.data(), (unsigned int *)g.s1, (unsigned int *)g.s2, rs.regChoice, rs.affMethod, flagTmx, rs.ftol,
+		rs.itLimit, rs.deviceNum, rs.gpuMemMode, rs.verbose, rec);
+	bool ok = checkmatrix(tmx, g.s1[0], g.s1[1], g.s1[2]);
+	if (ok && !(rec[3] < costBar)) return;
+	printf("\n\t... Attempt failed: transformation matrix problematic or cost function value %f < threshold %2.2f\n", rec[3], costBar);
+	printf("\n\t... Change scheme and redo the registration!!!\n");
+	const int other = (rs.regChoice == 4) ? 2 : 4;
+	(void)reg3d(reg.data(), tmx, img1.data(), img2.data(), (unsigned int *)g.s1, (unsigned int *)g.s2, other, rs.affMethod, false, rs.ftol, rs.itLimit,
+		rs.deviceNum, rs.gpuMemMode, rs.verbose, rec);
+	if (recheck) ok = checkmatrix(tmx, g.s1[0], g.s1[1], g.s1[2]);
+	if ((!ok || rec[3] < costBar) && flagTmx) {
+		printf("\n\t... Attempt failed: transformation matrix problematic or cost function value %f < threshold %2.2f\n", rec[3], costBar);
+		printf("\n\t... Use input transformation matrix!!!\n");
+		memcpy(tmx, tmxInitial, 12 * sizeof(float));
+		(void)reg3d(reg.data(), tmx, img1.data(), img2.data(), (unsigned int *)g.s1, (unsigned int *)g.s2, 0, rs.affMethod, true, rs.ftol, rs.itLimit,
+			rs.deviceNum, rs.gpuMemMode, rs.verbose, rec);
+	}
+}
