@@ -24,7 +24,8 @@ SOURCES = ["decon.cu", "decon_fast.cu", "decon_fast_n64.cu", "decon_fast_n128.cu
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=default", "-DPROJECT_EXPORTS"]
+EXTRA = os.environ.get("MILB_NVCC_FLAGS", "").split()
+COMMON = [*EXTRA, "-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC,-ffp-contract=off,-fvisibility=default", "-DPROJECT_EXPORTS"]
 
 
 def _deps():

@@ -287,7 +287,7 @@ template <int N, int L, int T, bool SKIP_FIRST> __device__ __forceinline__ void 
 // ------------------------------------------------------------------------------------------------
 // Y forward, transposing:  in plane [N = Y rows][Z]  ->  out plane [Z rows][N = Y]
 template <int N, int L, int T>
-__global__ void __launch_bounds__(T, 2)
+__global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
 k_ypassT(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes)
 {
 	using G = TileGeom<N, L>;
@@ -315,7 +315,7 @@ k_ypassT(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *
 
 // Y pass, in place, plain: plane [N rows][Z], lanes along z
 template <int N, int L, int T, bool INV>
-__global__ void __launch_bounds__(T, 2)
+__global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
 k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes)
 {
 	using P = FastPlan<N>;
@@ -351,7 +351,7 @@ k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int 
 //   CONV : forward, * otf (same layout as `in`), inverse, transposed out [Yc rows][N = Z]
 //   !CONV: forward only, in place, scaled (OTF generation)
 template <int N, int L, int T, bool CONV>
-__global__ void __launch_bounds__(T, 2)
+__global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
 k_zconvT(float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ otf, const float2 *__restrict__ g_tw, int Yc,
 	int plane0, int nplanes, float scale)
 {
@@ -487,5 +487,109 @@ k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 		const float2 ck = tile[fast_pos<N>(k) * L + l];
 		const float2 cn = tile[fast_pos<N>((N - k) % N) * L + l];
 		spec[(long long)k * M + col0 + l] = split_pair(ck, cn);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Persistent fused X pencils with prefetch (RATIO / UPDATE / UPDATE_LAST).
+// One CTA per SM, T = (N/8)*L threads, tiles of L column pairs.  Three shared buffers:
+//   W  working tile            N x L float2
+//   SL spectrum landing buffer (N/2+1) x L float4   (cp.async, consumed by the merge step)
+//   AL aux landing buffer      N x L float2         (A for RATIO, E for UPDATE; consumed by stage 0)
+// As soon as a landing buffer has been consumed the next tile's rows are already requested, so the
+// spectrum and aux loads of tile t+1 overlap the butterflies of tile t.
+template <int N, int L, int T, int MODE>
+__global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
+k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M, int ntiles)
+{
+	using P = FastPlan<N>;
+	static_assert(P::r0 == 8 && (N / 8) * L == T, "stage 0 must be one radix-8 butterfly per thread");
+	extern __shared__ float2 sm[];
+	constexpr int half = N / 2, M0 = N / 8;
+	float2 *W = sm;
+	float4 *SL = (float4 *)(sm + N * L);
+	float2 *AL = sm + N * L + 2 * (half + 1) * L;
+	float2 *tw = AL + N * L;
+	load_tw<N>(tw, g_tw);
+	const float2 *auxsrc = (MODE == XF_RATIO) ? aux : (const float2 *)vol_io;
+	const int lane = threadIdx.x % L, q = threadIdx.x / L;
+
+	auto load_spec = [&](int t) {
+		const float4 *src = spec + (long long)t * L;
+		for (int c = threadIdx.x; c < (half + 1) * L; c += T) cp_async16(SL + c, src + (long long)(c / L) * M + (c % L));
+	};
+	auto load_aux = [&](int t) {
+		const float2 *src = auxsrc + (long long)t * L;
+		constexpr int CPR = L / 2;
+		for (int c = threadIdx.x; c < N * CPR; c += T) cp_async16(AL + (c / CPR) * L + 2 * (c % CPR), src + (long long)(c / CPR) * M + 2 * (c % CPR));
+	};
+
+	int t = blockIdx.x;
+	if (t < ntiles) load_spec(t);
+	cp_async_commit();
+	if (t < ntiles) load_aux(t);
+	cp_async_commit();
+	for (; t < ntiles; t += gridDim.x) {
+		const long long col0 = (long long)t * L;
+		const int tn = t + gridDim.x;
+		cp_async_wait<1>(); // spectrum of this tile landed (the aux group may still be in flight)
+		__syncthreads();
+		for (int idx = threadIdx.x; idx < (half + 1) * L; idx += T) {
+			const int k = idx / L, l = idx % L;
+			float4 ab = SL[idx];
+			const bool self = (k == 0) || (k == half);
+			if (self) { ab.y = 0.f; ab.w = 0.f; }
+			float2 ck, cn;
+			merge_pair(ab, ck, cn);
+			W[fast_pos<N>(k) * L + l] = ck;
+			if (!self) W[fast_pos<N>(N - k) * L + l] = cn;
+		}
+		__syncthreads();
+		if (tn < ntiles) load_spec(tn);
+		cp_async_commit();
+		inv_head_smem<N, L, T>(W, tw);
+		cp_async_wait<1>(); // aux of this tile landed (the next spectrum may still be in flight)
+		__syncthreads();
+		float2 v[8];
+#pragma unroll
+		for (int j = 0; j < 8; j++) v[j] = W[(q + j * M0) * L + lane];
+#pragma unroll
+		for (int j = 1; j < 8; j++) v[j] = cmulc(v[j], tw[q * j]);
+		bfly8<true>(v);
+		if (MODE == XF_RATIO) {
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				const float2 a = AL[(q + j * M0) * L + lane];
+				v[j].x = a.x / v[j].x; v[j].y = a.y / v[j].y; // div3Dkernel
+			}
+		} else {
+#pragma unroll
+			for (int j = 0; j < 8; j++) {
+				float2 e = AL[(q + j * M0) * L + lane];
+				e.x *= v[j].x; e.y *= v[j].y;                                   // multi3Dkernel
+				e.x = (e.x > SMALLVALUE_FAST) ? e.x : SMALLVALUE_FAST;          // maxvalue3Dgpukernel
+				e.y = (e.y > SMALLVALUE_FAST) ? e.y : SMALLVALUE_FAST;
+				vol_io[(long long)(q + j * M0) * M + col0 + lane] = e;
+				v[j] = e;
+			}
+		}
+		if (MODE != XF_UPDATE_LAST) {
+			bfly8<false>(v);
+#pragma unroll
+			for (int j = 1; j < 8; j++) v[j] = cmul(v[j], tw[q * j]);
+#pragma unroll
+			for (int j = 0; j < 8; j++) W[(q + j * M0) * L + lane] = v[j];
+		}
+		__syncthreads(); // AL consumed by everybody
+		if (tn < ntiles) load_aux(tn);
+		cp_async_commit();
+		if (MODE == XF_UPDATE_LAST) continue;
+		fwd_tail_smem<N, L, T>(W, tw);
+		for (int idx = threadIdx.x; idx < (half + 1) * L; idx += T) {
+			const int k = idx / L, l = idx % L;
+			const float2 ck = W[fast_pos<N>(k) * L + l];
+			const float2 cn = W[fast_pos<N>((N - k) % N) * L + l];
+			spec[(long long)k * M + col0 + l] = split_pair(ck, cn);
+		}
 	}
 }
