@@ -198,14 +198,29 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K) : "memory"); }
 
-// N rows of L pencils (row pitch `pitch` float2 in global memory) -> skewed shared tile
+// N rows of L pencils (row pitch `pitch` float2 in global memory) -> skewed shared tile.
+// A thread always copies the same 16-byte column chunk of rows r0, r0 + RPI, ...: both addresses
+// advance by constants, so the loop is one cp.async plus one 64-bit add per chunk.
 template <int N, int L, int T> __device__ __forceinline__ void tile_load_async(float2 *buf, const float2 *__restrict__ src, long long pitch)
 {
-	constexpr int CPR = L / 2, NC = N * CPR; // 16-byte chunks per row / per tile
+	constexpr int CPR = L / 2;          // 16-byte chunks per row
+	if constexpr ((T % CPR) == 0 && (N % (T / CPR)) == 0 && ((T / CPR) % 8) == 0) {
+		constexpr int RPI = T / CPR;    // rows covered per iteration (multiple of 8: the skew stays linear)
+		constexpr int IT = N / RPI;
+		constexpr int SROWS = (L <= 8) ? RPI + RPI / 8 : RPI;
+		const int p = threadIdx.x % CPR, r0 = threadIdx.x / CPR;
+		float2 *s = buf + prow<L>(r0) * L + 2 * p;
+		const float2 *g = src + (long long)r0 * pitch + 2 * p;
+		const long long gstep = (long long)RPI * pitch;
+#pragma unroll
+		for (int it = 0; it < IT; it++) cp_async16(s + it * SROWS * L, g + it * gstep);
+	} else {
+		constexpr int NC = N * CPR;
 #pragma unroll 4
-	for (int c = threadIdx.x; c < NC; c += T) {
-		const int r = c / CPR, p = c % CPR;
-		cp_async16(buf + prow<L>(r) * L + 2 * p, src + (long long)r * pitch + 2 * p);
+		for (int c = threadIdx.x; c < NC; c += T) {
+			const int r = c / CPR, p = c % CPR;
+			cp_async16(buf + prow<L>(r) * L + 2 * p, src + (long long)r * pitch + 2 * p);
+		}
 	}
 }
 
@@ -217,13 +232,25 @@ template <int L> __device__ __forceinline__ int swz(int row, int lane)
 	return prow<L>(row) * L + (lane ^ f);
 }
 
-// coalesced transposed copy-out of a swizzled N x L tile: out[lane * out_pitch + row]
+// coalesced transposed copy-out of a swizzled N x L tile: out[lane * out_pitch + row].
+// With T a multiple of N a thread keeps its row; only the lane advances, by a constant.
 template <int N, int L, int T> __device__ __forceinline__ void store_transposed(const float2 *tile2, float2 *__restrict__ out, long long out_pitch)
 {
+	if constexpr ((T % N) == 0 && (L % (T / N)) == 0) {
+		constexpr int LSTEP = T / N, IT = L / LSTEP;
+		const int row = threadIdx.x % N, lane0 = threadIdx.x / N;
+		const int f = (L >= 16) ? (row & 15) : (L == 8) ? ((row >> 1) & 7) : ((row >> 2) & 3);
+		const float2 *s = tile2 + prow<L>(row) * L;
+		float2 *g = out + (long long)lane0 * out_pitch + row;
+		const long long gstep = (long long)LSTEP * out_pitch;
+#pragma unroll
+		for (int it = 0; it < IT; it++) g[it * gstep] = s[(lane0 + it * LSTEP) ^ f];
+	} else {
 #pragma unroll 4
-	for (int idx = threadIdx.x; idx < N * L; idx += T) {
-		const int row = idx % N, lane = idx / N;
-		out[(long long)lane * out_pitch + row] = tile2[swz<L>(row, lane)];
+		for (int idx = threadIdx.x; idx < N * L; idx += T) {
+			const int row = idx % N, lane = idx / N;
+			out[(long long)lane * out_pitch + row] = tile2[swz<L>(row, lane)];
+		}
 	}
 }
 
