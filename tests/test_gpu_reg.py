@@ -103,7 +103,8 @@ def test_zncc_sums_and_cost_vs_oracle():
 
 def test_zncc_matches_hardware_texture_filtering():
     """Pins the texture-filter restatement on real hardware: the software fetch used by the product
-    and the oracle must agree with a genuine tex3D (linear filter, clamp) to float rounding."""
+    and the oracle must agree with a genuine tex3D (linear filter, clamp) to float rounding --
+    including the unit's 8-bit rounding of the corner-weight products (oracle/reg_oracle.c)."""
     import ctypes as C
     from microimagelib_b200 import _lib
     lib = _lib.load()
@@ -180,3 +181,23 @@ def test_source_size_mismatch_is_centre_aligned():
     reg, tmx, st, _ = libapi.reg3d(tgt, small, regChoice=0, inputTmx=False)
     assert st == 0
     assert np.array_equal(reg, do.align_size(small, tgt.shape))
+
+
+def test_software_fetch_equals_hardware_fetch_on_random_samples():
+    """20000 random sub-voxel samples of a white-noise volume: software restatement == tex3D."""
+    import ctypes as C
+    from microimagelib_b200 import _lib
+    lib = _lib.load()
+    F = C.POINTER(C.c_float)
+    lib.milb_debug_tex3d_sample.argtypes = [F, F, C.POINTER(C.c_uint), F, C.c_int, C.c_int]
+    rng = np.random.default_rng(11)
+    vol = (rng.random((16, 20, 24)) * 1000).astype(np.float32)
+    n = 20000
+    c = np.stack([rng.random(n) * 23 + 0.5, rng.random(n) * 19 + 0.5, rng.random(n) * 15 + 0.5], axis=1).astype(np.float32)
+    size = (C.c_uint * 3)(24, 20, 16)
+    out = {}
+    for hw in (1, 0):
+        o = np.zeros(n, np.float32)
+        assert lib.milb_debug_tex3d_sample(o.ctypes.data_as(F), vol.ctypes.data_as(F), size, c.ctypes.data_as(F), n, hw) == 0
+        out[hw] = o
+    assert float(np.abs(out[1] - out[0]).max()) <= 1e-3      # values up to 1000: float rounding only
