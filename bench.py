@@ -216,7 +216,7 @@ def main():
     launches = device.launch_count() - l0
     ms = ev0.elapsed_time(ev1)
     clk = clocks.stop()
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    t = torch.tensor([ms], dtype=torch.float64, device=torch.device("cuda", local_rank))
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_max = float(t.item())
@@ -228,14 +228,14 @@ def main():
         h_img = torch.from_numpy(img).pin_memory().numpy()
         h_out = torch.empty(shape, dtype=torch.float32).pin_memory().numpy()
         for _ in range(2):
-            libapi.decon_singleview(h_img, psf, args.iters, out=h_out)
+            libapi.decon_singleview(h_img, psf, args.iters, deviceNum=local_rank, out=h_out)
         barrier()
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            out, st, rec = libapi.decon_singleview(h_img, psf, args.iters, out=h_out)
+            out, st, rec = libapi.decon_singleview(h_img, psf, args.iters, deviceNum=local_rank, out=h_out)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local_rank))
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e = {"value": n_fft * args.iters * args.steps * world / float(tt.item()), "unit": "voxel-iters/s",
