@@ -67,6 +67,25 @@ int milb_decon_set_chunk_planes(milb_decon_t *h, int planes);
 int milb_decon_run_cufft_yardstick(milb_decon_t *h, int iterations, int const_init, void *stream,
 	float *loop_ms /* out: CUDA-event time of the iteration loop only */);
 
+/* Distributed slab FFT (one volume over P GPUs) -----------------------------------------------------
+ * Local pieces of the slab-decomposed loop; the all-to-all between them is
+ * issued by the caller over NCCL (microimagelib_b200/dist_decon.py).  Power-of-two boxes only.
+ * New work: the reference has no multi-GPU path (last rows). */
+typedef struct milb_dslab milb_dslab_t;
+/* fftSize = full FFT box {W,H,S}; this rank owns rows y in [y0, y0+ny) of the real volumes and
+ * planes_local whole kx-planes of the half spectrum */
+int milb_dslab_create(milb_dslab_t **out, const unsigned int *fftSize, int y0, int ny, int planes_local);
+void milb_dslab_destroy(milb_dslab_t *h);
+/* fused X pencils on the local slab [S][ny][W]; mode 0 forward-real, 1 ratio, 2 update, 3 update-last
+ * (same kernels as the single-GPU loop, src/api_subfunc.cu:3406-3415) */
+int milb_dslab_xpass(milb_dslab_t *h, int mode, float *vol_io, const float *aux, void *spec, void *stream);
+/* Y/Z passes (+ OTF product) on my whole planes; otf == NULL: forward only, scaled result left in S2 */
+int milb_dslab_planes(milb_dslab_t *h, void *S, void *S2, const void *otf, float scale, void *stream);
+/* my slab of the boxed PSF volume (genOTFgpu preparation, src/api_subfunc.cu:3283-3293) */
+int milb_dslab_psf_box(milb_dslab_t *h, float *out_slab, const float *d_psf, const unsigned int *psfSize, int flip, void *stream);
+/* mode 0: out = max(a, 0.01); mode 1: out = (a + b) * 0.5  (src/api_subfunc.cu:3380, 3616-3617) */
+int milb_dslab_elementwise(float *out, const float *a, const float *b, long long n, int mode, void *stream);
+
 /* Registration ----------------------------------------------------------------------------------
  * A handle owns the mean-removed target and source volumes of one reg3d_affine1 call
  * (src/api_subfunc.cu:2838-2875). */

@@ -379,6 +379,38 @@ int milb_psf_box_async(float *d_out, const float *d_psf, const double *d_sum, in
 	return MILB_OK;
 }
 
+// y-slab [X][ny][Z] (y in [y0, y0+ny)) of the same boxed PSF volume, for the distributed path
+__global__ void k_psf_box_slab(float *__restrict__ out, const float *__restrict__ psf, const double *__restrict__ d_sum, int X, int Y, int Z, int y0,
+	int ny, int px, int py, int pz, int flip)
+{
+	const long long n = (long long)X * ny * Z;
+	const bool boxed = (X < px) || (Y < py) || (Z < pz);
+	const float inv_sum = (float)(1.0 / d_sum[0]);
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		int z = (int)(i % Z);
+		long long t = i / Z;
+		int y = (int)(t % ny) + y0, x = (int)(t / ny);
+		int sx = psf_src_index(x, X, px, boxed), sy = psf_src_index(y, Y, py, boxed), sz = psf_src_index(z, Z, pz, boxed);
+		float v = 0.f;
+		if (sx >= 0 && sy >= 0 && sz >= 0) {
+			if (flip) { sx = px - 1 - sx; sy = py - 1 - sy; sz = pz - 1 - sz; }
+			v = psf[((long long)sx * py + sy) * pz + sz] * inv_sum;
+		}
+		out[i] = v;
+	}
+}
+
+int milb_psf_box_slab_async(float *d_out, const float *d_psf, const double *d_sum, int X, int Y, int Z, int y0, int ny, int px, int py, int pz,
+	int flip, cudaStream_t st)
+{
+	const long long n = (long long)X * ny * Z;
+	long long b = cdiv_ll(n, 256);
+	k_psf_box_slab<<<(int)(b > 148 * 16 ? 148 * 16 : b), 256, 0, st>>>(d_out, d_psf, d_sum, X, Y, Z, y0, ny, px, py, pz, flip);
+	milb_count_launches(1);
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
 static int grid_for(long long n) { long long b = cdiv_ll(n, 256); return (int)(b > 148 * 16 ? 148 * 16 : b); }
 
 // OTF of one PSF into dst (genOTFgpu).  The 1/N of the two un-normalised transforms of each

@@ -40,3 +40,5 @@ struct milb_decon {
 // normalised / flipped / boxed / origin-shifted PSF volume (decon.cu)
 int milb_psf_box_async(float *d_out, const float *d_psf, const double *d_sum, int X, int Y, int Z, int px, int py, int pz, int flip,
 	cudaStream_t st);
+int milb_psf_box_slab_async(float *d_out, const float *d_psf, const double *d_sum, int X, int Y, int Z, int y0, int ny, int px, int py, int pz,
+	int flip, cudaStream_t st);
