@@ -1,0 +1,114 @@
+#!/usr/bin/env python
+"""bench_dist.py -- BASELINE config 3: deconDualView joint RL on ONE 1024x1024x512 pair, slab-decomposed
+distributed 3-D FFT with NCCL all-to-all at P = 2/4/8 B200 (strong scaling of a single volume).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node P --master-addr 127.0.0.1 \
+        --master-port 29500 bench_dist.py --iters 5
+
+Prints one JSON line on rank 0: ms per dual-view iteration, voxel-iterations/s, the all-to-all's
+bytes, its stand-alone time and achieved NVLink GB/s per direction per GPU (against the measured
+770 GB/s peer-copy figure of B200_PROFILING.md), and the share of the iteration spent in it.
+Timing: CUDA events on the launching stream, max over ranks.  Data: synthetic (uniform noise on a
+background, generated on the device: the loop's cost does not depend on the voxel values).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--shape", default="512,1024,1024", help="slices,H,W of the FFT box")
+    ap.add_argument("--iters", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=1)
+    ap.add_argument("--views", type=int, default=2)
+    args = ap.parse_args()
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from microimagelib_b200 import synth
+    from microimagelib_b200.dist_decon import DistDecon
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    shape = tuple(int(v) for v in args.shape.split(","))
+    dd = DistDecon(shape, args.views)
+    L = dd.L
+    psf_a = synth.gaussian_psf((65, 65, 65), (4, 2, 2))
+    psf_b = synth.gaussian_psf((65, 65, 65), (2, 2, 4))
+    dd.set_psf(0, psf_a)
+    if args.views == 2:
+        dd.set_psf(1, psf_b)
+    g = torch.Generator(device=dev)
+    g.manual_seed(20260 + rank)
+    for v in range(args.views):
+        dd.set_image(v, torch.rand((L.X, L.ny, L.Z), generator=g, device=dev) * 50 + 100)
+
+    def timed(fn, reps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b) / reps], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    dd.run(args.warmup)
+    ms_run = timed(lambda: dd.run(args.iters), 1)
+    ms_iter = ms_run / args.iters
+
+    def exchange_only():
+        L.to_planes(dd.slab, dd.planes, dd.scratch)
+        L.to_slabs(dd.planes, dd.slab, dd.scratch)
+
+    exchange_only()
+    ms_pair = timed(exchange_only, 3)             # two all-to-alls + the two local re-layout copies
+
+    def a2a_only():
+        if world > 1:
+            dist.all_to_all_single(dd.scratch[: world * L.np * L.row], dd.slab.reshape(-1), L.plane_splits(), L.slab_splits())
+
+    a2a_only()
+    ms_a2a = timed(a2a_only, 5) if world > 1 else 0.0
+    nconv = 2 * args.views
+    sent = dd.a2a_bytes_per_gpu()
+    if rank == 0:
+        nfft = float(np.prod(shape))
+        line = {
+            "metric": "RL voxel-iters/sec (one volume, slab-decomposed distributed FFT)", "value": nfft / (ms_iter * 1e-3),
+            "unit": "voxel-iters/s", "n_gpus": world, "scaling": "strong", "ms_per_iteration": ms_iter, "iterations": args.iters,
+            "config": {"workload": f"deconDualView joint RL {shape[2]}x{shape[1]}x{shape[0]} pair (BASELINE config 3)" if args.views == 2
+                       else f"deconSingleView RL {shape[2]}x{shape[1]}x{shape[0]}", "views": args.views,
+                       "decomposition": "real volumes by rows (y), spectrum by whole kx-planes; 2 all-to-alls per convolution"},
+            "all_to_all": {"per_iteration": 2 * nconv, "bytes_sent_per_gpu_each": sent, "ms_each_standalone": ms_a2a,
+                           "GBps_per_direction_per_gpu": (sent / (ms_a2a * 1e-3) / 1e9) if ms_a2a else None,
+                           "nvlink_peak_GBps": 770.0, "frac_of_peak": (sent / (ms_a2a * 1e-3) / 1e9 / 770.0) if ms_a2a else None,
+                           "ms_exchange_pair_with_relayout": ms_pair,
+                           "share_of_iteration": nconv * ms_pair / ms_iter},
+            "dtype": "f32", "data": "synthetic (device-generated noise on background; timing only)",
+        }
+        print(json.dumps(line), flush=True)
+    dd.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
