@@ -116,6 +116,37 @@ int milb_reg3d_affine(float *reg_out, float *iTmx, const float *target, const fl
 	const unsigned int *size, int affMethod, int flagTmx, float FTOL, int itLimit, int on_device,
 	int verbose, float *records, void *stream);
 
+/* Pre-alignment (reg3d regChoice 1 / 3 / 4, reg2d) -------------------------------------------------
+ * phase-correlation shift of img2 against img1, both DEVICE volumes of size {W,H,S} (S = 1: 2-D).
+ * Replaces reg3d_phasor1 / reg2d_phasor1 (src/api_subfunc.cu:2466-2590, 2128-2227): cuFFT forward
+ * transforms like the reference, then fused normalisation, shifted arg-max with max3Dgpu's tie
+ * order, and the ZNCC comparison of the wrapped aliases when a shift exceeds a quarter extent. */
+int milb_phasor(long long *shiftXYZ, const float *d_img1, const float *d_img2, const unsigned int *size, void *stream);
+/* integer shift with zero fill on DEVICE volumes: out[x] = in[x - shift]; replaces imshiftgpu,
+ * src/api_subfunc.cu:838-844 */
+int milb_imshift(float *d_out, const float *d_in, const unsigned int *size, const long long *shiftXYZ, void *stream);
+
+/* 2-D registration state: mean-removed image 1 and image 2 of one reg2d_* call
+ * (src/api_subfunc.cu:1921-1940).  Matrices are 6 floats, row-major 2x3, target -> source. */
+typedef struct milb_reg2d milb_reg2d_t;
+int milb_reg2d_create(milb_reg2d_t **out, const float *img1, const unsigned int *size1 /* {W,H} */, const float *img2,
+	const unsigned int *size2, int on_device, float *sd_t, void *stream);
+void milb_reg2d_destroy(milb_reg2d_t *h);
+/* K cost evaluations (any K) in one launch; replaces costfunc2D -> corrfunc2D -> corr2Dkernel + two
+ * D2H copies + sumcpu, src/api_subfunc.cu:1014-1036, 1815-1821 */
+int milb_reg2d_cost(milb_reg2d_t *h, const float *matrices, int K, float *costs, void *stream);
+/* affineTransform2D of the raw (raw_source != 0) or mean-removed image 2, src/api_subfunc.cu:1007-1012 */
+int milb_reg2d_warp(milb_reg2d_t *h, const float *tmx, int raw_source, float *out, int on_device, void *stream);
+/* exhaustive shift search, all candidates in ONE launch.  search_y != 0 replaces reg2d_shiftalign1
+ * (src/api_subfunc.cu:1860-1993), search_y == 0 replaces reg2d_shiftalignX1 (:1996-2117).
+ * records (>= 9 floats, may be NULL): [4] initial ZNCC, [5] best ZNCC, [8] as the reference. */
+int milb_reg2d_shiftalign(float *reg_out, float *tmx, const float *img1, const unsigned int *size1, const float *img2,
+	const unsigned int *size2, int flagTmx, int search_y, float shiftRegion, float totalStep, int on_device, float *records,
+	void *stream);
+/* 6-parameter 2-D affine registration by Powell; replaces reg2d_affine1, src/api_subfunc.cu:2229-2336 */
+int milb_reg2d_affine(float *reg_out, float *tmx, const float *img1, const unsigned int *size1, const float *img2,
+	const unsigned int *size2, int affMethod, int flagTmx, float FTOL, int itLimit, int on_device, float *records, void *stream);
+
 /* host-side helpers exported for parity tests: src/api_subfunc.cu:557-623, 715-824 */
 void milb_p2matrix(float *m, const float *x);
 void milb_matrix2p(const float *m, float *x);

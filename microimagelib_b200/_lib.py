@@ -76,6 +76,14 @@ CAPI_PROTOS = {
     "milb_reg_warp_source": (C.c_int, [_VP, _F, _VP, C.c_int, _VP]),
     "milb_affine_warp": (C.c_int, [_VP, _U, _VP, _U, _F, C.c_int, _VP]),
     "milb_reg3d_affine": (C.c_int, [_VP, _F, _VP, _VP, _U, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int, _F, _VP]),
+    "milb_phasor": (C.c_int, [C.POINTER(_LL), _VP, _VP, _U, _VP]),
+    "milb_imshift": (C.c_int, [_VP, _VP, _U, C.POINTER(_LL), _VP]),
+    "milb_reg2d_create": (C.c_int, [C.POINTER(_VP), _VP, _U, _VP, _U, C.c_int, _F, _VP]),
+    "milb_reg2d_destroy": (None, [_VP]),
+    "milb_reg2d_cost": (C.c_int, [_VP, _F, C.c_int, _F, _VP]),
+    "milb_reg2d_warp": (C.c_int, [_VP, _F, C.c_int, _VP, C.c_int, _VP]),
+    "milb_reg2d_shiftalign": (C.c_int, [_VP, _F, _VP, _U, _VP, _U, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, _F, _VP]),
+    "milb_reg2d_affine": (C.c_int, [_VP, _F, _VP, _U, _VP, _U, C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, _F, _VP]),
     "milb_p2matrix": (None, [_F, _F]),
     "milb_matrix2p": (None, [_F, _F]),
     "milb_matrixmultiply": (None, [_F, _F, _F]),

@@ -9,6 +9,7 @@
 #include <string.h>
 #include <time.h>
 
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <mutex>
@@ -224,9 +225,8 @@ int reg3d(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int 
 		printf("\n*** Wrong registration choice is setup, no registraiton performed !!! **** \n");
 		return 1;
 	}
-	if (regChoice == 1 || regChoice == 3 || regChoice == 4) {
-		// phasor / 2-D MIP pre-alignment: SURVEY.md section 8(f) rank 3, not built yet
-		printf("\n ****regChoice %d (pre-alignment) is not available in the B200 backend yet **** \n", regChoice);
+	if (regChoice == 4 && gpuMemMode == 2) { // src/api_reg.cpp:583-586
+		printf("\n ****2D MIP registration --> affine registraion function is under developing **** \n");
 		return -1;
 	}
 	// modes 1 and 2 run the same device-resident path
@@ -244,6 +244,60 @@ int reg3d(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int 
 	cuda_fatal(cudaMemcpy(d_t, h_img1, sizeof(float) * n1, cudaMemcpyHostToDevice), "H2D");
 	records[9] = free_mb();
 	if (regChoice == 0) affMethod = 0;
+	if (regChoice == 1 || regChoice == 3) {
+		// phase-correlation shift, src/api_reg.cpp:418-444
+		long long shiftXYZ[3] = {0, 0, 0};
+		fatal_if(milb_phasor(shiftXYZ, d_t, d_s, imSize1, nullptr), "phasor registration");
+		for (int j = 0; j < 12; j++) iTmx[j] = 0;
+		iTmx[0] = iTmx[5] = iTmx[10] = 1;
+		iTmx[3] = (float)shiftXYZ[0]; iTmx[7] = (float)shiftXYZ[1]; iTmx[11] = (float)shiftXYZ[2];
+		if (regChoice == 1) {
+			const long long neg[3] = {-shiftXYZ[0], -shiftXYZ[1], -shiftXYZ[2]};
+			fatal_if(milb_imshift(d_reg, d_s, imSize1, neg, nullptr), "imshift");
+			cuda_fatal(cudaMemcpy(h_reg, d_reg, sizeof(float) * n1, cudaMemcpyDeviceToHost), "D2H");
+			cudaFree(d_t); cudaFree(d_s); cudaFree(d_reg);
+			if (d_tmp) cudaFree(d_tmp);
+			records[10] = free_mb();
+			records[7] = (float)(now_s() - t_start);
+			if (verbose) printf("\t... registration done !!! \n");
+			return 0;
+		}
+		flagTmx = true;
+	}
+	if (regChoice == 4) {
+		// 2-D MIP shift search: XY projection for (x, y), then ZX projection for z, src/api_reg.cpp:445-519
+		printf("\t... 2D MIP registration ... \n");
+		const float shiftRegion = 0.3f, totalStep = 30.f;
+		const long long n2d = std::max((long long)imSize1[0] * imSize1[1], (long long)imSize1[2] * imSize1[0]);
+		float *d_m1 = nullptr, *d_m2 = nullptr;
+		cuda_fatal(cudaMalloc(&d_m1, sizeof(float) * n2d), "cudaMalloc");
+		cuda_fatal(cudaMalloc(&d_m2, sizeof(float) * n2d), "cudaMalloc");
+		float tmx1[6] = {1, 0, 0, 0, 1, 0}, rec2d[9];
+		fatal_if(milb_mip_dev(d_m1, d_t, imSize1[0], imSize1[1], imSize1[2], 1, nullptr), "mip");
+		fatal_if(milb_mip_dev(d_m2, d_s, imSize1[0], imSize1[1], imSize1[2], 1, nullptr), "mip");
+		const unsigned int sxy[2] = {imSize1[0], imSize1[1]};
+		int rc2 = milb_reg2d_shiftalign(nullptr, tmx1, d_m1, sxy, d_m2, sxy, 0, 1, shiftRegion, totalStep, 1, rec2d, nullptr);
+		float tmx2[6] = {1, 0, 0, 0, 1, tmx1[2]};
+		if (rc2 == MILB_OK) {
+			fatal_if(milb_mip_dev(d_m1, d_t, imSize1[0], imSize1[1], imSize1[2], 2, nullptr), "mip");
+			fatal_if(milb_mip_dev(d_m2, d_s, imSize1[0], imSize1[1], imSize1[2], 2, nullptr), "mip");
+			const unsigned int szx[2] = {imSize1[2], imSize1[0]};
+			rc2 = milb_reg2d_shiftalign(nullptr, tmx2, d_m1, szx, d_m2, szx, 1, 0, shiftRegion, totalStep, 1, rec2d, nullptr);
+		}
+		cudaFree(d_m1); cudaFree(d_m2);
+		if (rc2 == MILB_ERR_EMPTY) {
+			fprintf(stderr, "*** SD of image 1 is zero, empty image input **** \n");
+			exit(1);
+		}
+		fatal_if(rc2, "2D MIP registration");
+		for (int j = 0; j < 12; j++) iTmx[j] = 0;
+		iTmx[0] = iTmx[5] = iTmx[10] = 1;
+		iTmx[3] = tmx1[2]; iTmx[7] = tmx1[5]; iTmx[11] = tmx2[2];
+		printf("\t... shift translation, X: %2.1f; Y: %2.1f; Z: %2.1f\n", tmx1[2], tmx1[5], tmx2[2]);
+		printf("\t... 2D MIP registration completed. \n");
+		printf("\t... 3D registration ... \n");
+		flagTmx = true;
+	}
 	int rc = milb_reg3d_affine(d_reg, iTmx, d_t, d_s, imSize1, affMethod, flagTmx ? 1 : 0, FTOL, itLimit, 1, verbose ? 1 : 0, records, nullptr);
 	if (rc == 4) {
 		fprintf(stderr, "*** SD of image is zero, empty image input or empty image after initial transformation **** \n");
@@ -275,11 +329,77 @@ int reg_3dgpu(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned 
 	return st;
 }
 
-int reg2d(float *, float *, float *, float *, unsigned int *, unsigned int *, int, bool, float, int, int, int, bool, float *)
+int reg2d(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int *imSize1, unsigned int *imSize2, int regChoice,
+	bool flagTmx, float FTOL, int itLimit, int deviceNum, int gpuMemMode, bool verbose, float *records)
 {
-	// 2-D registration is only reached through the pre-alignment choices
-	printf("\n ****reg2d is not available in the B200 backend **** \n");
-	return -1;
+	// src/api_reg.cpp:115-240
+	const double t_start = now_s();
+	if (gpuMemMode == 1) {
+		cuda_fatal(cudaSetDevice(deviceNum), "cudaSetDevice");
+		records[8] = free_mb();
+		if (verbose) printf("...GPU free memory before registration is %.0f MB\n", records[8]);
+	}
+	records[0] = (float)gpuMemMode;
+	if (gpuMemMode == 0) {
+		if (regChoice < 0 || regChoice > 2) {
+			printf("\n ****Wrong registration choice is setup, no registraiton performed !!! **** \n");
+			return 1;
+		}
+		printf("\n **** 2D CPU registration is currently not supported !!! **** \n");
+	} else if (gpuMemMode == 1) {
+		records[9] = free_mb();
+		const unsigned int s1[2] = {imSize1[0], imSize1[1]}, s2[2] = {imSize2[0], imSize2[1]};
+		int rc = MILB_OK;
+		float rec9[9];
+		switch (regChoice) {
+		case 0:
+			if (flagTmx) rc = milb_reg2d_affine(h_reg, iTmx, h_img1, s1, h_img2, s2, 0, 1, FTOL, itLimit, 0, records, nullptr);
+			break;
+		case 1:
+			rc = milb_reg2d_shiftalign(h_reg, iTmx, h_img1, s1, h_img2, s2, flagTmx ? 1 : 0, 1, 0.4f, 40.f, 0, rec9, nullptr);
+			break;
+		case 2:
+			rc = milb_reg2d_affine(h_reg, iTmx, h_img1, s1, h_img2, s2, 1, flagTmx ? 1 : 0, FTOL, itLimit, 0, records, nullptr);
+			break;
+		case 3: {
+			if (s1[0] != s2[0] || s1[1] != s2[1]) {
+				printf("\n ****Image size of the 2D images is not matched, processing stop !!! **** \n");
+				return 1;
+			}
+			const long long n = (long long)s1[0] * s1[1];
+			float *d_t = nullptr, *d_s = nullptr;
+			cuda_fatal(cudaMalloc(&d_t, sizeof(float) * n), "cudaMalloc");
+			cuda_fatal(cudaMalloc(&d_s, sizeof(float) * n), "cudaMalloc");
+			cuda_fatal(cudaMemcpy(d_t, h_img1, sizeof(float) * n, cudaMemcpyHostToDevice), "H2D");
+			cuda_fatal(cudaMemcpy(d_s, h_img2, sizeof(float) * n, cudaMemcpyHostToDevice), "H2D");
+			const unsigned int s3[3] = {s1[0], s1[1], 1};
+			long long sh[3] = {0, 0, 0};
+			rc = milb_phasor(sh, d_t, d_s, s3, nullptr);
+			const long long neg[3] = {-sh[0], -sh[1], 0};
+			if (rc == MILB_OK) rc = milb_imshift(d_t, d_s, s3, neg, nullptr);
+			if (rc == MILB_OK) cuda_fatal(cudaMemcpy(h_reg, d_t, sizeof(float) * n, cudaMemcpyDeviceToHost), "D2H");
+			cudaFree(d_t); cudaFree(d_s);
+			iTmx[0] = 1; iTmx[1] = 0; iTmx[2] = (float)sh[0];
+			iTmx[3] = 0; iTmx[4] = 1; iTmx[5] = (float)sh[1];
+			break;
+		}
+		default:
+			printf("\n ****Wrong registration choice is setup, no registraiton performed !!! **** \n");
+			return 1;
+		}
+		if (rc == MILB_ERR_EMPTY) {
+			fprintf(stderr, "*** SD of image 1 is zero, empty image input **** \n");
+			exit(1);
+		}
+		fatal_if(rc, "2D registration failed");
+		records[10] = free_mb();
+	} else {
+		printf("\n****Wrong gpuMemMode setup, no deconvolution performed !!! ****\n");
+		return 1;
+	}
+	records[7] = (float)(now_s() - t_start);
+	if (verbose) printf("Total time cost for whole processing is %2.3f s\n", records[7]);
+	return 0;
 }
 
 int atrans3dgpu(float *h_reg, float *iTmx, float *h_img2, unsigned int *imSize1, unsigned int *imSize2, int deviceNum)

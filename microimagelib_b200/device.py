@@ -212,6 +212,122 @@ def reg3d_affine(target, source, aff_method, flag_tmx=False, itmx=None, ftol=1e-
     return reg, tmx, rec
 
 
+# ---- pre-alignment (reg3d regChoice 1 / 3 / 4, reg2d) ------------------------------------------
+def _size2(shape):
+    return (C.c_uint * 2)(int(shape[1]), int(shape[0]))
+
+
+def _to_device(a):
+    import torch
+    return a if _is_torch(a) else torch.as_tensor(np.ascontiguousarray(a, np.float32), device="cuda")
+
+
+def phasor(img1, img2, stream=None):
+    """milb_phasor: integer (x, y, z) shift of img2 against img1; (S, H, W) volumes or (H, W) images."""
+    lib = _lib.load()
+    a, b = _to_device(img1), _to_device(img2)
+    shape = tuple(a.shape) if a.dim() == 3 else (1,) + tuple(a.shape)
+    sh = (C.c_longlong * 3)()
+    _check(lib.milb_phasor(sh, C.c_void_p(a.data_ptr()), C.c_void_p(b.data_ptr()), _size(shape), _stream(stream)), "milb_phasor")
+    return [int(sh[0]), int(sh[1]), int(sh[2])]
+
+
+def imshift(vol, shift, stream=None):
+    """milb_imshift: out[x] = vol[x - shift] with zero fill, shift = (dx, dy, dz); returns a numpy array."""
+    import torch
+    lib = _lib.load()
+    a = _to_device(vol)
+    out = torch.empty_like(a)
+    sh = (C.c_longlong * 3)(*[int(v) for v in shift])
+    _check(lib.milb_imshift(C.c_void_p(out.data_ptr()), C.c_void_p(a.data_ptr()), _size(a.shape), sh, _stream(stream)), "milb_imshift")
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+class Reg2D:
+    """milb_reg2d_*: mean-removed 2-D image pair; matrices are 6 floats (2x3, target -> source)."""
+
+    def __init__(self, img1, img2, stream=None):
+        self.lib = _lib.load()
+        self._h = C.c_void_p()
+        p1, d1, self._k1 = _ptr(img1)
+        p2, d2, self._k2 = _ptr(img2)
+        assert d1 == d2
+        self.shape = tuple(img1.shape)
+        sd = C.c_float(0)
+        _check(self.lib.milb_reg2d_create(C.byref(self._h), p1, _size2(img1.shape), p2, _size2(img2.shape), d1, C.byref(sd), _stream(stream)),
+               "milb_reg2d_create")
+        self.sd_t = np.float32(sd.value)
+
+    def close(self):
+        if self._h:
+            self.lib.milb_reg2d_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def cost(self, matrices, stream=None):
+        m = np.ascontiguousarray(matrices, np.float32).reshape(-1, 6)
+        out = np.empty(m.shape[0], np.float32)
+        _check(self.lib.milb_reg2d_cost(self._h, m.ctypes.data_as(_F), m.shape[0], out.ctypes.data_as(_F), _stream(stream)), "milb_reg2d_cost")
+        return out
+
+    def warp(self, tmx, raw_source=True, stream=None):
+        m = np.ascontiguousarray(tmx, np.float32).reshape(6)
+        out = np.empty(self.shape, np.float32)
+        _check(self.lib.milb_reg2d_warp(self._h, m.ctypes.data_as(_F), 1 if raw_source else 0, C.c_void_p(out.ctypes.data), 0, _stream(stream)),
+               "milb_reg2d_warp")
+        return out
+
+
+def reg2d_shiftalign(img1, img2, flag_tmx=False, itmx=None, search_y=True, shift_region=0.3, total_step=30.0, stream=None):
+    """milb_reg2d_shiftalign on host images.  Returns (reg, tmx, records)."""
+    lib = _lib.load()
+    p1, d1, k1 = _ptr(img1)
+    p2, d2, k2 = _ptr(img2)
+    reg = np.empty(tuple(img1.shape), np.float32)
+    tmx = np.array([1, 0, 0, 0, 1, 0], np.float32) if itmx is None else np.array(itmx, np.float32).reshape(6)
+    rec = np.zeros(9, np.float32)
+    assert d1 == 0 and d2 == 0
+    _check(lib.milb_reg2d_shiftalign(C.c_void_p(reg.ctypes.data), tmx.ctypes.data_as(_F), p1, _size2(img1.shape), p2, _size2(img2.shape),
+                                     1 if flag_tmx else 0, 1 if search_y else 0, float(shift_region), float(total_step), 0,
+                                     rec.ctypes.data_as(_F), _stream(stream)), "milb_reg2d_shiftalign")
+    return reg, tmx, rec
+
+
+def reg2d_affine(img1, img2, aff_method=1, flag_tmx=False, itmx=None, ftol=1e-4, it_limit=3000, stream=None):
+    """milb_reg2d_affine on host images.  Returns (reg, tmx, records)."""
+    lib = _lib.load()
+    p1, d1, k1 = _ptr(img1)
+    p2, d2, k2 = _ptr(img2)
+    assert d1 == 0 and d2 == 0
+    reg = np.empty(tuple(img1.shape), np.float32)
+    tmx = np.array([1, 0, 0, 0, 1, 0], np.float32) if itmx is None else np.array(itmx, np.float32).reshape(6)
+    rec = np.zeros(11, np.float32)
+    _check(lib.milb_reg2d_affine(C.c_void_p(reg.ctypes.data), tmx.ctypes.data_as(_F), p1, _size2(img1.shape), p2, _size2(img2.shape),
+                                 int(aff_method), 1 if flag_tmx else 0, float(ftol), int(it_limit), 0, rec.ctypes.data_as(_F),
+                                 _stream(stream)), "milb_reg2d_affine")
+    return reg, tmx, rec
+
+
+def tex2d_samples(img, coords, hardware=False):
+    """test utility: tex2D of a (H, W) image at (n, 2) texture coordinates, hardware unit or software restatement"""
+    lib = _lib.load()
+    img = np.ascontiguousarray(img, np.float32)
+    c = np.ascontiguousarray(coords, np.float32).reshape(-1, 2)
+    out = np.empty(c.shape[0], np.float32)
+    fn = lib.milb_debug_tex2d_sample
+    fn.restype = C.c_int
+    fn.argtypes = [_F, _F, C.POINTER(C.c_uint), _F, C.c_int, C.c_int]
+    _check(fn(out.ctypes.data_as(_F), img.ctypes.data_as(_F), _size2(img.shape), c.ctypes.data_as(_F), c.shape[0], 1 if hardware else 0),
+           "milb_debug_tex2d_sample")
+    return out
+
+
 # ---- host-side helpers exported for parity tests
 def p2matrix(x):
     x = np.ascontiguousarray(x, np.float32)

@@ -80,6 +80,20 @@ def reg3d(img1, img2, regChoice=2, regMethod=6, inputTmx=False, iTmx=None, FTOL=
     return out, tmx, st, rec
 
 
+def reg2d(img1, img2, regChoice=2, flagTmx=False, iTmx=None, FTOL=1e-4, itLimit=3000, deviceNum=0, gpuMemMode=1, verbose=False):
+    """reg2d (include/libapi.h).  Images are (H, W).  Returns (h_reg, iTmx[6], status, records)."""
+    lib = _lib.load()
+    img1, img2 = _f32(img1), _f32(img2)
+    out = np.zeros_like(img1)
+    tmx = np.array([1, 0, 0, 0, 1, 0], np.float32) if iTmx is None else _f32(iTmx).reshape(6).copy()
+    rec = np.zeros(11, np.float32)
+    s1 = (C.c_uint * 3)(img1.shape[1], img1.shape[0], 1)
+    s2 = (C.c_uint * 3)(img2.shape[1], img2.shape[0], 1)
+    st = lib.reg2d(_fp(out), _fp(tmx), _fp(img1), _fp(img2), s1, s2, int(regChoice), bool(flagTmx), float(FTOL), int(itLimit),
+                   int(deviceNum), int(gpuMemMode), bool(verbose), _fp(rec))
+    return out, tmx, st, rec
+
+
 def checkmatrix(iTmx, sx, sy, sz) -> bool:
     m = _f32(iTmx).reshape(12)
     return bool(_lib.load().checkmatrix(_fp(m), int(sx), int(sy), int(sz)))

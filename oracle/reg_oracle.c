@@ -217,3 +217,99 @@ void orc_dof9tomatrix(float *p_out, const float *p_dof, int dofNum)
 	t3[0] = cosf(theta); t3[2] = -sinf(theta); t3[5] = 1; t3[8] = sinf(theta); t3[10] = cosf(theta);
 	orc_matrixmultiply(p_out, t2, t3);
 }
+
+/* ---- 2-D path: tex2D fetch, corr2Dkernel, affineTransform2Dkernel ----------------------------
+ * include/cukernel.cuh:558-593.  BindTexture2D (src/api_subfunc.cu:990-999) asks for wrap
+ * addressing with un-normalised coordinates, which CUDA turns into clamp.  The bilinear weights are
+ * the 3-D unit's with the z weight pinned to one texel: x weights exact, then the rounded y split
+ * (checked on the B200 by tests/test_gpu_prealign.py through a hardware tex2D fetch).          */
+static inline float tex2d_linear(const float *v, long long sx, long long sy, float tx, float ty)
+{
+	int ix, iy, a, b;
+	split_coord(tx, &ix, &a);
+	split_coord(ty, &iy, &b);
+	int xi[2] = { clampi(ix, (int)sx - 1), clampi(ix + 1, (int)sx - 1) };
+	int yi[2] = { clampi(iy, (int)sy - 1), clampi(iy + 1, (int)sy - 1) };
+	int wx[2] = { 256 - a, a };
+	int w[2][2];
+	for (int dx = 0; dx < 2; dx++) {
+		int tie = dx ? 128 : 127;
+		int hi = (wx[dx] * b + tie) >> 8;
+		w[1][dx] = hi;
+		w[0][dx] = wx[dx] - hi;
+	}
+	float acc = 0.0f;
+	for (int dy = 0; dy < 2; dy++) {
+		const float *row = v + (long long)yi[dy] * sx;
+		acc = fmaf((float)w[dy][0], row[xi[0]], acc);
+		acc = fmaf((float)w[dy][1], row[xi[1]], acc);
+	}
+	return acc * (1.0f / 256.0f);
+}
+
+/* d_aff[0]*ix + d_aff[1]*iy + d_aff[2] + 0.5 under nvcc's contraction: mul, fma, add, add */
+static inline float aff_coord2d(const float *a, float ix, float iy)
+{
+	float t = a[0] * ix;
+	t = fmaf(a[1], iy, t);
+	t = t + a[2];
+	return (float)((double)t + 0.5);
+}
+
+static inline float sample2d(const float *src, long long sx2, long long sy2, const float *aff, long long x, long long y)
+{
+	float tx = aff_coord2d(aff + 0, (float)x, (float)y);
+	float ty = aff_coord2d(aff + 3, (float)x, (float)y);
+	if (tx > 0 && tx < (float)sx2 && ty > 0 && ty < (float)sy2)
+		return tex2d_linear(src, sx2, sy2, tx, ty);
+	return 0.0f;
+}
+
+/* corr2Dkernel + the two sumcpu calls of corrfunc2D (src/api_subfunc.cu:1014-1036): float
+ * products, summed sequentially in double. */
+void orc_corr2d_sums(const float *target, const float *src, long long sx, long long sy, long long sx2, long long sy2,
+	const float *aff, double *out_sqr, double *out_corr)
+{
+	double sqr = 0, corr = 0;
+	for (long long y = 0; y < sy; y++)
+		for (long long x = 0; x < sx; x++) {
+			float t = sample2d(src, sx2, sy2, aff, x, y);
+			float s = target[x + y * sx];
+			float tt = t * t, st = s * t;
+			sqr += (double)tt;
+			corr += (double)st;
+		}
+	*out_sqr = sqr; *out_corr = corr;
+}
+
+/* K candidates at once (the shift search evaluates thousands) */
+void orc_corr2d_costs(const float *target, const float *src, long long sx, long long sy, long long sx2, long long sy2,
+	const float *affs, int K, float sd_t, float *costs)
+{
+#pragma omp parallel for schedule(dynamic, 8)
+	for (int k = 0; k < K; k++) {
+		double sqr, corr;
+		orc_corr2d_sums(target, src, sx, sy, sx2, sy2, affs + 6 * k, &sqr, &corr);
+		/* corrfunc2D tail + costfunc2D negation, :1034-1035, 1819-1820 */
+		costs[k] = (sqrt(sqr) == 0) ? 2.0f : -((float)(corr / sqrt(sqr)) / sd_t);
+	}
+}
+
+void orc_affine2d(float *out, const float *src, long long sx, long long sy, long long sx2, long long sy2, const float *aff)
+{
+	for (long long y = 0; y < sy; y++)
+		for (long long x = 0; x < sx; x++)
+			out[x + y * sx] = sample2d(src, sx2, sy2, aff, x, y);
+}
+
+/* mean removal as reg2d_* do it on the host (src/api_subfunc.cu:1921-1924): meanValue =
+ * (float)sum / n; out = in + (-meanValue); returns float(sqrt(sum of float squares in double)) */
+float orc_demean2d(float *out, const float *in, long long n)
+{
+	return orc_demean(out, in, n);   /* -(a/b) == (-a)/b in IEEE arithmetic */
+}
+
+void orc_tex2d_samples(float *out, const float *src, long long sx, long long sy, const float *coords, long long n)
+{
+	for (long long i = 0; i < n; i++) out[i] = tex2d_linear(src, sx, sy, coords[2 * i], coords[2 * i + 1]);
+}
