@@ -86,6 +86,24 @@ int milb_dslab_psf_box(milb_dslab_t *h, float *out_slab, const float *d_psf, con
 /* mode 0: out = max(a, 0.01); mode 1: out = (a + b) * 0.5  (src/api_subfunc.cu:3380, 3616-3617) */
 int milb_dslab_elementwise(float *out, const float *a, const float *b, long long n, int mode, void *stream);
 
+/* Exchange folded into the kernels (no all-to-all): with the peers' plane and slab buffers mapped
+ * into this process (milb_ipc_*), the X pass stores every spectrum row straight into the plane
+ * buffer of the rank that owns it and the last plane pass stores every output row straight into the
+ * slab buffer of its owner, over NVLink, tile by tile while the next tile is being transformed.
+ * The caller separates the two phases with a cross-rank barrier.  world <= 8, ny a power of two. */
+int milb_dslab_set_peers(milb_dslab_t *h, int world, int rank, void *const *planes_ptrs, void *const *slab_ptrs,
+	const int *plane_counts);
+/* modes as milb_dslab_xpass; reads the local slab spectrum (modes 1..3), writes the owners' planes (modes 0..2) */
+int milb_dslab_xpass_peer(milb_dslab_t *h, int mode, float *vol_io, const float *aux, const void *spec_slab, void *stream);
+/* S <- F^-1(F(S) * otf) on my planes; the result rows land in the owners' slab buffers */
+int milb_dslab_planes_peer(milb_dslab_t *h, void *S, void *S2, const void *otf, void *stream);
+/* cudaMalloc'd buffers that other ranks can map (cudaIpcGetMemHandle / cudaIpcOpenMemHandle); handle = 64 bytes */
+int milb_dev_alloc(void **out, unsigned long long bytes);
+int milb_dev_free(void *p);
+int milb_ipc_export(void *p, unsigned char *handle64);
+int milb_ipc_open(const unsigned char *handle64, void **out);
+int milb_ipc_close(void *p);
+
 /* Registration ----------------------------------------------------------------------------------
  * A handle owns the mean-removed target and source volumes of one reg3d_affine1 call
  * (src/api_subfunc.cu:2838-2875). */

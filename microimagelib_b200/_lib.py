@@ -67,6 +67,14 @@ CAPI_PROTOS = {
     "milb_dslab_planes": (C.c_int, [_VP, _VP, _VP, _VP, C.c_float, _VP]),
     "milb_dslab_psf_box": (C.c_int, [_VP, _VP, _VP, _U, C.c_int, _VP]),
     "milb_dslab_elementwise": (C.c_int, [_VP, _VP, _VP, _LL, C.c_int, _VP]),
+    "milb_dslab_set_peers": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(_VP), C.POINTER(_VP), _I]),
+    "milb_dslab_xpass_peer": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP]),
+    "milb_dslab_planes_peer": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "milb_dev_alloc": (C.c_int, [C.POINTER(_VP), C.c_ulonglong]),
+    "milb_dev_free": (C.c_int, [_VP]),
+    "milb_ipc_export": (C.c_int, [_VP, C.c_char_p]),
+    "milb_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(_VP)]),
+    "milb_ipc_close": (C.c_int, [_VP]),
     "milb_reg_create": (C.c_int, [C.POINTER(_VP), _U]),
     "milb_reg_destroy": (None, [_VP]),
     "milb_reg_set_images": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP]),

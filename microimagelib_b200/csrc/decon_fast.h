@@ -2,6 +2,17 @@
 #pragma once
 #include <cuda_runtime.h>
 
+// Destination of a spectrum exchange that is folded into a kernel's stores (dslab.cu): the peers'
+// buffers mapped into this process over NVLink (CUDA IPC).  Rank d owns kx planes [p0[d], p0[d+1])
+// of the half spectrum (as whole Y x Z planes) and rows [d*ny, (d+1)*ny) of every real volume.
+struct PeerMap {
+	void *base[8];   // planes buffer of rank d (X pass stores) or slab buffer of rank d (Y-inverse stores)
+	int p0[9];       // first kx plane of rank d; p0[world] = X/2 + 1
+	int world, me;
+	int ny, log2ny;  // rows per rank (a power of two)
+	int Y, Z;        // plane extents in complex elements
+};
+
 struct FastAxisOps {
 	int n = 0;                 // FFT length
 	int lanes = 0;             // pencils per CTA
@@ -15,6 +26,11 @@ struct FastAxisOps {
 	void (*pass_inv)(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st) = nullptr;
 	// planes [n rows][cols]: forward, * otf, inverse, transposed into out [cols rows][n]
 	void (*convT)(float2 *in, float2 *out, const float2 *otf, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st) = nullptr;
+	// xpass whose output spectrum goes straight into the owning ranks' plane buffers (pm.base), M columns of my slab
+	void (*xpass_peer)(int mode, float2 *vol_io, const float2 *aux, const float4 *spec, const float2 *tw, long long M, const PeerMap *pm,
+		cudaStream_t st) = nullptr;
+	// pass_inv on my planes whose output rows go straight into the owning ranks' slab buffers (pm.base)
+	void (*pass_inv_peer)(const float2 *spec, const float2 *tw, int cols, int nplanes, const PeerMap *pm, cudaStream_t st) = nullptr;
 	// in-place forward only, scaled (OTF generation)
 	void (*fwd_scaled)(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, float scale, cudaStream_t st) = nullptr;
 };

@@ -42,6 +42,10 @@ int setup()
 	bad |= optin(k_xpassP<N, XL, XT, XF_RATIO>, SMX);
 	bad |= optin(k_xpassP<N, XL, XT, XF_UPDATE>, SMX);
 	bad |= optin(k_xpassP<N, XL, XT, XF_UPDATE_LAST>, SMX);
+	bad |= optin(k_xpassF<N, L, T, XF_FWD_REAL, true>, SM1);
+	bad |= optin(k_xpassP<N, XL, XT, XF_RATIO, true>, SMX);
+	bad |= optin(k_xpassP<N, XL, XT, XF_UPDATE, true>, SMX);
+	bad |= optin(k_ypassF<N, PL, PT, true, true>, SMP2);
 	bad |= optin(k_ypassT<N, PL, PT>, SMP3);
 	bad |= optin(k_ypassF<N, PL, PT, true>, SMP2);
 	bad |= optin(k_zconvT<N, PL, PT, true>, SMP3);
@@ -70,6 +74,26 @@ void xpass(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const floa
 	case XF_UPDATE: k_xpassF<N, L, T, XF_UPDATE><<<grid, T, SM1, st>>>(vol_io, aux, spec, tw, M); break;
 	default: k_xpassF<N, L, T, XF_UPDATE_LAST><<<grid, T, SM1, st>>>(vol_io, aux, spec, tw, M); break;
 	}
+}
+
+// distributed variants: the output spectrum is stored into the owning ranks' buffers (peer memory)
+void xpass_peer(int mode, float2 *vol_io, const float2 *aux, const float4 *spec, const float2 *tw, long long M, const PeerMap *pm, cudaStream_t st)
+{
+	float4 *sp = const_cast<float4 *>(spec);
+	if (mode == XF_FWD_REAL) {
+		k_xpassF<N, L, T, XF_FWD_REAL, true><<<(unsigned)(M / L), T, SM1, st>>>(vol_io, aux, sp, tw, M, *pm);
+		return;
+	}
+	const int ntiles = (int)(M / XL), cap = (XT <= 512 ? 2 : 1) * g_sms, grid = ntiles < cap ? ntiles : cap;
+	if (mode == XF_RATIO) k_xpassP<N, XL, XT, XF_RATIO, true><<<grid, XT, SMX, st>>>(vol_io, aux, sp, tw, M, ntiles, *pm);
+	else if (mode == XF_UPDATE) k_xpassP<N, XL, XT, XF_UPDATE, true><<<grid, XT, SMX, st>>>(vol_io, aux, sp, tw, M, ntiles, *pm);
+	else k_xpassP<N, XL, XT, XF_UPDATE_LAST><<<grid, XT, SMX, st>>>(vol_io, aux, sp, tw, M, ntiles); // no spectrum output
+}
+
+void pass_inv_peer(const float2 *spec, const float2 *tw, int cols, int nplanes, const PeerMap *pm, cudaStream_t st)
+{
+	const int tiles = (cols / PL) * nplanes;
+	k_ypassF<N, PL, PT, true, true><<<tiles < g_ctas ? tiles : g_ctas, PT, SMP2, st>>>(const_cast<float2 *>(spec), tw, cols, 0, nplanes, *pm);
 }
 
 void passT(const float2 *in, float2 *out, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
@@ -103,6 +127,6 @@ const FastAxisOps *MILB_CAT(milb_fast_ops_, MILB_FAST_N)()
 {
 	static FastAxisOps ops;
 	ops.n = N; ops.lanes = L; ops.setup = setup; ops.xpass = xpass; ops.passT = passT; ops.pass_inv = pass_inv;
-	ops.convT = convT; ops.fwd_scaled = fwd_scaled;
+	ops.convT = convT; ops.fwd_scaled = fwd_scaled; ops.xpass_peer = xpass_peer; ops.pass_inv_peer = pass_inv_peer;
 	return &ops;
 }

@@ -21,6 +21,8 @@ struct milb_dslab {
 	int np = 0;              // my kx-planes
 	float2 *tw[3] = {nullptr, nullptr, nullptr};
 	double *d_sums = nullptr;
+	bool have_peers = false;
+	PeerMap to_planes, to_slabs; // forward exchange (X-pass stores) / backward exchange (Y-inverse stores)
 };
 
 static int upload_tw(float2 **dst, int n)
@@ -124,5 +126,98 @@ extern "C" int milb_dslab_elementwise(float *out, const float *a, const float *b
 	k_slab_elementwise<<<(int)(g > 148 * 16 ? 148 * 16 : g), 256, 0, (cudaStream_t)stream>>>(out, a, b, n, mode);
 	milb_count_launches(1);
 	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+// ---- exchange folded into the kernels' stores (peer memory over NVLink) -----------------------------
+// The all-to-alls of the slab decomposition disappear: the X pass stores each spectrum row straight
+// into the plane buffer of the rank that owns it, and the last plane pass (Y inverse) stores each
+// output row straight into the slab buffer of the rank that owns it.  The caller provides the
+// peers' buffers (opened with milb_ipc_open) and a cross-rank barrier between the two phases.
+extern "C" int milb_dslab_set_peers(milb_dslab_t *h, int world, int rank, void *const *planes_ptrs, void *const *slab_ptrs,
+	const int *plane_counts)
+{
+	if (!h || world < 1 || world > 8 || rank < 0 || rank >= world || !planes_ptrs || !slab_ptrs || !plane_counts) return MILB_ERR_ARG;
+	if (h->ny * world != h->Y || (h->ny & (h->ny - 1)) || h->y0 != rank * h->ny) return MILB_ERR_ARG;
+	if ((h->Z / 2) % milb_fast_ops(h->X)->lanes) return MILB_ERR_SIZE; // an X-pass tile must stay inside one row
+	PeerMap pm;
+	memset(&pm, 0, sizeof pm);
+	pm.world = world; pm.me = rank; pm.ny = h->ny; pm.Y = h->Y; pm.Z = h->Z;
+	for (pm.log2ny = 0; (1 << pm.log2ny) < h->ny; pm.log2ny++) {}
+	int acc = 0;
+	for (int d = 0; d < world; d++) { pm.p0[d] = acc; acc += plane_counts[d]; }
+	for (int d = world; d <= 8; d++) pm.p0[d] = acc;
+	if (acc != h->X / 2 + 1 || plane_counts[rank] != h->np) return MILB_ERR_ARG;
+	h->to_planes = pm;
+	h->to_slabs = pm;
+	for (int d = 0; d < world; d++) {
+		if (!planes_ptrs[d] && plane_counts[d]) return MILB_ERR_ARG;
+		if (!slab_ptrs[d]) return MILB_ERR_ARG;
+		h->to_planes.base[d] = planes_ptrs[d];
+		h->to_slabs.base[d] = slab_ptrs[d];
+	}
+	h->have_peers = true;
+	return MILB_OK;
+}
+
+// X pencils on my slab; modes 0..2 store the output spectrum into the owners' plane buffers
+extern "C" int milb_dslab_xpass_peer(milb_dslab_t *h, int mode, float *vol_io, const float *aux, const void *spec_slab, void *stream)
+{
+	if (!h || !h->have_peers || mode < 0 || mode > 3 || (mode != 0 && !spec_slab)) return MILB_ERR_ARG;
+	const long long M = (long long)h->ny * h->Z / 2;
+	milb_fast_ops(h->X)->xpass_peer(mode, (float2 *)vol_io, (const float2 *)aux, (const float4 *)spec_slab, h->tw[0], M, &h->to_planes,
+		(cudaStream_t)stream);
+	milb_count_launches(1);
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+// S <- F^-1(F(S) * otf) on my planes, the result rows stored into the owners' slab buffers
+extern "C" int milb_dslab_planes_peer(milb_dslab_t *h, void *S, void *S2, const void *otf, void *stream)
+{
+	if (!h || !h->have_peers || !S || !S2 || !otf) return MILB_ERR_ARG;
+	if (h->np == 0) return MILB_OK;
+	cudaStream_t st = (cudaStream_t)stream;
+	const FastAxisOps *oy = milb_fast_ops(h->Y), *oz = milb_fast_ops(h->Z);
+	oy->passT((const float2 *)S, (float2 *)S2, h->tw[1], h->Z, 0, h->np, st);
+	oz->convT((float2 *)S2, (float2 *)S, (const float2 *)otf, h->tw[2], h->Y, 0, h->np, st);
+	oy->pass_inv_peer((const float2 *)S, h->tw[1], h->Z, h->np, &h->to_slabs, st);
+	milb_count_launches(3);
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+// ---- device buffers that can be mapped into the other ranks' processes (CUDA IPC) --------------------
+extern "C" int milb_dev_alloc(void **out, unsigned long long bytes)
+{
+	if (!out || !bytes) return MILB_ERR_ARG;
+	MILB_CUDA_TRY(cudaMalloc(out, bytes));
+	return MILB_OK;
+}
+extern "C" int milb_dev_free(void *p)
+{
+	if (p) MILB_CUDA_TRY(cudaFree(p));
+	return MILB_OK;
+}
+extern "C" int milb_ipc_export(void *p, unsigned char *handle64)
+{
+	if (!p || !handle64) return MILB_ERR_ARG;
+	static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+	cudaIpcMemHandle_t hd;
+	MILB_CUDA_TRY(cudaIpcGetMemHandle(&hd, p));
+	memcpy(handle64, &hd, 64);
+	return MILB_OK;
+}
+extern "C" int milb_ipc_open(const unsigned char *handle64, void **out)
+{
+	if (!handle64 || !out) return MILB_ERR_ARG;
+	cudaIpcMemHandle_t hd;
+	memcpy(&hd, handle64, 64);
+	MILB_CUDA_TRY(cudaIpcOpenMemHandle(out, hd, cudaIpcMemLazyEnablePeerAccess));
+	return MILB_OK;
+}
+extern "C" int milb_ipc_close(void *p)
+{
+	if (p) MILB_CUDA_TRY(cudaIpcCloseMemHandle(p));
 	return MILB_OK;
 }

@@ -15,6 +15,7 @@
 //   k_xpassF  : the fused X pencils: C2R inverse -> ratio | update+clamp -> R2C forward.
 // Run plane-chunk by plane-chunk the three plane passes keep their intermediates in the 126 MB L2.
 #pragma once
+#include "decon_fast.h"
 #include "fft_core.h"
 
 #define SMALLVALUE_FAST 0.01f // src/api_subfunc.cu:24
@@ -340,10 +341,13 @@ k_ypassT(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *
 	}
 }
 
-// Y pass, in place, plain: plane [N rows][Z], lanes along z
-template <int N, int L, int T, bool INV>
+// Y pass, in place, plain: plane [N rows][Z], lanes along z.
+// PEER: the output row y of plane kx is not written back in place but into the slab buffer of the
+// rank that owns row y -- slab_d[kx][y - d*ny][z] -- through peer memory (NVLink): the backward
+// exchange of the slab-decomposed FFT rides on this kernel's stores, tile by tile.
+template <int N, int L, int T, bool INV, bool PEER = false>
 __global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
-k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes)
+k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes, PeerMap pm = PeerMap())
 {
 	using P = FastPlan<N>;
 	using G = TileGeom<N, L>;
@@ -362,16 +366,29 @@ k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int 
 		if (tn < ntiles) tile_load_async<N, L, T>(sm + (cur ^ 1) * G::elems, ptr_of(tn), Z);
 		cp_async_commit();
 		float2 *tile = sm + cur * G::elems;
-		float2 *p = ptr_of(t);
-		auto gs = [p, Z](int r, int l, float2 v) { p[(long long)r * Z + l] = v; };
-		if (INV) {
+		if constexpr (PEER) {
+			static_assert(INV, "the exchange follows the inverse pass");
+			const long long kx = pm.p0[pm.me] + plane0 + t / tpp;
+			const long long off = kx * pm.ny * (long long)Z + (long long)(t % tpp) * L;
+			auto ps = [&pm, off, Z](int r, int l, float2 v) {
+				const int d = r >> pm.log2ny;
+				((float2 *)pm.base[d])[off + (long long)(r & (pm.ny - 1)) * Z + l] = v;
+			};
 			inv_but_last<N, L, T, false>(tile, tw);
-			sstage_to<N, L, T, P::r0, N, true>(tile, tw, gs);
+			sstage_to<N, L, T, P::r0, N, true>(tile, tw, ps);
 		} else {
-			fwd_but_last<N, L, T>(tile, tw);
-			fwd_last<N, L, T>(tile, tw, gs);
+			float2 *p = ptr_of(t);
+			auto gs = [p, Z](int r, int l, float2 v) { p[(long long)r * Z + l] = v; };
+			if (INV) {
+				inv_but_last<N, L, T, false>(tile, tw);
+				sstage_to<N, L, T, P::r0, N, true>(tile, tw, gs);
+			} else {
+				fwd_but_last<N, L, T>(tile, tw);
+				fwd_last<N, L, T>(tile, tw, gs);
+			}
 		}
 	}
+	if constexpr (PEER) __threadfence_system();
 }
 
 // Z pass on the transposed planes: in [N = Z rows][Yc], lanes along ky'.
@@ -436,13 +453,31 @@ k_zconvT(float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__rest
 	}
 }
 
+// Where row k of the tile's output spectrum goes.  !PEER: my own half spectrum, spec[k*M + col0 ..].
+// PEER: the plane buffer of the rank that owns plane k -- planes_d[k - p0[d]][y0 + y][z] -- through
+// peer memory, so the forward exchange of the slab-decomposed FFT rides on the X pass's stores.
+template <bool PEER>
+__device__ __forceinline__ float4 *spec_row_dst(float4 *spec, long long M, long long col0, int k, const PeerMap &pm)
+{
+	if constexpr (!PEER) return spec + (long long)k * M + col0;
+	else {
+		int d = 0;
+#pragma unroll
+		for (int i = 1; i < 8; i++) d += (i < pm.world && k >= pm.p0[i]) ? 1 : 0;
+		const int zp = pm.Z / 2;                       // float4 (column pairs) per row
+		const long long y = pm.me * (long long)pm.ny + col0 / zp;
+		return (float4 *)pm.base[d] + ((long long)(k - pm.p0[d]) * pm.Y + y) * zp + col0 % zp;
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // Fused X pencils (see fft_kernels.cuh k_xpass for the mode semantics).
 enum { XF_FWD_REAL = 0, XF_RATIO = 1, XF_UPDATE = 2, XF_UPDATE_LAST = 3 };
 
-template <int N, int L, int T, int MODE>
+template <int N, int L, int T, int MODE, bool PEER = false>
 __global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
-k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M)
+k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M,
+	PeerMap pm = PeerMap())
 {
 	using P = FastPlan<N>;
 	static_assert(P::r0 == 8 && (N / 8) * L == T, "stage 0 must be one radix-8 butterfly per thread");
@@ -513,8 +548,9 @@ k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 		const int k = idx / L, l = idx % L;
 		const float2 ck = tile[fast_pos<N>(k) * L + l];
 		const float2 cn = tile[fast_pos<N>((N - k) % N) * L + l];
-		spec[(long long)k * M + col0 + l] = split_pair(ck, cn);
+		spec_row_dst<PEER>(spec, M, col0, k, pm)[l] = split_pair(ck, cn);
 	}
+	if constexpr (PEER) __threadfence_system();
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -525,9 +561,10 @@ k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 //   AL aux landing buffer      N x L float2         (A for RATIO, E for UPDATE; consumed by stage 0)
 // As soon as a landing buffer has been consumed the next tile's rows are already requested, so the
 // spectrum and aux loads of tile t+1 overlap the butterflies of tile t.
-template <int N, int L, int T, int MODE>
+template <int N, int L, int T, int MODE, bool PEER = false>
 __global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
-k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M, int ntiles)
+k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M, int ntiles,
+	PeerMap pm = PeerMap())
 {
 	using P = FastPlan<N>;
 	static_assert(P::r0 == 8 && (N / 8) * L == T, "stage 0 must be one radix-8 butterfly per thread");
@@ -616,7 +653,8 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 			const int k = idx / L, l = idx % L;
 			const float2 ck = W[fast_pos<N>(k) * L + l];
 			const float2 cn = W[fast_pos<N>((N - k) % N) * L + l];
-			spec[(long long)k * M + col0 + l] = split_pair(ck, cn);
+			spec_row_dst<PEER>(spec, M, col0, k, pm)[l] = split_pair(ck, cn);
 		}
 	}
+	if constexpr (PEER) __threadfence_system();
 }

@@ -7,16 +7,28 @@ One process per GPU (torch.distributed, NCCL).  Decomposition (DESIGN.md section
   half spectrum, "planes"   rank r owns a contiguous range of kx planes   [np_r][Y][Z]
   OTFs                      plane layout (each rank keeps only its planes)
 
-Per convolution: fused X pencils locally on the slab (csrc/fft_fast.cuh k_xpassP) -> all-to-all ->
-Y / Z passes and OTF product locally on whole planes -> all-to-all -> X pencils.  Two all-to-alls
-per convolution, eight per dual-view iteration, each moving (P-1)/P of the local spectrum
-(4*N*(P-1)/P^2 bytes per GPU).  All arithmetic is done by the same sm_100a kernels as the
-single-GPU path through include/milb_capi.h (milb_dslab_*); torch provides device memory, the
-stream and the NCCL all-to-all.  The reference has no multi-GPU path at all.
+Per convolution: fused X pencils locally on the slab (csrc/fft_fast.cuh k_xpassP) -> exchange ->
+Y / Z passes and OTF product locally on whole planes -> exchange -> X pencils.  Two exchanges per
+convolution, eight per dual-view iteration, each moving (P-1)/P of the local spectrum
+(4*N*(P-1)/P^2 bytes per GPU).  Two implementations of the exchange:
+
+  fused (default)  the exchange is folded into the kernels: with every rank's slab and plane
+                   buffers mapped into every process (CUDA IPC over NVLink), the X pass stores each
+                   spectrum row straight into the plane buffer of the rank that owns it and the
+                   last plane pass stores each result row straight into its owner's slab buffer --
+                   the transfer overlaps the butterflies tile by tile, there is no all-to-all and
+                   no re-layout copy; a one-element NCCL all-reduce is the barrier between phases.
+  nccl             torch.distributed.all_to_all_single + two re-layout copies (the baseline; also
+                   used for the one-time OTF generation).
+
+All arithmetic is done by the same sm_100a kernels as the single-GPU path through
+include/milb_capi.h (milb_dslab_*); torch provides device memory, the stream and NCCL.  The
+reference has no multi-GPU path at all.
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -84,10 +96,33 @@ class SlabLayout:
         return slab
 
 
-class DistDecon:
-    """Distributed single- or dual-view RL deconvolution of one FFT-box-sized volume."""
+class _SharedBuf:
+    """cudaMalloc'd float32 buffer that other ranks can map (CUDA IPC); torch sees it through
+    __cuda_array_interface__ (torch does not own the memory)."""
 
-    def __init__(self, fft_shape, nviews=1, group=None, device=None):
+    def __init__(self, lib, nfloats):
+        self.lib = lib
+        self.n = int(nfloats)
+        self.ptr = C.c_void_p()
+        _check(lib.milb_dev_alloc(C.byref(self.ptr), self.n * 4), "milb_dev_alloc")
+        self.__cuda_array_interface__ = {"shape": (self.n,), "typestr": "<f4", "data": (self.ptr.value, False), "version": 2}
+
+    def handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(self.lib.milb_ipc_export(self.ptr, buf), "milb_ipc_export")
+        return buf.raw
+
+    def free(self):
+        if self.ptr:
+            self.lib.milb_dev_free(self.ptr)
+            self.ptr = C.c_void_p()
+
+
+class DistDecon:
+    """Distributed single- or dual-view RL deconvolution of one FFT-box-sized volume.
+    fused=None picks the fused exchange unless MILB_DIST_FUSED=0."""
+
+    def __init__(self, fft_shape, nviews=1, group=None, device=None, fused=None):
         import torch
         import torch.distributed as dist
         self.torch = torch
@@ -99,24 +134,80 @@ class DistDecon:
         self.L = SlabLayout(fft_shape, self.rank, self.world)
         L = self.L
         self.nviews = nviews
+        self.fused = (os.environ.get("MILB_DIST_FUSED", "1") != "0") if fused is None else bool(fused)
+        # the fused exchange needs <= 8 ranks, power-of-two slabs, and X-pass tiles (4096 / X column pairs)
+        # that do not straddle rows of Z / 2 pairs; anything else takes the all-to-all path
+        if self.fused and (self.world > 8 or (L.ny & (L.ny - 1)) or min(L.counts) < 1 or (L.Z // 2) % max(4096 // L.X, 1)):
+            self.fused = False
         self._h = C.c_void_p()
         size = (C.c_uint * 3)(L.Z, L.Y, L.X)
         _check(self.lib.milb_dslab_create(C.byref(self._h), size, L.y0, L.ny, L.np), "milb_dslab_create")
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.A = [torch.empty((L.X, L.ny, L.Z), **f32) for _ in range(nviews)]
         self.E = torch.empty((L.X, L.ny, L.Z), **f32)
-        self.slab = torch.empty((L.nplanes, L.ny, L.Z, 2), **f32)
         npmax = max(L.counts)
-        self.planes = torch.empty((max(L.np, 1), L.Y, L.Z, 2), **f32)
+        self._shared, self._opened = [], []
+        if self.fused:
+            self._setup_peers()
+        else:
+            self.slab = torch.empty((L.nplanes, L.ny, L.Z, 2), **f32)
+            self.planes = torch.empty((max(L.np, 1), L.Y, L.Z, 2), **f32)
         self.planes2 = torch.empty((max(L.np, 1), L.Z, L.Y, 2), **f32)
         self.scratch = torch.empty(max(self.world * npmax * L.row, 1), **f32)
         self.otf = [[torch.empty((max(L.np, 1), L.Z, L.Y, 2), **f32) for _ in range(2)] for _ in range(nviews)]
         self.nfft = L.X * L.Y * L.Z
 
+    def _setup_peers(self):
+        """allocate my slab / plane buffers as IPC-shareable memory, map everybody else's, tell the kernels"""
+        torch = self.torch
+        import torch.distributed as dist
+        L = self.L
+        slab_b = _SharedBuf(self.lib, L.nplanes * L.ny * L.Z * 2)
+        planes_b = _SharedBuf(self.lib, max(L.np, 1) * L.Y * L.Z * 2)
+        self._shared = [slab_b, planes_b]
+        self.slab = torch.as_tensor(slab_b, device=self.dev).view(L.nplanes, L.ny, L.Z, 2)
+        self.planes = torch.as_tensor(planes_b, device=self.dev).view(max(L.np, 1), L.Y, L.Z, 2)
+        slab_ptrs = (C.c_void_p * self.world)()
+        planes_ptrs = (C.c_void_p * self.world)()
+        if self.world > 1:
+            mine = (slab_b.handle(), planes_b.handle())
+            everyone = [None] * self.world
+            dist.all_gather_object(everyone, mine, group=self.group)
+        for r in range(self.world):
+            if r == self.rank:
+                slab_ptrs[r], planes_ptrs[r] = slab_b.ptr.value, planes_b.ptr.value
+                continue
+            for k, arr in ((0, slab_ptrs), (1, planes_ptrs)):
+                p = C.c_void_p()
+                _check(self.lib.milb_ipc_open(everyone[r][k], C.byref(p)), "milb_ipc_open")
+                self._opened.append(p)
+                arr[r] = p.value
+        counts = (C.c_int * self.world)(*L.counts)
+        _check(self.lib.milb_dslab_set_peers(self._h, self.world, self.rank, planes_ptrs, slab_ptrs, counts), "milb_dslab_set_peers")
+        self._flag = torch.zeros(1, dtype=torch.float32, device=self.dev)
+        self._barrier()
+
+    def _barrier(self):
+        """stream-ordered cross-rank barrier: nobody's later kernels start before everybody's earlier ones finished"""
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self._flag, group=self.group)
+
     def close(self):
         if self._h:
+            if self.fused and self.world > 1:
+                self.torch.cuda.synchronize()
+                self._barrier()                       # nobody still writes into a buffer that is about to go away
+                self.torch.cuda.synchronize()
             self.lib.milb_dslab_destroy(self._h)
             self._h = C.c_void_p()
+            for p in self._opened:
+                self.lib.milb_ipc_close(p)
+            self._opened = []
+            self.slab = self.planes = None
+            for b in self._shared:
+                b.free()
+            self._shared = []
 
     def __del__(self):
         try:
@@ -170,6 +261,17 @@ class DistDecon:
         assert tuple(t.shape) == tuple(self.A[view].shape)
         _check(self.lib.milb_dslab_elementwise(self._p(self.A[view]), self._p(t), None, t.numel(), 0, self._st()), "clamp")
 
+    def _xpass_peer(self, mode, vol_io, aux):
+        _check(self.lib.milb_dslab_xpass_peer(self._h, mode, self._p(vol_io), self._p(aux), self._p(self.slab), self._st()), "milb_dslab_xpass_peer")
+
+    def _convolve_fused(self, otf):
+        """planes (filled by everybody's X pass) -> * otf -> everybody's slabs; the exchange rides on the kernels' stores"""
+        self._barrier()                                   # every rank's X pass has landed in my planes
+        if self.L.np:
+            _check(self.lib.milb_dslab_planes_peer(self._h, self._p(self.planes), self._p(self.planes2), self._p(otf), self._st()),
+                   "milb_dslab_planes_peer")
+        self._barrier()                                   # every rank's result rows have landed in my slab
+
     def run(self, iterations):
         """decon_singleview_OTF1 / decon_dualview_OTF1 loop (src/api_subfunc.cu:3404-3416, 3634-3660)."""
         nv = self.nviews
@@ -178,6 +280,17 @@ class DistDecon:
         else:
             _check(self.lib.milb_dslab_elementwise(self._p(self.E), self._p(self.A[0]), self._p(self.A[1]), self.E.numel(), 1, self._st()), "init")
         if iterations == 0:
+            return self.E
+        if self.fused:
+            self._barrier()                               # the previous call's readers of `planes` are done everywhere
+            self._xpass_peer(0, self.E, None)
+            for it in range(iterations):
+                for v in range(nv):
+                    self._convolve_fused(self.otf[v][0])
+                    self._xpass_peer(1, None, self.A[v])
+                    self._convolve_fused(self.otf[v][1])
+                    last = it == iterations - 1 and v == nv - 1
+                    self._xpass_peer(3 if last else 2, self.E, None)
             return self.E
         self._xpass(0, self.E, None)
         for it in range(iterations):

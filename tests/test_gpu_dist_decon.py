@@ -38,13 +38,15 @@ def _single_gpu(shape, dual, iters):
     return out
 
 
+@pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("dual", [False, True])
-def test_one_rank_distributed_path_equals_single_gpu_path(dual):
+def test_one_rank_distributed_path_equals_single_gpu_path(dual, fused):
     import torch
     from microimagelib_b200.dist_decon import DistDecon
-    shape = (64, 128, 64)
+    shape = (64, 128, 128)
     a, b, pa, pb = _inputs(shape, dual)
-    dd = DistDecon(shape, 2 if dual else 1)
+    dd = DistDecon(shape, 2 if dual else 1, fused=fused)
+    assert dd.fused == fused
     dd.set_psf(0, pa)
     dd.set_image(0, a)
     if dual:
@@ -68,22 +70,26 @@ torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 shape, dual, iters = (64, 128, 128), True, 3
 a, b, pa, pb = T._inputs(shape, dual)
-dd = DistDecon(shape, 2)
-L = dd.L
-dd.set_psf(0, pa); dd.set_psf(1, pb)
-dd.set_image(0, a[:, L.y0:L.y0 + L.ny, :]); dd.set_image(1, b[:, L.y0:L.y0 + L.ny, :])
-E = dd.run(iters)
-parts = [torch.empty_like(E) for _ in range(dist.get_world_size())]
-dist.all_gather(parts, E)
-if rank == 0:
-    got = torch.cat(parts, dim=1).cpu().numpy()
-    ref = T._single_gpu(shape, dual, iters)
-    print("DIST_EQUAL", bool(np.array_equal(got, ref)), float(np.abs(got - ref).max()))
+ref = T._single_gpu(shape, dual, iters) if rank == 0 else None
+for fused in (False, True):
+    dd = DistDecon(shape, 2, fused=fused)
+    assert dd.fused == fused
+    L = dd.L
+    dd.set_psf(0, pa); dd.set_psf(1, pb)
+    dd.set_image(0, a[:, L.y0:L.y0 + L.ny, :]); dd.set_image(1, b[:, L.y0:L.y0 + L.ny, :])
+    for rep in range(2):                         # twice: the second run reuses the mapped buffers
+        E = dd.run(iters)
+    parts = [torch.empty_like(E) for _ in range(dist.get_world_size())]
+    dist.all_gather(parts, E)
+    if rank == 0:
+        got = torch.cat(parts, dim=1).cpu().numpy()
+        print("DIST_EQUAL", "fused" if fused else "nccl", bool(np.array_equal(got, ref)), float(np.abs(got - ref).max()))
+    dd.close()
 dist.destroy_process_group()
 """ % (ROOT, ROOT)
 
 
-def test_two_ranks_over_nccl(tmp_path):
+def test_two_ranks_nccl_and_fused_exchange(tmp_path):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
@@ -97,5 +103,7 @@ def test_two_ranks_over_nccl(tmp_path):
            "--master-port", str(port), str(script)]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
-    line = [l for l in r.stdout.splitlines() if l.startswith("DIST_EQUAL")][-1]
-    assert line.split()[1] == "True", line
+    lines = [l for l in r.stdout.splitlines() if l.startswith("DIST_EQUAL")]
+    assert len(lines) == 2, r.stdout[-1500:] + r.stderr[-3000:]
+    for line in lines:                            # the NCCL all-to-all path and the fused peer-store path
+        assert line.split()[2] == "True", line
