@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=1)
     ap.add_argument("--views", type=int, default=2)
     ap.add_argument("--modes", default="fused,nccl", help="comma list of exchange implementations to time")
+    ap.add_argument("--profile", action="store_true", help="rank 0 prints a per-kernel time table (torch.profiler / CUPTI) of 2 iterations per mode")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -87,6 +88,16 @@ def main():
         ms_iter = timed(lambda: dd.run(args.iters), 1) / args.iters
         res[mode] = {"ms_per_iteration": ms_iter}
         checks[mode] = dd.E.double().sum().item()      # same inputs, same kernels: the two modes must agree exactly
+        if args.profile:
+            from torch.profiler import ProfilerActivity, profile
+            if world > 1:
+                dist.barrier()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                dd.run(2)
+                torch.cuda.synchronize()
+            if rank == 0:
+                print(f"---- {mode}: kernels of 2 iterations on rank 0", flush=True)
+                print(prof.key_averages().table(sort_by="cuda_time_total", row_limit=14, max_name_column_width=60), flush=True)
         if mode == "nccl":
             def exchange_only():
                 L.to_planes(dd.slab, dd.planes, dd.scratch)

@@ -30,7 +30,10 @@ struct FastAxisOps {
 	void (*xpass_peer)(int mode, float2 *vol_io, const float2 *aux, const float4 *spec, const float2 *tw, long long M, const PeerMap *pm,
 		cudaStream_t st) = nullptr;
 	// pass_inv on my planes whose output rows go straight into the owning ranks' slab buffers (pm.base)
-	void (*pass_inv_peer)(const float2 *spec, const float2 *tw, int cols, int nplanes, const PeerMap *pm, cudaStream_t st) = nullptr;
+	void (*pass_inv_peer)(const float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, const PeerMap *pm, cudaStream_t st) = nullptr;
+	// persistent-grid override for the plane passes (0 = one CTA per SM): lets two plane kernels share the
+	// machine side by side (dslab.cu runs the link-bound peer-store pass next to the next chunk's transforms)
+	int *grid_cap = nullptr;
 	// in-place forward only, scaled (OTF generation)
 	void (*fwd_scaled)(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, float scale, cudaStream_t st) = nullptr;
 };

@@ -26,6 +26,8 @@ constexpr size_t SMP3 = (size_t)(3 * TileGeom<N, PL>::elems + N) * sizeof(float2
 constexpr int XL = (MILB_X_WIDE ? 8192 : 4096) / N, XT = MILB_X_WIDE ? 1024 : 512;
 constexpr size_t SMX = (size_t)(2 * N * XL + 2 * (N / 2 + 1) * XL + N) * sizeof(float2);
 int g_ctas = 0, g_sms = 0; // persistent grids
+int g_cap = 0;              // override (FastAxisOps::grid_cap)
+inline int plane_grid(int tiles) { const int c = (g_cap > 0 && g_cap < g_ctas) ? g_cap : g_ctas; return tiles < c ? tiles : c; }
 
 template <typename K> int optin(K k, size_t bytes)
 {
@@ -90,16 +92,16 @@ void xpass_peer(int mode, float2 *vol_io, const float2 *aux, const float4 *spec,
 	else k_xpassP<N, XL, XT, XF_UPDATE_LAST><<<grid, XT, SMX, st>>>(vol_io, aux, sp, tw, M, ntiles); // no spectrum output
 }
 
-void pass_inv_peer(const float2 *spec, const float2 *tw, int cols, int nplanes, const PeerMap *pm, cudaStream_t st)
+void pass_inv_peer(const float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, const PeerMap *pm, cudaStream_t st)
 {
 	const int tiles = (cols / PL) * nplanes;
-	k_ypassF<N, PL, PT, true, true><<<tiles < g_ctas ? tiles : g_ctas, PT, SMP2, st>>>(const_cast<float2 *>(spec), tw, cols, 0, nplanes, *pm);
+	k_ypassF<N, PL, PT, true, true><<<plane_grid(tiles), PT, SMP2, st>>>(const_cast<float2 *>(spec), tw, cols, plane0, nplanes, *pm);
 }
 
 void passT(const float2 *in, float2 *out, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
 {
 	const int tiles = (cols / PL) * nplanes;
-	k_ypassT<N, PL, PT><<<tiles < g_ctas ? tiles : g_ctas, PT, SMP3, st>>>(in, out, tw, cols, plane0, nplanes);
+	k_ypassT<N, PL, PT><<<plane_grid(tiles), PT, SMP3, st>>>(in, out, tw, cols, plane0, nplanes);
 }
 
 void pass_inv(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
@@ -111,7 +113,7 @@ void pass_inv(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes,
 void convT(float2 *in, float2 *out, const float2 *otf, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
 {
 	const int tiles = (cols / PL) * nplanes;
-	k_zconvT<N, PL, PT, true><<<tiles < g_ctas ? tiles : g_ctas, PT, SMP3, st>>>(in, out, otf, tw, cols, plane0, nplanes, 1.0f);
+	k_zconvT<N, PL, PT, true><<<plane_grid(tiles), PT, SMP3, st>>>(in, out, otf, tw, cols, plane0, nplanes, 1.0f);
 }
 
 void fwd_scaled(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, float scale, cudaStream_t st)
@@ -127,6 +129,6 @@ const FastAxisOps *MILB_CAT(milb_fast_ops_, MILB_FAST_N)()
 {
 	static FastAxisOps ops;
 	ops.n = N; ops.lanes = L; ops.setup = setup; ops.xpass = xpass; ops.passT = passT; ops.pass_inv = pass_inv;
-	ops.convT = convT; ops.fwd_scaled = fwd_scaled; ops.xpass_peer = xpass_peer; ops.pass_inv_peer = pass_inv_peer;
+	ops.convT = convT; ops.fwd_scaled = fwd_scaled; ops.xpass_peer = xpass_peer; ops.pass_inv_peer = pass_inv_peer; ops.grid_cap = &g_cap;
 	return &ops;
 }

@@ -23,6 +23,11 @@ struct milb_dslab {
 	double *d_sums = nullptr;
 	bool have_peers = false;
 	PeerMap to_planes, to_slabs; // forward exchange (X-pass stores) / backward exchange (Y-inverse stores)
+	// plane stage of the fused exchange: chunks of planes, the link-bound peer-store pass of chunk c on a
+	// side stream next to the transforms of chunk c + 1
+	cudaStream_t side = nullptr;
+	cudaEvent_t ev_z[8] = {}, ev_done = nullptr;
+	int chunks = 4, side_ctas = 48;
 };
 
 static int upload_tw(float2 **dst, int n)
@@ -63,6 +68,10 @@ extern "C" void milb_dslab_destroy(milb_dslab_t *h)
 	for (int i = 0; i < 3; i++)
 		if (h->tw[i]) cudaFree(h->tw[i]);
 	if (h->d_sums) cudaFree(h->d_sums);
+	if (h->side) cudaStreamDestroy(h->side);
+	for (int i = 0; i < 8; i++)
+		if (h->ev_z[i]) cudaEventDestroy(h->ev_z[i]);
+	if (h->ev_done) cudaEventDestroy(h->ev_done);
 	delete h;
 }
 
@@ -156,6 +165,15 @@ extern "C" int milb_dslab_set_peers(milb_dslab_t *h, int world, int rank, void *
 		h->to_planes.base[d] = planes_ptrs[d];
 		h->to_slabs.base[d] = slab_ptrs[d];
 	}
+	if (!h->side) {
+		MILB_CUDA_TRY(cudaStreamCreateWithFlags(&h->side, cudaStreamNonBlocking));
+		for (int i = 0; i < 8; i++) MILB_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_z[i], cudaEventDisableTiming));
+		MILB_CUDA_TRY(cudaEventCreateWithFlags(&h->ev_done, cudaEventDisableTiming));
+	}
+	if (const char *e = getenv("MILB_DSLAB_CHUNKS")) h->chunks = atoi(e);
+	if (const char *e = getenv("MILB_DSLAB_SIDE_CTAS")) h->side_ctas = atoi(e);
+	if (h->chunks < 1) h->chunks = 1;
+	if (h->chunks > 8) h->chunks = 8;
 	h->have_peers = true;
 	return MILB_OK;
 }
@@ -179,10 +197,40 @@ extern "C" int milb_dslab_planes_peer(milb_dslab_t *h, void *S, void *S2, const 
 	if (h->np == 0) return MILB_OK;
 	cudaStream_t st = (cudaStream_t)stream;
 	const FastAxisOps *oy = milb_fast_ops(h->Y), *oz = milb_fast_ops(h->Z);
-	oy->passT((const float2 *)S, (float2 *)S2, h->tw[1], h->Z, 0, h->np, st);
-	oz->convT((float2 *)S2, (float2 *)S, (const float2 *)otf, h->tw[2], h->Y, 0, h->np, st);
-	oy->pass_inv_peer((const float2 *)S, h->tw[1], h->Z, h->np, &h->to_slabs, st);
-	milb_count_launches(3);
+	int sms = 148;
+	{
+		int dev = 0;
+		cudaGetDevice(&dev);
+		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+	}
+	const int C = (h->chunks <= h->np) ? h->chunks : h->np;
+	if (C <= 1 || h->side_ctas <= 0 || h->side_ctas >= sms) {
+		oy->passT((const float2 *)S, (float2 *)S2, h->tw[1], h->Z, 0, h->np, st);
+		oz->convT((float2 *)S2, (float2 *)S, (const float2 *)otf, h->tw[2], h->Y, 0, h->np, st);
+		oy->pass_inv_peer((const float2 *)S, h->tw[1], h->Z, 0, h->np, &h->to_slabs, st);
+		milb_count_launches(3);
+		MILB_CUDA_TRY(cudaGetLastError());
+		return MILB_OK;
+	}
+	// Chunked: Y-forward and Z-conv of chunk c on the caller's stream, the Y-inverse whose stores ARE the
+	// backward exchange on the side stream.  That pass is bound by NVLink egress, not by the SMs, so it
+	// gets side_ctas of them and the next chunk's transforms get the rest; only the first transforms and
+	// the last exchange pass have the machine to themselves.
+	int *cap_y = oy->grid_cap, *cap_z = oz->grid_cap;
+	for (int c = 0; c < C; c++) {
+		const int p0 = (int)((long long)h->np * c / C), p1 = (int)((long long)h->np * (c + 1) / C);
+		*cap_y = *cap_z = (c == 0) ? 0 : sms - h->side_ctas;
+		oy->passT((const float2 *)S, (float2 *)S2, h->tw[1], h->Z, p0, p1 - p0, st);
+		oz->convT((float2 *)S2, (float2 *)S, (const float2 *)otf, h->tw[2], h->Y, p0, p1 - p0, st);
+		MILB_CUDA_TRY(cudaEventRecord(h->ev_z[c], st));
+		MILB_CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_z[c], 0));
+		*cap_y = (c == C - 1) ? 0 : h->side_ctas;
+		oy->pass_inv_peer((const float2 *)S, h->tw[1], h->Z, p0, p1 - p0, &h->to_slabs, h->side);
+	}
+	*cap_y = *cap_z = 0;
+	MILB_CUDA_TRY(cudaEventRecord(h->ev_done, h->side));
+	MILB_CUDA_TRY(cudaStreamWaitEvent(st, h->ev_done, 0));
+	milb_count_launches(3 * C);
 	MILB_CUDA_TRY(cudaGetLastError());
 	return MILB_OK;
 }
