@@ -62,9 +62,11 @@ __global__ void __launch_bounds__(256) k_zncc(const float *__restrict__ tgt, con
 		if (x >= sx || y >= sy) continue;
 		const float fx = (float)x, fy = (float)y;
 		const int z_end = min(sz, (bz + 1) * REG_ZT);
-		for (int z = bz * REG_ZT; z < z_end; z++) {
+		const long long pl = (long long)sx * sy;
+		const float *tp = tgt + (x + (long long)y * sx + (long long)(bz * REG_ZT) * pl);
+		for (int z = bz * REG_ZT; z < z_end; z++, tp += pl) {
 			const float fz = (float)z;
-			const float t = tgt[x + (long long)y * sx + (long long)z * sx * sy];
+			const float t = *tp;
 #pragma unroll
 			for (int k = 0; k < K; k++) {
 				const float *a = aff.m[k];

@@ -24,14 +24,22 @@ __device__ __forceinline__ float tex3d_linear(const float *__restrict__ v, int s
 	split_coord(tx, ix, a);
 	split_coord(ty, iy, b);
 	split_coord(tz, iz, c);
-	const int x0 = min(max(ix, 0), sx - 1), x1 = min(max(ix + 1, 0), sx - 1);
-	const int y0 = min(max(iy, 0), sy - 1), y1 = min(max(iy + 1, 0), sy - 1);
-	const int z0 = min(max(iz, 0), sz - 1), z1 = min(max(iz + 1, 0), sz - 1);
-	const int pl = sx * sy; // volumes stay below 2^31 voxels
-	const float *p00 = v + y0 * sx + z0 * pl, *p10 = v + y1 * sx + z0 * pl;
-	const float *p01 = v + y0 * sx + z1 * pl, *p11 = v + y1 * sx + z1 * pl;
-	const float t000 = __ldg(p00 + x0), t100 = __ldg(p00 + x1), t010 = __ldg(p10 + x0), t110 = __ldg(p10 + x1);
-	const float t001 = __ldg(p01 + x0), t101 = __ldg(p01 + x1), t011 = __ldg(p11 + x0), t111 = __ldg(p11 + x1);
+	float t000, t100, t010, t110, t001, t101, t011, t111;
+	const int pl = sx * sy; // volumes stay below 2^31 voxels: 32-bit element indices
+	if ((unsigned)ix < (unsigned)(sx - 1) && (unsigned)iy < (unsigned)(sy - 1) && (unsigned)iz < (unsigned)(sz - 1)) {
+		// interior (almost every sample): one base address, the eight corners at fixed offsets
+		const float *p = v + (ix + iy * sx + iz * pl), *py = p + sx, *pz = p + pl, *pyz = pz + sx;
+		t000 = __ldg(p); t100 = __ldg(p + 1); t010 = __ldg(py); t110 = __ldg(py + 1);
+		t001 = __ldg(pz); t101 = __ldg(pz + 1); t011 = __ldg(pyz); t111 = __ldg(pyz + 1);
+	} else {
+		// within half a texel of a face: clamp addressing
+		const int x0 = min(max(ix, 0), sx - 1), x1 = min(max(ix + 1, 0), sx - 1);
+		const int y0 = min(max(iy, 0), sy - 1), y1 = min(max(iy + 1, 0), sy - 1);
+		const int z0 = min(max(iz, 0), sz - 1), z1 = min(max(iz + 1, 0), sz - 1);
+		const int r00 = y0 * sx + z0 * pl, r10 = y1 * sx + z0 * pl, r01 = y0 * sx + z1 * pl, r11 = y1 * sx + z1 * pl;
+		t000 = __ldg(v + (r00 + x0)); t100 = __ldg(v + (r00 + x1)); t010 = __ldg(v + (r10 + x0)); t110 = __ldg(v + (r10 + x1));
+		t001 = __ldg(v + (r01 + x0)); t101 = __ldg(v + (r01 + x1)); t011 = __ldg(v + (r11 + x0)); t111 = __ldg(v + (r11 + x1));
+	}
 	const int a0 = 256 - a, c0 = 256 - c;
 	// x-z products (dx = 0 ties down: +127, dx = 1 ties up: +128), then the y split
 	const int w0z0 = (a0 * c0 + 127) >> 8, w1z0 = (a * c0 + 128) >> 8;
