@@ -162,6 +162,19 @@ def run_reference(args, shape, rank, world):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pin this process to the CPUs next to its GPU (what `numactl` would do for a user), so that the
+    pinned host buffers of the end-to-end leg are allocated on the NUMA node the GPU hangs off."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        return sorted(os.sched_getaffinity(0))[:2] + [len(os.sched_getaffinity(0))]
+    except Exception as e:  # best effort
+        return str(e)
+
+
 def main():
     args = parse()
     shape = tuple(int(s) for s in args.shape.split(","))
@@ -179,6 +192,7 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
+    numa = bind_to_gpu_numa_node(local_rank)   # the end-to-end leg moves 2 x 256 MiB over PCIe per step
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -238,7 +252,19 @@ def main():
         tt = torch.tensor([dt], dtype=torch.float64, device=torch.device("cuda", local_rank))
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        xt = torch.empty(shape, dtype=torch.float32, device="cuda")
+        hp = torch.from_numpy(h_img)
+        xt.copy_(hp)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        xt.copy_(hp, non_blocking=True)
+        torch.cuda.synchronize()
+        h2d_gbps = n_img * 4 / (time.perf_counter() - t0) / 1e9
+        del xt
         e2e = {"value": n_fft * args.iters * args.steps * world / float(tt.item()), "unit": "voxel-iters/s",
+               "pcie_h2d_GBps_pinned": h2d_gbps, "cpu_affinity": numa,
+               "last_call_records_ms": {"init": float(rec[6]) * 1e3, "cache_check_h2d_pad": float(rec[7]) * 1e3,
+                                        "loop_crop_d2h": float(rec[8]) * 1e3, "total": float(rec[9]) * 1e3},
                "h2d_bytes_per_step": int(n_img * 4), "d2h_bytes_per_step": int(n_img * 4),
                "ms_per_step": 1e3 * float(tt.item()) / args.steps,
                "call": "libapi.decon_singleview(host float32 image, host PSF) -> host float32 volume; OTFs cached across calls"}
@@ -262,6 +288,19 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "launch": "one single-view RL iteration = 6 plane-pass launches + 2 fused X-pass launches",
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_VOXEL_ITER * n_fft, "ms_per_launch": ms_iter}
+    if world == 1:
+        try:                                             # per-kernel break-down: kernel-level bytes / measured launch time
+            kms = d.time_kernels(5, stream=stream)
+            nspec = float(d.fft_shape[0] // 2 + 1) * d.fft_shape[1] * d.fft_shape[2]
+            rows = [("k_ypassT (Y forward, transposing)", 16 * nspec, kms[0], 2), ("k_zconvT (Z forward * OTF, Z inverse)", 24 * nspec, kms[1], 2),
+                    ("k_ypassF (Y inverse)", 16 * nspec, kms[2], 2), ("k_xpassP ratio (C2R, A/T, R2C)", 16 * nspec + 4 * n_fft, kms[3], 1),
+                    ("k_xpassP update (C2R, E*T clamp, R2C)", 16 * nspec + 8 * n_fft, kms[4], 1)]
+            roofline["kernels"] = [{"kernel": k, "launches_per_iteration": n, "bytes_per_launch": b, "ms_per_launch": float(ms),
+                                    "GBps": b / (float(ms) * 1e-3) / 1e9, "frac_of_peak": b / (float(ms) * 1e-3) / 1e9 / peak}
+                                   for k, b, ms, n in rows]
+            roofline["kernels_note"] = "kernel-level HBM bytes (what each launch must read + write), CUDA events around every launch"
+        except Exception as e:
+            roofline["kernels"] = {"error": str(e)}
     yard = None
     if world == 1 and not args.no_yardstick:
         try:

@@ -67,6 +67,11 @@ int milb_decon_set_chunk_planes(milb_decon_t *h, int planes);
 int milb_decon_run_cufft_yardstick(milb_decon_t *h, int iterations, int const_init, void *stream,
 	float *loop_ms /* out: CUDA-event time of the iteration loop only */);
 
+/* per-kernel timing of the loop (CUDA events around every launch, `reps` iterations of view 0): ms5 =
+ * average ms per launch of {Y-forward, Z-conv, Y-inverse, X ratio, X update}.  bench.py's roofline
+ * break-down; power-of-two boxes only. */
+int milb_decon_time_kernels(milb_decon_t *h, int reps, float *ms5, void *stream);
+
 /* Distributed slab FFT (one volume over P GPUs) -----------------------------------------------------
  * Local pieces of the slab-decomposed loop; the all-to-all between them is
  * issued by the caller over NCCL (microimagelib_b200/dist_decon.py).  Power-of-two boxes only.

@@ -511,6 +511,51 @@ int milb_decon_run(milb_decon_t *h, int iterations, int const_init, void *stream
 	return MILB_OK;
 }
 
+// Per-kernel timing of the loop (bench.py's roofline break-down): `reps` iterations of view 0 with CUDA
+// events around every launch; ms5 = average ms per launch of
+// {Y-forward (k_ypassT), Z-conv (k_zconvT), Y-inverse (k_ypassF), X ratio (k_xpassP), X update (k_xpassP)}.
+// Power-of-two boxes only (the fast kernels); the estimate E is advanced like by milb_decon_run.
+int milb_decon_time_kernels(milb_decon_t *h, int reps, float *ms5, void *stream)
+{
+	if (!h || reps < 1 || !ms5 || !h->fast || !h->have_psf[0] || !h->have_img[0]) return MILB_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream;
+	const FastAxisOps *oy = milb_fast_ops(h->Y), *oz = milb_fast_ops(h->Z);
+	const int planes = h->X / 2 + 1;
+	cudaEvent_t ev[9];
+	for (auto &e : ev) MILB_CUDA_TRY(cudaEventCreate(&e));
+	double acc[5] = {0, 0, 0, 0, 0};
+	launch_xpass<X_FWD_REAL>(h, h->E, nullptr, st);
+	for (int r = 0; r < reps; r++) {
+		int k = 0;
+		MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+		for (int half = 0; half < 2; half++) {
+			const float2 *otf = half ? h->otf_bp[0] : h->otf[0];
+			oy->passT(h->S, h->S2, h->py.d_tw, h->Z, 0, planes, st);
+			MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+			oz->convT(h->S2, h->S, otf, h->pz.d_tw, h->Y, 0, planes, st);
+			MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+			oy->pass_inv(h->S, h->py.d_tw, h->Z, 0, planes, st);
+			MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+			if (half == 0) launch_xpass<X_RATIO>(h, nullptr, h->A[0], st);
+			else launch_xpass<X_UPDATE>(h, h->E, nullptr, st);
+			MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+		}
+		milb_count_launches(6);
+		MILB_CUDA_TRY(cudaStreamSynchronize(st));
+		float t[8];
+		for (int i = 0; i < 8; i++) MILB_CUDA_TRY(cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]));
+		acc[0] += 0.5 * (t[0] + t[4]);
+		acc[1] += 0.5 * (t[1] + t[5]);
+		acc[2] += 0.5 * (t[2] + t[6]);
+		acc[3] += t[3];
+		acc[4] += t[7];
+	}
+	for (auto &e : ev) cudaEventDestroy(e);
+	for (int i = 0; i < 5; i++) ms5[i] = (float)(acc[i] / reps);
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
 int milb_decon_get_result(milb_decon_t *h, float *out, int on_device, void *stream)
 {
 	if (!h || !out) return MILB_ERR_ARG;

@@ -347,7 +347,7 @@ k_ypassT(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *
 // exchange of the slab-decomposed FFT rides on this kernel's stores, tile by tile.
 template <int N, int L, int T, bool INV, bool PEER = false>
 __global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
-k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes, PeerMap pm = PeerMap())
+k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes, const __grid_constant__ PeerMap pm = PeerMap())
 {
 	using P = FastPlan<N>;
 	using G = TileGeom<N, L>;
@@ -477,7 +477,7 @@ enum { XF_FWD_REAL = 0, XF_RATIO = 1, XF_UPDATE = 2, XF_UPDATE_LAST = 3 };
 template <int N, int L, int T, int MODE, bool PEER = false>
 __global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
 k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M,
-	PeerMap pm = PeerMap())
+	const __grid_constant__ PeerMap pm = PeerMap())
 {
 	using P = FastPlan<N>;
 	static_assert(P::r0 == 8 && (N / 8) * L == T, "stage 0 must be one radix-8 butterfly per thread");
@@ -564,7 +564,7 @@ k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 template <int N, int L, int T, int MODE, bool PEER = false>
 __global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
 k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M, int ntiles,
-	PeerMap pm = PeerMap())
+	const __grid_constant__ PeerMap pm = PeerMap())
 {
 	using P = FastPlan<N>;
 	static_assert(P::r0 == 8 && (N / 8) * L == T, "stage 0 must be one radix-8 butterfly per thread");

@@ -103,6 +103,12 @@ class Decon:
                "milb_decon_run_cufft_yardstick")
         return float(ms.value)
 
+    def time_kernels(self, reps=5, stream=None):
+        """average ms per launch of (Y-forward, Z-conv, Y-inverse, X ratio, X update), CUDA events around every launch"""
+        ms = np.zeros(5, np.float32)
+        _check(self.lib.milb_decon_time_kernels(self._h, int(reps), ms.ctypes.data_as(_F), _stream(stream)), "milb_decon_time_kernels")
+        return ms
+
     def set_chunk_planes(self, planes):
         _check(self.lib.milb_decon_set_chunk_planes(self._h, int(planes)), "milb_decon_set_chunk_planes")
 
