@@ -84,6 +84,56 @@ __device__ __forceinline__ void fstage(const float2 *__restrict__ tw, LD ld, ST 
 	}
 }
 
+// Register-resident twiddles.  In the persistent plane kernels a thread executes the same butterflies
+// (same row q of every sub-transform) for every tile, so the R-1 twiddles of each of its butterflies are
+// loaded from the table once, before the tile loop, instead of R-1 shared-memory broadcasts per
+// butterfly, stage and tile (16 % of the kernels' shared-memory wavefronts).
+template <int N, int L, int T, int R, int NS> struct StageTw {
+	static constexpr int M = NS / R, NB = (N / R) * L, IT = (NB + T - 1) / T;
+	float2 w[IT][R - 1];
+	__device__ __forceinline__ void load(const float2 *__restrict__ tw)
+	{
+#pragma unroll
+		for (int it = 0; it < IT; it++) {
+			const int q = ((threadIdx.x + it * T) / L) % M;
+#pragma unroll
+			for (int j = 1; j < R; j++) w[it][j - 1] = tw[q * (N / NS) * j];
+		}
+	}
+};
+
+// fstage with the twiddles taken from a StageTw (same butterfly-to-thread mapping as fstage)
+template <int N, int L, int T, int R, int NS, bool INV, class LD, class ST>
+__device__ __forceinline__ void fstage_rt(const StageTw<N, L, T, R, NS> &tw, LD ld, ST st)
+{
+	constexpr int M = NS / R;
+	constexpr int NB = (N / R) * L;
+	constexpr int IT = (NB + T - 1) / T;
+	static_assert(M > 1, "the last stage has no twiddles");
+#pragma unroll
+	for (int it = 0; it < IT; it++) {
+		const int bl = threadIdx.x + it * T;
+		if ((NB % T) != 0 && bl >= NB) break;
+		const int lane = bl % L, b = bl / L;
+		const int blk = b / M, q = b % M;
+		const int base = blk * NS + q;
+		float2 v[R];
+#pragma unroll
+		for (int j = 0; j < R; j++) v[j] = ld(base + j * M, lane);
+		if (INV) {
+#pragma unroll
+			for (int j = 1; j < R; j++) v[j] = cmulc(v[j], tw.w[it][j - 1]);
+		}
+		fbfly<R, INV>(v);
+		if (!INV) {
+#pragma unroll
+			for (int j = 1; j < R; j++) v[j] = cmul(v[j], tw.w[it][j - 1]);
+		}
+#pragma unroll
+		for (int j = 0; j < R; j++) st(base + j * M, lane, v[j]);
+	}
+}
+
 // forward: stage 0 reads through ld0, the last stage writes through stl, the rest is in `tile`
 template <int N, int L, int T, class LD, class ST>
 __device__ __forceinline__ void fwd_stages(float2 *tile, const float2 *tw, LD ld0, ST stl)
@@ -312,16 +362,68 @@ template <int N, int L, int T, bool SKIP_FIRST> __device__ __forceinline__ void 
 	}
 }
 
+// Twiddles of all twiddled stages of one plane-pass thread (stages 0 .. S-2; the last stage has none).
+// Kept for up to three stages (N <= 512): 2 x 7 complex per butterfly; N = 1024 would need 34 and
+// stays on the shared-memory table.
+template <int N, int L, int T> struct PlaneTw {
+	using P = FastPlan<N>;
+	static constexpr bool kUse = (P::S <= 3);
+	static constexpr int ns1 = N / P::r0;
+	StageTw<N, L, T, P::r0, N> s0;
+	StageTw<N, L, T, (P::S >= 3 ? P::r1 : 2), (P::S >= 3 ? ns1 : 4)> s1; // unused (dummy shape) when S == 2
+	__device__ __forceinline__ void load(const float2 *__restrict__ tw)
+	{
+		s0.load(tw);
+		if (P::S >= 3) s1.load(tw);
+	}
+};
+
+template <int N, int L, int T, int R, int NS, bool INV, class ST>
+__device__ __forceinline__ void sstage_rt_to(float2 *tile, const StageTw<N, L, T, R, NS> &tw, ST st)
+{
+	fstage_rt<N, L, T, R, NS, INV>(tw, [tile](int r, int l) { return tile[prow<L>(r) * L + l]; }, st);
+}
+template <int N, int L, int T, int R, int NS, bool INV> __device__ __forceinline__ void sstage_rt(float2 *tile, const StageTw<N, L, T, R, NS> &tw)
+{
+	sstage_rt_to<N, L, T, R, NS, INV>(tile, tw, [tile](int r, int l, float2 v) { tile[prow<L>(r) * L + l] = v; });
+}
+// forward stages 0..S-2 in place (S <= 3), register twiddles
+template <int N, int L, int T> __device__ __forceinline__ void fwd_but_last_rt(float2 *tile, const PlaneTw<N, L, T> &pt)
+{
+	using P = FastPlan<N>;
+	sstage_rt<N, L, T, P::r0, N, false>(tile, pt.s0);
+	__syncthreads();
+	if constexpr (P::S >= 3) {
+		sstage_rt<N, L, T, P::r1, N / P::r0, false>(tile, pt.s1);
+		__syncthreads();
+	}
+}
+// inverse stages S-2..1 in place (the caller did stage S-1, or does it here), register twiddles; stage 0 is left to the caller
+template <int N, int L, int T, bool SKIP_FIRST> __device__ __forceinline__ void inv_but_last_rt(float2 *tile, const float2 *tw, const PlaneTw<N, L, T> &pt)
+{
+	using P = FastPlan<N>;
+	constexpr int ns1 = N / P::r0, ns2 = ns1 / P::r1;
+	if constexpr (P::S == 3) {
+		if (!SKIP_FIRST) { sstage<N, L, T, P::r2, ns2, true>(tile, tw); __syncthreads(); } // last-stage butterflies: no twiddles
+		sstage_rt<N, L, T, P::r1, ns1, true>(tile, pt.s1);
+		__syncthreads();
+	} else {
+		if (!SKIP_FIRST) { sstage<N, L, T, P::r1, ns1, true>(tile, tw); __syncthreads(); }
+	}
+}
+
 // ------------------------------------------------------------------------------------------------
 // Y forward, transposing:  in plane [N = Y rows][Z]  ->  out plane [Z rows][N = Y]
 template <int N, int L, int T>
-__global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
+__global__ void __launch_bounds__(T, (N * L <= 4096) ? 2 : 1)
 k_ypassT(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes)
 {
 	using G = TileGeom<N, L>;
 	extern __shared__ float2 sm[];
 	float2 *tile2 = sm + 2 * G::elems, *tw = sm + 3 * G::elems;
 	load_tw<N>(tw, g_tw);
+	PlaneTw<N, L, T> pt;
+	if constexpr (PlaneTw<N, L, T>::kUse) pt.load(g_tw);
 	const int tpp = Z / L, ntiles = nplanes * tpp;
 	auto src_of = [&](int t) { return in + (long long)(t / tpp + plane0) * N * Z + (long long)(t % tpp) * L; };
 	int t = blockIdx.x, cur = 0;
@@ -334,7 +436,8 @@ k_ypassT(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *
 		if (tn < ntiles) tile_load_async<N, L, T>(sm + (cur ^ 1) * G::elems, src_of(tn), Z);
 		cp_async_commit();
 		float2 *tile = sm + cur * G::elems;
-		fwd_but_last<N, L, T>(tile, tw);
+		if constexpr (PlaneTw<N, L, T>::kUse) fwd_but_last_rt<N, L, T>(tile, pt);
+		else fwd_but_last<N, L, T>(tile, tw);
 		fwd_last<N, L, T>(tile, tw, [tile2](int r, int l, float2 v) { tile2[swz<L>(r, l)] = v; });
 		__syncthreads();
 		store_transposed<N, L, T>(tile2, out + (long long)(t / tpp + plane0) * N * Z + (long long)(t % tpp) * L * N, N);
@@ -346,7 +449,7 @@ k_ypassT(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *
 // rank that owns row y -- slab_d[kx][y - d*ny][z] -- through peer memory (NVLink): the backward
 // exchange of the slab-decomposed FFT rides on this kernel's stores, tile by tile.
 template <int N, int L, int T, bool INV, bool PEER = false>
-__global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
+__global__ void __launch_bounds__(T, (N * L <= 4096) ? 2 : 1)
 k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes, const __grid_constant__ PeerMap pm = PeerMap())
 {
 	using P = FastPlan<N>;
@@ -354,6 +457,11 @@ k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int 
 	extern __shared__ float2 sm[];
 	float2 *tw = sm + 2 * G::elems;
 	load_tw<N>(tw, g_tw);
+	PlaneTw<N, L, T> pt;
+	// measured: register twiddles pay in the transposing passes (-3 %) but not here, where the 28 extra
+	// live registers push this kernel into spills (94.8 -> 97.9 us)
+	constexpr bool kRt = false && PlaneTw<N, L, T>::kUse;
+	if constexpr (kRt) pt.load(g_tw);
 	const int tpp = Z / L, ntiles = nplanes * tpp;
 	auto ptr_of = [&](int t) { return spec + (long long)(t / tpp + plane0) * N * Z + (long long)(t % tpp) * L; };
 	int t = blockIdx.x, cur = 0;
@@ -374,16 +482,27 @@ k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int 
 				const int d = r >> pm.log2ny;
 				((float2 *)pm.base[d])[off + (long long)(r & (pm.ny - 1)) * Z + l] = v;
 			};
-			inv_but_last<N, L, T, false>(tile, tw);
-			sstage_to<N, L, T, P::r0, N, true>(tile, tw, ps);
+			if constexpr (kRt) {
+				inv_but_last_rt<N, L, T, false>(tile, tw, pt);
+				sstage_rt_to<N, L, T, P::r0, N, true>(tile, pt.s0, ps);
+			} else {
+				inv_but_last<N, L, T, false>(tile, tw);
+				sstage_to<N, L, T, P::r0, N, true>(tile, tw, ps);
+			}
 		} else {
 			float2 *p = ptr_of(t);
 			auto gs = [p, Z](int r, int l, float2 v) { p[(long long)r * Z + l] = v; };
 			if (INV) {
-				inv_but_last<N, L, T, false>(tile, tw);
-				sstage_to<N, L, T, P::r0, N, true>(tile, tw, gs);
+				if constexpr (kRt) {
+					inv_but_last_rt<N, L, T, false>(tile, tw, pt);
+					sstage_rt_to<N, L, T, P::r0, N, true>(tile, pt.s0, gs);
+				} else {
+					inv_but_last<N, L, T, false>(tile, tw);
+					sstage_to<N, L, T, P::r0, N, true>(tile, tw, gs);
+				}
 			} else {
-				fwd_but_last<N, L, T>(tile, tw);
+				if constexpr (kRt) fwd_but_last_rt<N, L, T>(tile, pt);
+				else fwd_but_last<N, L, T>(tile, tw);
 				fwd_last<N, L, T>(tile, tw, gs);
 			}
 		}
@@ -395,7 +514,7 @@ k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int 
 //   CONV : forward, * otf (same layout as `in`), inverse, transposed out [Yc rows][N = Z]
 //   !CONV: forward only, in place, scaled (OTF generation)
 template <int N, int L, int T, bool CONV>
-__global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
+__global__ void __launch_bounds__(T, (N * L <= 4096) ? 2 : 1)
 k_zconvT(float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__restrict__ otf, const float2 *__restrict__ g_tw, int Yc,
 	int plane0, int nplanes, float scale)
 {
@@ -404,6 +523,9 @@ k_zconvT(float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__rest
 	extern __shared__ float2 sm[];
 	float2 *tile2 = sm + 2 * G::elems, *tw = sm + 3 * G::elems; // tile2 doubles as the OTF landing buffer
 	load_tw<N>(tw, g_tw);
+	PlaneTw<N, L, T> pt;
+	constexpr bool kRt = PlaneTw<N, L, T>::kUse;
+	if constexpr (kRt) pt.load(g_tw);
 	const int tpp = Yc / L, ntiles = nplanes * tpp;
 	auto off_of = [&](int t) { return (long long)(t / tpp + plane0) * N * Yc + (long long)(t % tpp) * L; };
 	int t = blockIdx.x, cur = 0;
@@ -418,7 +540,8 @@ k_zconvT(float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__rest
 		if (tn < ntiles) tile_load_async<N, L, T>(sm + (cur ^ 1) * G::elems, in + off_of(tn), Yc);
 		cp_async_commit();
 		float2 *tile = sm + cur * G::elems;
-		fwd_but_last<N, L, T>(tile, tw);
+		if constexpr (kRt) fwd_but_last_rt<N, L, T>(tile, pt);
+		else fwd_but_last<N, L, T>(tile, tw);
 		if (!CONV) {
 			float2 *p = in + off_of(t);
 			fwd_last<N, L, T>(tile, tw, [p, Yc, scale](int r, int l, float2 v) { p[(long long)r * Yc + l] = make_float2(v.x * scale, v.y * scale); });
@@ -446,8 +569,13 @@ k_zconvT(float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__rest
 			}
 			__syncthreads();
 		}
-		inv_but_last<N, L, T, true>(tile, tw);
-		sstage_to<N, L, T, P::r0, N, true>(tile, tw, [tile2](int r, int l, float2 v) { tile2[swz<L>(r, l)] = v; });
+		if constexpr (kRt) {
+			inv_but_last_rt<N, L, T, true>(tile, tw, pt);
+			sstage_rt_to<N, L, T, P::r0, N, true>(tile, pt.s0, [tile2](int r, int l, float2 v) { tile2[swz<L>(r, l)] = v; });
+		} else {
+			inv_but_last<N, L, T, true>(tile, tw);
+			sstage_to<N, L, T, P::r0, N, true>(tile, tw, [tile2](int r, int l, float2 v) { tile2[swz<L>(r, l)] = v; });
+		}
 		__syncthreads();
 		store_transposed<N, L, T>(tile2, out + (long long)(t / tpp + plane0) * N * Yc + (long long)(t % tpp) * L * N, N);
 	}

@@ -23,5 +23,5 @@ r = device.Reg(shape); r.set_images(t, t); r.prepare()
 for _ in range(3): r.cost(m)
 torch.cuda.synchronize()
 PY
-ncu --set full --clock-control none --import-source on -k regex:'k_zncc<' -s 1 -c 1 -o gpurun_out/prof_zncc_$TAG -f python /tmp/prof_reg.py > gpurun_out/prof_zncc_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:k_zncc -s 2 -c 1 -o gpurun_out/prof_zncc_$TAG -f python /tmp/prof_reg.py > gpurun_out/prof_zncc_$TAG.log 2>&1
 ls -la gpurun_out/*$TAG*
