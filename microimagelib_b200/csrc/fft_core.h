@@ -108,6 +108,35 @@ template <bool INV> MILB_HD void bfly8(float2 *v)
 	v[1] = a4; v[3] = a5; v[5] = a6; v[7] = a7;
 }
 
+// radix-16: one radix-2 layer with the w16^j twiddles on the odd half, then two radix-8 butterflies
+template <bool INV> MILB_HD void bfly16(float2 *v)
+{
+	const float h = 0.70710678118654752440f, c1 = 0.92387953251128675613f, s1 = 0.38268343236508977173f;
+	float2 a[8], b[8];
+#pragma unroll
+	for (int j = 0; j < 8; j++) {
+		a[j] = cadd(v[j], v[j + 8]);
+		b[j] = csub(v[j], v[j + 8]);
+	}
+	// b[j] *= w16^j (forward: exp(-2 pi i j / 16); inverse: the conjugate)
+	const float2 w1 = make_float2(c1, INV ? s1 : -s1), w3 = make_float2(s1, INV ? c1 : -c1);
+	const float2 w5 = make_float2(-s1, INV ? c1 : -c1), w7 = make_float2(-c1, INV ? s1 : -s1);
+	b[1] = cmul(b[1], w1);
+	b[2] = cscale(cadd(b[2], mul_mi<INV>(b[2])), h);
+	b[3] = cmul(b[3], w3);
+	b[4] = mul_mi<INV>(b[4]);
+	b[5] = cmul(b[5], w5);
+	b[6] = cscale(csub(mul_mi<INV>(b[6]), b[6]), h);
+	b[7] = cmul(b[7], w7);
+	bfly8<INV>(a); // X[2k]
+	bfly8<INV>(b); // X[2k+1]
+#pragma unroll
+	for (int k = 0; k < 8; k++) {
+		v[2 * k] = a[k];
+		v[2 * k + 1] = b[k];
+	}
+}
+
 // naive length-r DFT using the axis twiddle table (r divides n): w_r^t = tw[t * (n / r)]
 template <bool INV> MILB_HD void bfly_generic(float2 *v, int r, const float2 *tw, int n)
 {

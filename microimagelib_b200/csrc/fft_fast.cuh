@@ -30,7 +30,17 @@ MILB_FAST_PLAN(64, 2, 8, 8, 1, 1)
 MILB_FAST_PLAN(128, 3, 8, 4, 4, 1)
 MILB_FAST_PLAN(256, 3, 8, 8, 4, 1)
 MILB_FAST_PLAN(512, 3, 8, 8, 8, 1)
+// MILB_PLAN1024_R16: three stages (one radix-16, fft_core.h bfly16) instead of four.  Measured at
+// 1024x1024x512: Y inverse 1100 -> 885 us, but Y forward 1178 -> 1248 and Z conv 1924 -> 2173 us
+// (register pressure in the transposing passes): 13.28 -> 13.49 ms per iteration, so it stays off.
+#ifndef MILB_PLAN1024_R16
+#define MILB_PLAN1024_R16 0
+#endif
+#if MILB_PLAN1024_R16
+MILB_FAST_PLAN(1024, 3, 8, 16, 8, 1)
+#else
 MILB_FAST_PLAN(1024, 4, 8, 8, 4, 4)
+#endif
 
 // position of frequency k after the forward stages (same rule as AxisPlanTables::pos)
 template <int N> __device__ __forceinline__ int fast_pos(int k)
@@ -47,9 +57,10 @@ template <int N> __device__ __forceinline__ int fast_pos(int k)
 
 template <int R, bool INV> __device__ __forceinline__ void fbfly(float2 (&v)[R])
 {
-	if (R == 2) bfly2<INV>(v[0], v[1]);
-	else if (R == 4) bfly4<INV>(v[0], v[1], v[2], v[3]);
-	else bfly8<INV>(v);
+	if constexpr (R == 2) bfly2<INV>(v[0], v[1]);
+	else if constexpr (R == 4) bfly4<INV>(v[0], v[1], v[2], v[3]);
+	else if constexpr (R == 8) bfly8<INV>(v);
+	else bfly16<INV>(v);
 }
 
 // One stage of radix R on sub-transforms of length NS for the whole tile (N rows x L lanes),
@@ -367,7 +378,7 @@ template <int N, int L, int T, bool SKIP_FIRST> __device__ __forceinline__ void 
 // stays on the shared-memory table.
 template <int N, int L, int T> struct PlaneTw {
 	using P = FastPlan<N>;
-	static constexpr bool kUse = (P::S <= 3);
+	static constexpr bool kUse = (P::S <= 3) && (P::r1 <= 8);
 	static constexpr int ns1 = N / P::r0;
 	StageTw<N, L, T, P::r0, N> s0;
 	StageTw<N, L, T, (P::S >= 3 ? P::r1 : 2), (P::S >= 3 ? ns1 : 4)> s1; // unused (dummy shape) when S == 2

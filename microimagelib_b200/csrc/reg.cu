@@ -64,7 +64,7 @@ __global__ void __launch_bounds__(256) k_zncc(const float *__restrict__ tgt, con
 		const int z_end = min(sz, (bz + 1) * REG_ZT);
 		const long long pl = (long long)sx * sy;
 		const float *tp = tgt + (x + (long long)y * sx + (long long)(bz * REG_ZT) * pl);
-		for (int z = bz * REG_ZT; z < z_end; z++, tp += pl) {
+		for (int z = bz * REG_ZT; z < z_end; z++, tp += pl) { // (unrolling by 2 costs occupancy: 0.40 -> 0.45 ms)
 			const float fz = (float)z;
 			const float t = *tp;
 #pragma unroll
