@@ -1,0 +1,120 @@
+// Host-side I/O pipeline of spimFusionBatch: read-ahead of the next time point's two TIFF stacks and
+// write-behind of the output stacks, so that disk I/O and the 16-bit <-> float conversions overlap
+// the GPU work of the current time point.  The reference reads, computes and writes strictly in
+// sequence (src/spim_fusion_batch.cpp:668-940); files, names and contents are unchanged here.
+// MILB_PIPELINE=0 restores the sequential behaviour.
+#pragma once
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+
+#include "cli_common.h"
+
+inline bool pipeline_enabled()
+{
+	const char *e = getenv("MILB_PIPELINE");
+	return !(e && e[0] == '0');
+}
+
+// Reads (path1, path2) in the background; take() hands the stacks over if they are the ones asked for.
+class ReadAhead {
+public:
+	~ReadAhead() { join(); }
+	void start(const std::string &p1, const std::string &p2, size_t n1, size_t n2)
+	{
+		join();
+		if (!pipeline_enabled() || !fexists((char *)p1.c_str()) || !fexists((char *)p2.c_str())) return;
+		k1_ = p1; k2_ = p2;
+		b1_.resize(n1); b2_.resize(n2);
+		busy_ = true;
+		th_ = std::thread([this] {
+			readtifstack(b1_.data(), (char *)k1_.c_str(), s1_);
+			readtifstack(b2_.data(), (char *)k2_.c_str(), s2_);
+		});
+	}
+	// true: raw1/raw2 and the size triples now hold the prefetched stacks
+	bool take(const std::string &p1, const std::string &p2, std::vector<float> &raw1, std::vector<float> &raw2, unsigned int *s1, unsigned int *s2)
+	{
+		if (!busy_) return false;
+		join();
+		if (p1 != k1_ || p2 != k2_) return false;
+		raw1.swap(b1_); raw2.swap(b2_);
+		memcpy(s1, s1_, sizeof s1_); memcpy(s2, s2_, sizeof s2_);
+		return true;
+	}
+
+private:
+	void join()
+	{
+		if (th_.joinable()) th_.join();
+		busy_ = false;
+	}
+	std::thread th_;
+	bool busy_ = false;
+	std::string k1_, k2_;
+	std::vector<float> b1_, b2_;
+	unsigned int s1_[3] = {0, 0, 0}, s2_[3] = {0, 0, 0};
+};
+
+// writetifstack on a worker thread; the data is copied at submission so the caller can reuse its buffer.
+class WriteBehind {
+public:
+	WriteBehind() { if (pipeline_enabled()) th_ = std::thread([this] { run(); }); }
+	~WriteBehind() { drain(); }
+	void write(const std::string &path, const float *data, const unsigned int *size, unsigned short bits)
+	{
+		if (!th_.joinable()) { // sequential mode
+			unsigned int s[3] = {size[0], size[1], size[2]};
+			writetifstack((char *)path.c_str(), (float *)data, s, bits);
+			return;
+		}
+		Job j;
+		j.path = path; j.bits = bits;
+		memcpy(j.size, size, sizeof j.size);
+		j.data.assign(data, data + voxels(size));
+		std::unique_lock<std::mutex> lk(mu_);
+		cv_space_.wait(lk, [this] { return q_.size() < 4; }); // bound the host memory held by pending writes
+		q_.push_back(std::move(j));
+		cv_work_.notify_one();
+	}
+	// waits until everything submitted so far is on disk (end of the batch)
+	void drain()
+	{
+		if (!th_.joinable()) return;
+		{
+			std::unique_lock<std::mutex> lk(mu_);
+			stop_ = true;
+			cv_work_.notify_one();
+		}
+		th_.join();
+	}
+
+private:
+	struct Job {
+		std::string path;
+		std::vector<float> data;
+		unsigned int size[3];
+		unsigned short bits;
+	};
+	void run()
+	{
+		for (;;) {
+			Job j;
+			{
+				std::unique_lock<std::mutex> lk(mu_);
+				cv_work_.wait(lk, [this] { return stop_ || !q_.empty(); });
+				if (q_.empty()) return;
+				j = std::move(q_.front());
+				q_.pop_front();
+				cv_space_.notify_one();
+			}
+			writetifstack((char *)j.path.c_str(), j.data.data(), j.size, j.bits);
+		}
+	}
+	std::thread th_;
+	std::mutex mu_;
+	std::condition_variable cv_work_, cv_space_;
+	std::deque<Job> q_;
+	bool stop_ = false;
+};

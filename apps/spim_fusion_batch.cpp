@@ -10,6 +10,7 @@
 #include <ctime>
 
 #include "fusion_common.h"
+#include "io_pipeline.h"
 
 static void usage(const char *app, bool full)
 {
@@ -32,7 +33,7 @@ static void usage(const char *app, bool full)
 		"32: <int>     Bit depth of the outputs (16 or 32)", "33: <int>     Query GPUs first (0/1)", "34: <int>     GPU device",
 		"35/36: <file> (optional) backward projectors 1 / 2"};
 	for (const char *l : lines) printf("\t%s\n", l);
-	printf("\nEnvironment: MILB_SHARD=<rank>/<world> processes every world-th time point on GPU <arg 34> + rank.\n");
+	printf("\nEnvironment: MILB_SHARD=<rank>/<world> processes every world-th time point on GPU <arg 34> + rank * MILB_SHARD_DEVICE_STRIDE (default 1);\n             MILB_PIPELINE=0 disables the read-ahead / write-behind I/O threads.\n");
 }
 
 static std::string join(const std::string &a, const std::string &b) { return a + b; }
@@ -80,7 +81,9 @@ int main(int argc, char **argv)
 			fprintf(stderr, "*** registration mode 2 chains matrices between time points and cannot be sharded\n");
 			return 1;
 		}
-		rs.deviceNum += shardRank;
+		int stride = 1; // GPU of shard r = <arg 34> + r * stride; MILB_SHARD_DEVICE_STRIDE=0 keeps every shard on <arg 34>
+		if (const char *ds = getenv("MILB_SHARD_DEVICE_STRIDE")) stride = atoi(ds);
+		rs.deviceNum += shardRank * stride;
 	}
 	if (query) queryDevice();
 
@@ -144,6 +147,8 @@ int main(int argc, char **argv)
 	if (saveXProj || saveYProj || saveZProj) mp2d.resize(sx * sy + sy * sz + sz * sx);
 	float regRec[11] = {0}, deconRec[10] = {0};
 	long long slot = 0; // ordinal of the time point in the batch, for sharding
+	ReadAhead ahead;     // next time point's input stacks (io_pipeline.h)
+	WriteBehind behind;  // output stacks written while the next time point is processed
 
 	for (int num = numStart; num <= numEnd; num += numStep) {
 		if (regMode == 0) rs.regChoice = 0;
@@ -156,10 +161,22 @@ int main(int argc, char **argv)
 		logf("a", "\n*** Image time point number: " + n + "\n");
 		const std::string f1 = dir1 + base1 + n + ".tif", f2 = dir2 + base2 + n + ".tif";
 		printf("... Preprocessing ...\n");
-		readtifstack(raw1.data(), (char *)f1.c_str(), tmp);
+		unsigned int tmp2[3];
+		if (!ahead.take(f1, f2, raw1, raw2, tmp, tmp2)) {
+			raw1.resize(voxels(g.in1)); raw2.resize(voxels(g.in2));
+			readtifstack(raw1.data(), (char *)f1.c_str(), tmp);
+			readtifstack(raw2.data(), (char *)f2.c_str(), tmp2);
+		}
 		if (memcmp(tmp, g.in1, sizeof tmp)) { printf("\t Input image 1 size does not match !!!\n"); return 1; }
-		readtifstack(raw2.data(), (char *)f2.c_str(), tmp);
-		if (memcmp(tmp, g.in2, sizeof tmp)) { printf("\t Input image 2 size does not match !!!\n"); return 1; }
+		if (memcmp(tmp2, g.in2, sizeof tmp2)) { printf("\t Input image 2 size does not match !!!\n"); return 1; }
+		{ // read the stacks of the time point this process will handle next while the GPU works on this one
+			const int step = (regMode == 1) ? 0 : numStep * shardWorld;
+			const int nextNum = (regMode == 1) ? numStart - 1 + numStep * (1 + shardRank) : num + step;
+			if (nextNum <= numEnd && nextNum != num) {
+				const std::string nn = std::to_string(nextNum);
+				ahead.start(dir1 + base1 + nn + ".tif", dir2 + base2 + nn + ".tif", voxels(g.in1), voxels(g.in2));
+			}
+		}
 		fusion_preprocess(g, raw1, raw2, img1, img2, rs.deviceNum);
 
 		printf("...Registration...\n");
@@ -209,8 +226,8 @@ int main(int argc, char **argv)
 			break;
 		}
 		write_tmx((tmxDir + "Matrix_" + n + ".tmx").c_str(), tmx); // the matrix is always saved
-		if (saveReg1) writetifstack((char *)(regDir1 + base1 + "reg_" + n + ".tif").c_str(), img1.data(), g.s1, (unsigned short)bitsImg);
-		if (saveReg2) writetifstack((char *)(regDir2 + base2 + "reg_" + n + ".tif").c_str(), reg.data(), g.s1, (unsigned short)bitsImg);
+		if (saveReg1) behind.write(regDir1 + base1 + "reg_" + n + ".tif", img1.data(), g.s1, (unsigned short)bitsImg);
+		if (saveReg2) behind.write(regDir2 + base2 + "reg_" + n + ".tif", reg.data(), g.s1, (unsigned short)bitsImg);
 		printf("\tTime cost for  registration: %2.3f s\n", tReg.s());
 		{
 			char buf[256];
@@ -224,7 +241,7 @@ int main(int argc, char **argv)
 		(void)decon_dualview(decon.data(), img1.data(), reg.data(), g.s1, psf1.data(), psf2.data(), psfSize, false, iters, rs.deviceNum, rs.gpuMemMode, rs.verbose,
 			deconRec, unmatched, bp1.data(), bp2.data());
 		const int modeActual = (int)deconRec[0];
-		writetifstack((char *)(deconDir + "Decon_" + n + ".tif").c_str(), decon.data(), g.s1, bits);
+		behind.write(deconDir + "Decon_" + n + ".tif", decon.data(), g.s1, bits);
 		printf("\tTime cost for  deconvolution: %2.3f s\n", tDec.s());
 		{
 			char buf[256];
@@ -235,9 +252,9 @@ int main(int argc, char **argv)
 		if (saveXProj || saveYProj || saveZProj) { // packed [Z-proj | X-proj | Y-proj], src/apifunc.cpp:485-505
 			unsigned int sizeMP[6], s2d[3] = {0, 0, 1};
 			(void)mp2dgpu(mp2d.data(), sizeMP, decon.data(), g.s1, saveZProj, saveXProj, saveYProj);
-			if (saveZProj) { s2d[0] = sizeMP[0]; s2d[1] = sizeMP[1]; writetifstack((char *)(mpXY + "MP_XY_" + n + ".tif").c_str(), mp2d.data(), s2d, bits); }
-			if (saveXProj) { s2d[0] = sizeMP[2]; s2d[1] = sizeMP[3]; writetifstack((char *)(mpYZ + "MP_YZ_" + n + ".tif").c_str(), mp2d.data() + sx * sy, s2d, bits); }
-			if (saveYProj) { s2d[0] = sizeMP[4]; s2d[1] = sizeMP[5]; writetifstack((char *)(mpZX + "MP_ZX_" + n + ".tif").c_str(), mp2d.data() + sx * sy + sy * sz, s2d, bits); }
+			if (saveZProj) { s2d[0] = sizeMP[0]; s2d[1] = sizeMP[1]; behind.write(mpXY + "MP_XY_" + n + ".tif", mp2d.data(), s2d, bits); }
+			if (saveXProj) { s2d[0] = sizeMP[2]; s2d[1] = sizeMP[3]; behind.write(mpYZ + "MP_YZ_" + n + ".tif", mp2d.data() + sx * sy, s2d, bits); }
+			if (saveYProj) { s2d[0] = sizeMP[4]; s2d[1] = sizeMP[5]; behind.write(mpZX + "MP_ZX_" + n + ".tif", mp2d.data() + sx * sy + sy * sz, s2d, bits); }
 		}
 		if (modeActual > 0) {
 			unsigned int s3d[3];
@@ -248,11 +265,12 @@ int main(int argc, char **argv)
 				mp3d.assign((size_t)((axis == 1 ? sx : sy) * R * projectNum), 0.f);
 				(void)mip3dgpu(mp3d.data(), s3d, decon.data(), g.s1, axis, projectNum);
 				const std::string f = (axis == 1) ? mp3X + "MP_3D_Xaxis_" + n + ".tif" : mp3Y + "MP_3D_Yaxis_" + n + ".tif";
-				writetifstack((char *)f.c_str(), mp3d.data(), s3d, bits);
+				behind.write(f, mp3d.data(), s3d, bits);
 			}
 		}
 		printf("...Time cost for current image is %2.3f s\n", tPoint.s());
 	}
+	behind.drain();
 	printf("Total time cost for whole processing is %2.3f s\n", whole.s());
 	return 0;
 }

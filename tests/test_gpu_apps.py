@@ -67,3 +67,60 @@ def test_reg3d_app_writes_matrix_and_image(tmp_path):
     got = np.array([float(v) for row in rows[:3] for v in row], np.float32)
     assert np.abs(got - ref["tmx"]).max() < 1e-5            # "%f" text keeps 6 decimals
     assert np.array_equal(libapi.readtifstack(tmp_path / "r.tif"), ref["reg"])
+
+
+def _batch_cmd(out_dir, in1, in2, psf_a, psf_b, first, last, reg_mode, initial_tmx="0"):
+    # the 34 positional arguments of spimFusionBatch (apps/spim_fusion_batch.cpp: usage)
+    return [_need("spimFusionBatch"), str(out_dir) + "/", str(in1) + "/", str(in2) + "/", "A_", "B_", str(first), str(last), "1", str(first),
+            "1", "1", "1", "1", "1", "1", str(reg_mode), "0", initial_tmx, "none", "0.001", "200", "0", "1", str(psf_a), str(psf_b), "3",
+            "1", "1", "1", "0", "0", "16", "0", "0"]
+
+
+def _tree(root):
+    out = {}
+    for d, _, files in os.walk(root):
+        for f in files:
+            if f.endswith((".tif", ".tmx")):
+                p = os.path.join(d, f)
+                out[os.path.relpath(p, root)] = open(p, "rb").read()
+    return out
+
+
+def test_spim_fusion_batch_pipeline_and_sharding(tmp_path):
+    """spimFusionBatch on three small time points: the read-ahead / write-behind I/O pipeline (apps/io_pipeline.h)
+    must write exactly the files of the sequential run, and two MILB_SHARD processes together must write them too."""
+    from microimagelib_b200 import libapi
+    from oracle import reg_oracle as ro
+    psf_a = synth.gaussian_psf((13, 13, 13), (2.5, 2, 2))
+    psf_b = synth.gaussian_psf((13, 13, 13), (2, 2, 2.5))
+    in1, in2 = tmp_path / "SPIMA", tmp_path / "SPIMB"
+    in1.mkdir(); in2.mkdir()
+    libapi.writetifstack(tmp_path / "pa.tif", psf_a, 32)
+    libapi.writetifstack(tmp_path / "pb.tif", psf_b, 32)
+    for t in range(3):
+        a = synth.bead_image((24, 40, 48), psf_a, density=1 / 512.0, seed=30 + t)
+        b = ro.imshift(synth.bead_image((24, 40, 48), psf_b, density=1 / 512.0, seed=30 + t, noise_seed=7), (1, -1, 0))
+        libapi.writetifstack(in1 / f"A_{t}.tif", a, 16)
+        libapi.writetifstack(in2 / f"B_{t}.tif", b, 16)
+    runs = {}
+    for tag, env in (("seq", {"MILB_PIPELINE": "0"}), ("pipe", {"MILB_PIPELINE": "1"})):
+        out = tmp_path / tag
+        r = subprocess.run(_batch_cmd(out, in1, in2, tmp_path / "pa.tif", tmp_path / "pb.tif", 0, 2, 3), capture_output=True, text=True,
+                           env={**os.environ, **env}, timeout=600)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        runs[tag] = _tree(out)
+    assert len(runs["seq"]) >= 3 * (1 + 1 + 1 + 3)            # per time point: Decon, RegB, matrix, three 2-D MIPs
+    assert runs["seq"].keys() == runs["pipe"].keys()
+    for k in runs["seq"]:
+        assert runs["seq"][k] == runs["pipe"][k], k
+    # two shards (both on GPU 0 here: MILB_SHARD_DEVICE_STRIDE=0) write the same files as the single process
+    out = tmp_path / "shards"
+    procs = [subprocess.Popen(_batch_cmd(out, in1, in2, tmp_path / "pa.tif", tmp_path / "pb.tif", 0, 2, 3), stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True, env={**os.environ, "MILB_SHARD": f"{r}/2", "MILB_SHARD_DEVICE_STRIDE": "0"})
+             for r in range(2)]
+    outs = [p.communicate(timeout=600)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs[0][-800:] + outs[1][-800:]
+    got = _tree(out)
+    assert got.keys() == runs["seq"].keys()
+    for k in got:
+        assert got[k] == runs["seq"][k], k
