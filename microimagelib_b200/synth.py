@@ -83,3 +83,18 @@ def invert_affine(m12) -> np.ndarray:
     """Inverse of a 3x4 affine (implicit last row 0 0 0 1), float64 -> float32."""
     M = np.vstack([np.asarray(m12, np.float64).reshape(3, 4), [0, 0, 0, 1]])
     return np.linalg.inv(M)[:3].astype(np.float32).reshape(12)
+
+
+def shift_zero_fill(vol, shift):
+    """out[z, y, x] = vol[z - dz, y - dy, x - dx] with zeros shifted in; shift = (dx, dy, dz) integers"""
+    vol = np.asarray(vol)
+    out = np.zeros_like(vol)
+    dx, dy, dz = (int(v) for v in shift)
+
+    def rng(n, d):
+        lo, hi = max(0, d), min(n, n + d)
+        return slice(lo, hi), slice(lo - d, hi - d)
+    (zo, zi), (yo, yi), (xo, xi) = rng(vol.shape[0], dz), rng(vol.shape[1], dy), rng(vol.shape[2], dx)
+    if zo.start < zo.stop and yo.start < yo.stop and xo.start < xo.stop:
+        out[zo, yo, xo] = vol[zi, yi, xi]
+    return out
