@@ -10,6 +10,33 @@
 #include <vector>
 
 #include "../include/libapi.h"
+#include "../include/milb_capi.h"
+
+// Volume buffers of the fusion apps live in page-locked host memory (milb_host_alloc), so that every
+// libapi.h call moves them over PCIe at full rate; MILB_PINNED=0 uses plain malloc like the reference.
+template <class T> struct PinnedAllocator {
+	using value_type = T;
+	PinnedAllocator() = default;
+	template <class U> PinnedAllocator(const PinnedAllocator<U> &) {}
+	T *allocate(size_t n)
+	{
+		static const bool pinned = [] { const char *e = getenv("MILB_PINNED"); return !(e && e[0] == '0'); }();
+		void *p = nullptr;
+		if (!pinned) p = malloc(n * sizeof(T));
+		else if (milb_host_alloc(&p, (unsigned long long)(n * sizeof(T))) != 0) p = nullptr;
+		if (!p) { fprintf(stderr, "*** host memory allocation of %zu bytes failed\n", n * sizeof(T)); exit(1); }
+		return (T *)p;
+	}
+	void deallocate(T *p, size_t)
+	{
+		static const bool pinned = [] { const char *e = getenv("MILB_PINNED"); return !(e && e[0] == '0'); }();
+		if (pinned) milb_host_free(p);
+		else free(p);
+	}
+	template <class U> bool operator==(const PinnedAllocator<U> &) const { return true; }
+	template <class U> bool operator!=(const PinnedAllocator<U> &) const { return false; }
+};
+using HostVec = std::vector<float, PinnedAllocator<float>>;
 
 struct Args {
 	int argc;

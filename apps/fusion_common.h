@@ -31,24 +31,28 @@ inline void fusion_geometry(FusionGeometry &g, const float px1[3], const float p
 	}
 }
 
-// view A: resample; view B: rotate about Y then resample (src/spim_fusion.cpp:560-590)
-inline void fusion_preprocess(const FusionGeometry &g, const std::vector<float> &raw1, const std::vector<float> &raw2, std::vector<float> &img1,
-	std::vector<float> &img2, int deviceNum)
+// view A: resample; view B: rotate about Y then resample (src/spim_fusion.cpp:560-590).
+// raw1 / raw2 are consumed: when a view needs no resampling its buffer is swapped into img, not copied.
+inline void fusion_preprocess(const FusionGeometry &g, HostVec &raw1, HostVec &raw2, HostVec &img1, HostVec &img2, int deviceNum)
 {
-	img1.assign(voxels(g.s1), 0.f);
-	img2.assign(voxels(g.s2), 0.f);
-	if (!memcmp(g.in1, g.s1, sizeof g.s1)) img1 = raw1;
-	else (void)imresize3d(img1.data(), (float *)raw1.data(), g.s1[0], g.s1[1], g.s1[2], g.in1[0], g.in1[1], g.in1[2], deviceNum);
-	std::vector<float> rot;
+	if (!memcmp(g.in1, g.s1, sizeof g.s1)) img1.swap(raw1);
+	else {
+		img1.resize(voxels(g.s1));
+		(void)imresize3d(img1.data(), raw1.data(), g.s1[0], g.s1[1], g.s1[2], g.in1[0], g.in1[1], g.in1[2], deviceNum);
+	}
+	static HostVec rot; // scratch of the rotated view, kept between time points
 	unsigned int rs[3] = {g.in2[0], g.in2[1], g.in2[2]};
-	const std::vector<float> *src = &raw2;
+	HostVec *src = &raw2;
 	if (g.opChoice) {
-		rot.assign(raw2.size(), 0.f);
-		(void)imoperation3D(rot.data(), rs, (float *)raw2.data(), (unsigned int *)g.in2, g.opChoice, deviceNum);
+		rot.resize(raw2.size());
+		(void)imoperation3D(rot.data(), rs, raw2.data(), (unsigned int *)g.in2, g.opChoice, deviceNum);
 		src = &rot;
 	}
-	if (!memcmp(rs, g.s2, sizeof rs)) img2 = *src;
-	else (void)imresize3d(img2.data(), (float *)src->data(), g.s2[0], g.s2[1], g.s2[2], rs[0], rs[1], rs[2], deviceNum);
+	if (!memcmp(rs, g.s2, sizeof rs)) img2.swap(*src);
+	else {
+		img2.resize(voxels(g.s2));
+		(void)imresize3d(img2.data(), src->data(), g.s2[0], g.s2[1], g.s2[2], rs[0], rs[1], rs[2], deviceNum);
+	}
 }
 
 struct RegSettings {
@@ -61,7 +65,7 @@ struct RegSettings {
 // (src/spim_fusion_batch.cpp:559,722-746): other pre-alignment scheme, then the initial matrix.
 // `recheck` re-evaluates checkmatrix after the second attempt (the reference does so only in its
 // regMode-2 branch, :764).
-inline void register_with_ladder(std::vector<float> &reg, float *tmx, std::vector<float> &img1, std::vector<float> &img2, const FusionGeometry &g,
+inline void register_with_ladder(HostVec &reg, float *tmx, HostVec &img1, HostVec &img2, const FusionGeometry &g,
 	const RegSettings &rs, bool flagTmx, const float *tmxInitial, bool recheck, float *rec)
 {
 	const float costBar = 0.1f;

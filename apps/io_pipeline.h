@@ -28,13 +28,14 @@ public:
 		k1_ = p1; k2_ = p2;
 		b1_.resize(n1); b2_.resize(n2);
 		busy_ = true;
-		th_ = std::thread([this] {
+		th_ = std::thread([this] { // the two views are decoded side by side
+			std::thread second([this] { readtifstack(b2_.data(), (char *)k2_.c_str(), s2_); });
 			readtifstack(b1_.data(), (char *)k1_.c_str(), s1_);
-			readtifstack(b2_.data(), (char *)k2_.c_str(), s2_);
+			second.join();
 		});
 	}
 	// true: raw1/raw2 and the size triples now hold the prefetched stacks
-	bool take(const std::string &p1, const std::string &p2, std::vector<float> &raw1, std::vector<float> &raw2, unsigned int *s1, unsigned int *s2)
+	bool take(const std::string &p1, const std::string &p2, HostVec &raw1, HostVec &raw2, unsigned int *s1, unsigned int *s2)
 	{
 		if (!busy_) return false;
 		join();
@@ -53,18 +54,24 @@ private:
 	std::thread th_;
 	bool busy_ = false;
 	std::string k1_, k2_;
-	std::vector<float> b1_, b2_;
+	HostVec b1_, b2_;
 	unsigned int s1_[3] = {0, 0, 0}, s2_[3] = {0, 0, 0};
 };
 
 // writetifstack on a worker thread; the data is copied at submission so the caller can reuse its buffer.
 class WriteBehind {
 public:
-	WriteBehind() { if (pipeline_enabled()) th_ = std::thread([this] { run(); }); }
+	WriteBehind()
+	{
+		if (!pipeline_enabled()) return;
+		int n = 3; // encoder / writer threads: one 16-bit conversion + fwrite stream does not keep up with the GPU
+		if (const char *e = getenv("MILB_WRITERS")) n = atoi(e);
+		for (int i = 0; i < (n < 1 ? 1 : n); i++) th_.emplace_back([this] { run(); });
+	}
 	~WriteBehind() { drain(); }
 	void write(const std::string &path, const float *data, const unsigned int *size, unsigned short bits)
 	{
-		if (!th_.joinable()) { // sequential mode
+		if (th_.empty()) { // sequential mode
 			unsigned int s[3] = {size[0], size[1], size[2]};
 			writetifstack((char *)path.c_str(), (float *)data, s, bits);
 			return;
@@ -74,26 +81,47 @@ public:
 		memcpy(j.size, size, sizeof j.size);
 		j.data.assign(data, data + voxels(size));
 		std::unique_lock<std::mutex> lk(mu_);
-		cv_space_.wait(lk, [this] { return q_.size() < 4; }); // bound the host memory held by pending writes
+		cv_space_.wait(lk, [this] { return q_.size() < 6; }); // bound the host memory held by pending writes
+		q_.push_back(std::move(j));
+		cv_work_.notify_one();
+	}
+	// like write(), but takes the caller's buffer instead of copying it: `buf` comes back holding a recycled
+	// buffer of the same size with unspecified contents (the caller overwrites it for the next time point)
+	void write_swap(const std::string &path, HostVec &buf, const unsigned int *size, unsigned short bits)
+	{
+		if (th_.empty()) { write(path, buf.data(), size, bits); return; }
+		Job j;
+		j.path = path; j.bits = bits;
+		memcpy(j.size, size, sizeof j.size);
+		{
+			std::unique_lock<std::mutex> lk(mu_);
+			if (!spare_.empty()) { j.big.swap(spare_.back()); spare_.pop_back(); }
+		}
+		if (j.big.size() != buf.size()) j.big.resize(buf.size());
+		j.big.swap(buf);
+		std::unique_lock<std::mutex> lk(mu_);
+		cv_space_.wait(lk, [this] { return q_.size() < 6; });
 		q_.push_back(std::move(j));
 		cv_work_.notify_one();
 	}
 	// waits until everything submitted so far is on disk (end of the batch)
 	void drain()
 	{
-		if (!th_.joinable()) return;
+		if (th_.empty()) return;
 		{
 			std::unique_lock<std::mutex> lk(mu_);
 			stop_ = true;
-			cv_work_.notify_one();
+			cv_work_.notify_all();
 		}
-		th_.join();
+		for (auto &t : th_) t.join();
+		th_.clear();
 	}
 
 private:
 	struct Job {
 		std::string path;
-		std::vector<float> data;
+		std::vector<float> data; // copied payload (small outputs) ...
+		HostVec big;             // ... or a buffer taken over from the caller (write_swap)
 		unsigned int size[3];
 		unsigned short bits;
 	};
@@ -109,12 +137,17 @@ private:
 				q_.pop_front();
 				cv_space_.notify_one();
 			}
-			writetifstack((char *)j.path.c_str(), j.data.data(), j.size, j.bits);
+			writetifstack((char *)j.path.c_str(), j.big.empty() ? j.data.data() : j.big.data(), j.size, j.bits);
+			if (!j.big.empty()) {
+				std::unique_lock<std::mutex> lk(mu_);
+				spare_.push_back(std::move(j.big));
+			}
 		}
 	}
-	std::thread th_;
+	std::vector<std::thread> th_;
 	std::mutex mu_;
 	std::condition_variable cv_work_, cv_space_;
 	std::deque<Job> q_;
+	std::vector<HostVec> spare_; // written-out big buffers waiting to be reused
 	bool stop_ = false;
 };

@@ -76,7 +76,7 @@ int main(int argc, char **argv)
 	printf("=====================================================\n\n");
 
 	printf("... Preprocessing ...\n");
-	std::vector<float> raw1(voxels(g.in1)), raw2(voxels(g.in2)), img1, img2;
+	HostVec raw1(voxels(g.in1)), raw2(voxels(g.in2)), img1, img2;
 	readtifstack(raw1.data(), (char *)fImg1.c_str(), tmp);
 	if (memcmp(tmp, g.in1, sizeof tmp)) { printf("\t Input image 1 size does not match !!!\n"); return 1; }
 	readtifstack(raw2.data(), (char *)fImg2.c_str(), tmp);
@@ -94,7 +94,7 @@ int main(int argc, char **argv)
 		printf("***** Iput transformation matrix file does not exist: %s\n", fITmx.c_str());
 		return 1;
 	}
-	std::vector<float> reg(voxels(g.s1), 0.f);
+	HostVec reg(voxels(g.s1), 0.f);
 	float regRec[11] = {0}, deconRec[10] = {0};
 	(void)reg3d(reg.data(), tmx, img1.data(), img2.data(), g.s1, g.s2, rs.regChoice, rs.affMethod, haveITmx, rs.ftol, rs.itLimit, rs.deviceNum,
 		rs.gpuMemMode, rs.verbose, regRec);

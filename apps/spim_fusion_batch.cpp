@@ -142,7 +142,7 @@ int main(int argc, char **argv)
 
 	const size_t sx = g.s1[0], sy = g.s1[1], sz = g.s1[2];
 	const long long projectNum = 36;
-	std::vector<float> raw1(voxels(g.in1)), raw2(voxels(g.in2)), img1, img2, reg(voxels(g.s1)), decon(voxels(g.s1));
+	HostVec raw1(voxels(g.in1)), raw2(voxels(g.in2)), img1, img2, reg(voxels(g.s1)), decon(voxels(g.s1));
 	std::vector<float> mp2d, mp3d;
 	if (saveXProj || saveYProj || saveZProj) mp2d.resize(sx * sy + sy * sz + sz * sx);
 	float regRec[11] = {0}, deconRec[10] = {0};
@@ -177,11 +177,13 @@ int main(int argc, char **argv)
 				ahead.start(dir1 + base1 + nn + ".tif", dir2 + base2 + nn + ".tif", voxels(g.in1), voxels(g.in2));
 			}
 		}
+		const double tRead = tPoint.s();
 		fusion_preprocess(g, raw1, raw2, img1, img2, rs.deviceNum);
+		printf("\tTime cost for  reading: %2.3f s, preprocessing: %2.3f s\n", tRead, tPoint.s() - tRead);
 
 		printf("...Registration...\n");
 		WallTimer tReg;
-		std::fill(reg.begin(), reg.end(), 0.f);
+		reg.resize(voxels(g.s1)); // every reg3d path writes the whole volume
 		if (flagTmx) memcpy(affInitial, tmx, sizeof tmx);
 		switch (regMode) {
 		case 0:
@@ -237,12 +239,12 @@ int main(int argc, char **argv)
 
 		printf("... Deconvolution ...\n");
 		WallTimer tDec;
-		std::fill(decon.begin(), decon.end(), 0.f);
+		decon.resize(voxels(g.s1));
 		(void)decon_dualview(decon.data(), img1.data(), reg.data(), g.s1, psf1.data(), psf2.data(), psfSize, false, iters, rs.deviceNum, rs.gpuMemMode, rs.verbose,
 			deconRec, unmatched, bp1.data(), bp2.data());
 		const int modeActual = (int)deconRec[0];
-		behind.write(deconDir + "Decon_" + n + ".tif", decon.data(), g.s1, bits);
 		printf("\tTime cost for  deconvolution: %2.3f s\n", tDec.s());
+		const double tAfterDecon = tPoint.s();
 		{
 			char buf[256];
 			snprintf(buf, sizeof buf, "...Deconvolution: GPU mode %d, %2.3f s, free memory %.0f MB\n", modeActual, deconRec[9], deconRec[5]);
@@ -268,6 +270,9 @@ int main(int argc, char **argv)
 				behind.write(f, mp3d.data(), s3d, bits);
 			}
 		}
+		// the deconvolved volume goes to the writer last, so that its buffer can be handed over instead of copied
+		behind.write_swap(deconDir + "Decon_" + n + ".tif", decon, g.s1, bits);
+		printf("\tTime cost for  projections and output hand-off: %2.3f s\n", tPoint.s() - tAfterDecon);
 		printf("...Time cost for current image is %2.3f s\n", tPoint.s());
 	}
 	behind.drain();

@@ -103,6 +103,10 @@ int milb_dslab_xpass_peer(milb_dslab_t *h, int mode, float *vol_io, const float 
 /* S <- F^-1(F(S) * otf) on my planes; the result rows land in the owners' slab buffers */
 int milb_dslab_planes_peer(milb_dslab_t *h, void *S, void *S2, const void *otf, void *stream);
 /* cudaMalloc'd buffers that other ranks can map (cudaIpcGetMemHandle / cudaIpcOpenMemHandle); handle = 64 bytes */
+/* page-locked host memory for the buffers a host program hands to the libapi.h functions (H2D / D2H at
+ * PCIe rate instead of through the driver's bounce buffers); falls back to malloc if pinning fails */
+int milb_host_alloc(void **out, unsigned long long bytes);
+int milb_host_free(void *p);
 int milb_dev_alloc(void **out, unsigned long long bytes);
 int milb_dev_free(void *p);
 int milb_ipc_export(void *p, unsigned char *handle64);

@@ -71,6 +71,8 @@ CAPI_PROTOS = {
     "milb_dslab_set_peers": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(_VP), C.POINTER(_VP), _I]),
     "milb_dslab_xpass_peer": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP]),
     "milb_dslab_planes_peer": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "milb_host_alloc": (C.c_int, [C.POINTER(_VP), C.c_ulonglong]),
+    "milb_host_free": (C.c_int, [_VP]),
     "milb_dev_alloc": (C.c_int, [C.POINTER(_VP), C.c_ulonglong]),
     "milb_dev_free": (C.c_int, [_VP]),
     "milb_ipc_export": (C.c_int, [_VP, C.c_char_p]),

@@ -235,6 +235,40 @@ extern "C" int milb_dslab_planes_peer(milb_dslab_t *h, void *S, void *S2, const 
 	return MILB_OK;
 }
 
+// ---- page-locked host buffers (apps/: the batch pipeline's volumes) -----------------------------------
+#include <mutex>
+#include <unordered_set>
+namespace {
+std::mutex g_host_mu;
+std::unordered_set<void *> g_host_malloced; // buffers that fell back to malloc
+}
+extern "C" int milb_host_alloc(void **out, unsigned long long bytes)
+{
+	if (!out || !bytes) return MILB_ERR_ARG;
+	if (cudaHostAlloc(out, bytes, cudaHostAllocDefault) == cudaSuccess) return MILB_OK;
+	cudaGetLastError(); // clear
+	*out = malloc(bytes);
+	if (!*out) return MILB_ERR_CUDA;
+	std::lock_guard<std::mutex> lk(g_host_mu);
+	g_host_malloced.insert(*out);
+	return MILB_OK;
+}
+extern "C" int milb_host_free(void *p)
+{
+	if (!p) return MILB_OK;
+	{
+		std::lock_guard<std::mutex> lk(g_host_mu);
+		auto it = g_host_malloced.find(p);
+		if (it != g_host_malloced.end()) {
+			g_host_malloced.erase(it);
+			free(p);
+			return MILB_OK;
+		}
+	}
+	MILB_CUDA_TRY(cudaFreeHost(p));
+	return MILB_OK;
+}
+
 // ---- device buffers that can be mapped into the other ranks' processes (CUDA IPC) --------------------
 extern "C" int milb_dev_alloc(void **out, unsigned long long bytes)
 {
