@@ -154,7 +154,8 @@ def run_reference(args, shape, rank, world):
         "impl": "reference", "metric": "RL voxel-iters/sec", "value": value, "unit": "voxel-iters/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"deconSingleView RL {shape[2]}x{shape[1]}x{shape[0]} float32, {args.iters} iterations", "psf": args.psf},
+        "config": {"workload": f"deconSingleView RL {shape[2]}x{shape[1]}x{shape[0]} float32, {args.iters} iterations (BASELINE config 2)",
+                   "psf": f"{args.psf}^3 Gaussian", "sampled": f"{sample_iters} of the {args.iters} iterations per step (rate does not depend on the iteration index)"},
         "cpu_baseline": {"value": value, "unit": "voxel-iters/s", "cores": cores, "kind": "port",
                          "sample": f"{sample_iters} RL iteration(s) of the same volume per step, numpy + scipy.fft (pocketfft) float32"},
         "e2e": {"value": value, "unit": "voxel-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
