@@ -95,6 +95,15 @@ __device__ __forceinline__ void fstage(const float2 *__restrict__ tw, LD ld, ST 
 	}
 }
 
+// compile-time twin of fast_pos (offsets of whole row blocks in the merge / split loops of the X pass)
+template <int N> __host__ __device__ constexpr int cfast_pos(int k)
+{
+	using P = FastPlan<N>;
+	const int d0 = k % P::r0, k1 = k / P::r0;
+	const int d1 = k1 % P::r1, k2 = k1 / P::r1;
+	const int d2 = k2 % P::r2, d3 = k2 / P::r2;
+	return d0 * (N / P::r0) + d1 * (N / (P::r0 * P::r1)) + d2 * (N / (P::r0 * P::r1 * P::r2)) + d3;
+}
 // Register-resident twiddles.  In the persistent plane kernels a thread executes the same butterflies
 // (same row q of every sub-transform) for every tile, so the R-1 twiddles of each of its butterflies are
 // loaded from the table once, before the tile loop, instead of R-1 shared-memory broadcasts per
@@ -716,6 +725,12 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 	load_tw<N>(tw, g_tw);
 	const float2 *auxsrc = (MODE == XF_RATIO) ? aux : (const float2 *)vol_io;
 	const int lane = threadIdx.x % L, q = threadIdx.x / L;
+	// structured merge / split indexing (see the merge loop): needs whole row blocks per iteration
+	constexpr int RIT = T / L, NB = N / RIT, NIT = half / RIT;
+	constexpr bool kStructured = (T % L == 0) && ((RIT & (RIT - 1)) == 0) && (RIT * NB == N) && (NIT * RIT == half) && (RIT <= half);
+	const int k0 = threadIdx.x / L, lane0 = threadIdx.x % L;
+	const int pA0 = fast_pos<N>(k0) * L + lane0;                    // position of row k0 (+ lane)
+	const int pB0 = fast_pos<N>((RIT - k0) % RIT) * L + lane0;      // position of the low bits of N - k0 (+ lane)
 
 	auto load_spec = [&](int t) {
 		const float4 *src = spec + (long long)t * L;
@@ -737,15 +752,39 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 		const int tn = t + gridDim.x;
 		cp_async_wait<1>(); // spectrum of this tile landed (the aux group may still be in flight)
 		__syncthreads();
-		for (int idx = threadIdx.x; idx < (half + 1) * L; idx += T) {
-			const int k = idx / L, l = idx % L;
-			float4 ab = SL[idx];
-			const bool self = (k == 0) || (k == half);
-			if (self) { ab.y = 0.f; ab.w = 0.f; }
-			float2 ck, cn;
-			merge_pair(ab, ck, cn);
-			W[fast_pos<N>(k) * L + l] = ck;
-			if (!self) W[fast_pos<N>(N - k) * L + l] = cn;
+		if constexpr (kStructured) {
+			// rows k = k0 + RIT*i: with power-of-two radices the position is a bit permutation, so
+			// pos(k) = pos(k0) + pos(RIT*i) and pos(N-k) = pos(m0) + pos(RIT*(NB-1-i)) (m0 = RIT - k0; the
+			// k0 = 0 rows pair with RIT*(NB-i)): per-thread bases plus compile-time offsets, no index math
+#pragma unroll
+			for (int i = 0; i < NIT; i++) {
+				float4 ab = SL[threadIdx.x + i * T];
+				const bool self = (i == 0) && (k0 == 0);
+				if (self) { ab.y = 0.f; ab.w = 0.f; }
+				float2 ck, cn;
+				merge_pair(ab, ck, cn);
+				W[pA0 + cfast_pos<N>(RIT * i) * L] = ck;
+				const int offB = k0 ? cfast_pos<N>(RIT * (NB - 1 - i)) * L : cfast_pos<N>((RIT * (NB - i)) % N) * L;
+				if (!self) W[pB0 + offB] = cn;
+			}
+			if (threadIdx.x < L) { // row k = N/2 pairs with itself
+				float4 ab = SL[half * L + threadIdx.x];
+				ab.y = 0.f; ab.w = 0.f;
+				float2 ck, cn;
+				merge_pair(ab, ck, cn);
+				W[cfast_pos<N>(half) * L + threadIdx.x] = ck;
+			}
+		} else {
+			for (int idx = threadIdx.x; idx < (half + 1) * L; idx += T) {
+				const int k = idx / L, l = idx % L;
+				float4 ab = SL[idx];
+				const bool self = (k == 0) || (k == half);
+				if (self) { ab.y = 0.f; ab.w = 0.f; }
+				float2 ck, cn;
+				merge_pair(ab, ck, cn);
+				W[fast_pos<N>(k) * L + l] = ck;
+				if (!self) W[fast_pos<N>(N - k) * L + l] = cn;
+			}
 		}
 		__syncthreads();
 		if (tn < ntiles) load_spec(tn);
@@ -788,11 +827,25 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 		cp_async_commit();
 		if (MODE == XF_UPDATE_LAST) continue;
 		fwd_tail_smem<N, L, T>(W, tw);
-		for (int idx = threadIdx.x; idx < (half + 1) * L; idx += T) {
-			const int k = idx / L, l = idx % L;
-			const float2 ck = W[fast_pos<N>(k) * L + l];
-			const float2 cn = W[fast_pos<N>((N - k) % N) * L + l];
-			spec_row_dst<PEER>(spec, M, col0, k, pm)[l] = split_pair(ck, cn);
+		if constexpr (kStructured) {
+#pragma unroll
+			for (int i = 0; i < NIT; i++) {
+				const float2 ck = W[pA0 + cfast_pos<N>(RIT * i) * L];
+				const int offB = k0 ? cfast_pos<N>(RIT * (NB - 1 - i)) * L : cfast_pos<N>((RIT * (NB - i)) % N) * L;
+				const float2 cn = W[pB0 + offB];
+				spec_row_dst<PEER>(spec, M, col0, k0 + RIT * i, pm)[lane0] = split_pair(ck, cn);
+			}
+			if (threadIdx.x < L) {
+				const float2 ch = W[cfast_pos<N>(half) * L + threadIdx.x];
+				spec_row_dst<PEER>(spec, M, col0, half, pm)[threadIdx.x] = split_pair(ch, ch);
+			}
+		} else {
+			for (int idx = threadIdx.x; idx < (half + 1) * L; idx += T) {
+				const int k = idx / L, l = idx % L;
+				const float2 ck = W[fast_pos<N>(k) * L + l];
+				const float2 cn = W[fast_pos<N>((N - k) % N) * L + l];
+				spec_row_dst<PEER>(spec, M, col0, k, pm)[l] = split_pair(ck, cn);
+			}
 		}
 	}
 	if constexpr (PEER) __threadfence_system();
