@@ -34,6 +34,25 @@ int g_ctas = 0, g_sms = 0; // persistent grids
 int g_cap = 0;              // override (FastAxisOps::grid_cap)
 inline int plane_grid(int tiles) { const int c = (g_cap > 0 && g_cap < g_ctas) ? g_cap : g_ctas; return tiles < c ? tiles : c; }
 
+// ---- tensor maps for the TMA tile loads (driver entry point fetched at run time: no -lcuda) ----------
+constexpr bool kTmaTiles = (PL > 8); // dense shared rows
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+	const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn g_encode = nullptr;
+bool g_use_tma = false;
+
+// plane buffer [rows_total][cols] complex -> 2-D float tensor, box = (PL pencils) x (min(N, 256) rows)
+bool make_tile_map(TileMap &tm, const void *base, int cols, long long rows_total)
+{
+	if (!g_encode) return false;
+	const cuuint64_t gdim[2] = {(cuuint64_t)2 * cols, (cuuint64_t)rows_total};
+	const cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(float2)};
+	const cuuint32_t box[2] = {(cuuint32_t)2 * PL, (cuuint32_t)(N < 256 ? N : 256)};
+	const cuuint32_t estr[2] = {1, 1};
+	return g_encode(&tm.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+			   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <typename K> int optin(K k, size_t bytes)
 {
 	return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess ? 0 : 1;
@@ -57,6 +76,19 @@ int setup()
 	bad |= optin(k_ypassF<N, PL, PT, true>, SMP2);
 	bad |= optin(k_zconvT<N, PL, PT, true>, SMP3);
 	bad |= optin(k_zconvT<N, PL, PT, false>, SMP3);
+	if constexpr (kTmaTiles) {
+		bad |= optin(k_ypassF<N, PL, PT, true, false, true>, SMP2);
+		bad |= optin(k_ypassF<N, PL, PT, true, true, true>, SMP2);
+		const char *e = getenv("MILB_TMA");
+		if (!(e && e[0] == '0')) {
+			void *fn = nullptr;
+			cudaDriverEntryPointQueryResult q;
+			if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) {
+				g_encode = (EncodeTiledFn)fn;
+				g_use_tma = true;
+			}
+		}
+	}
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -100,6 +132,13 @@ void xpass_peer(int mode, float2 *vol_io, const float2 *aux, const float4 *spec,
 void pass_inv_peer(const float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, const PeerMap *pm, cudaStream_t st)
 {
 	const int tiles = (cols / PL) * nplanes;
+	if constexpr (kTmaTiles) {
+		TileMap tm;
+		if (g_use_tma && make_tile_map(tm, spec, cols, (long long)N * (plane0 + nplanes))) {
+			k_ypassF<N, PL, PT, true, true, true><<<plane_grid(tiles), PT, SMP2, st>>>(const_cast<float2 *>(spec), tw, cols, plane0, nplanes, *pm, tm);
+			return;
+		}
+	}
 	k_ypassF<N, PL, PT, true, true><<<plane_grid(tiles), PT, SMP2, st>>>(const_cast<float2 *>(spec), tw, cols, plane0, nplanes, *pm);
 }
 
@@ -112,6 +151,13 @@ void passT(const float2 *in, float2 *out, const float2 *tw, int cols, int plane0
 void pass_inv(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
 {
 	const int tiles = (cols / PL) * nplanes;
+	if constexpr (kTmaTiles) {
+		TileMap tm;
+		if (g_use_tma && make_tile_map(tm, spec, cols, (long long)N * (plane0 + nplanes))) {
+			k_ypassF<N, PL, PT, true, false, true><<<plane_grid(tiles), PT, SMP2, st>>>(spec, tw, cols, plane0, nplanes, PeerMap(), tm);
+			return;
+		}
+	}
 	k_ypassF<N, PL, PT, true><<<tiles < g_ctas ? tiles : g_ctas, PT, SMP2, st>>>(spec, tw, cols, plane0, nplanes);
 }
 

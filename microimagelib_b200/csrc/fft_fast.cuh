@@ -15,6 +15,8 @@
 //   k_xpassF  : the fused X pencils: C2R inverse -> ratio | update+clamp -> R2C forward.
 // Run plane-chunk by plane-chunk the three plane passes keep their intermediates in the 126 MB L2.
 #pragma once
+#include <cuda.h>
+
 #include "decon_fast.h"
 #include "fft_core.h"
 
@@ -269,6 +271,49 @@ __device__ __forceinline__ void cp_async16(void *smem_dst, const void *gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int K> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(K) : "memory"); }
 
+// ---- TMA tile loads (cp.async.bulk.tensor, sm_90+) ---------------------------------------------------
+// A plane buffer is described to the copy engine as a 2-D float tensor [rows][2 * cols]; one elected
+// thread asks for a box of (min(N, 256) rows) x (L pencils) and the bytes land in the dense shared tile
+// while an mbarrier counts them.  Unlike LDGSTS this costs no LSU instructions, no address registers and
+// no shared-memory store wavefronts on the SM's own pipe.
+struct alignas(64) TileMap {
+	CUtensorMap m;
+};
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+	asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+// spins until the phase with the given parity has completed; traps instead of hanging the GPU if it never does
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+	const unsigned a = smem_u32(bar);
+	unsigned done = 0;
+	for (unsigned spin = 0; !done; spin++) {
+		asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+					 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+		if (spin > (1u << 26)) __trap();
+	}
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const TileMap *map, int c0, int c1, unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(smem_u32(smem_dst)),
+				 "l"((unsigned long long)map), "r"(c0), "r"(c1), "r"(smem_u32(bar)) : "memory");
+}
+// whole N x L tile starting at tensor row `row0`, pencil column `col0` (one thread calls this)
+template <int N, int L> __device__ __forceinline__ void tma_tile_load(float2 *buf, const TileMap *map, int row0, int col0, unsigned long long *bar)
+{
+	constexpr int RB = (N < 256) ? N : 256;
+	asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); // earlier generic-proxy accesses of the buffer are ordered before the copy
+	mbar_expect_tx(bar, (unsigned)(N * L * sizeof(float2)));
+#pragma unroll
+	for (int r = 0; r < N; r += RB) tma_load_2d(buf + r * L, map, 2 * col0, row0 + r, bar);
+}
+
 // N rows of L pencils (row pitch `pitch` float2 in global memory) -> skewed shared tile.
 // A thread always copies the same 16-byte column chunk of rows r0, r0 + RPI, ...: both addresses
 // advance by constants, so the loop is one cp.async plus one 64-bit add per chunk.
@@ -468,15 +513,26 @@ k_ypassT(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *
 // PEER: the output row y of plane kx is not written back in place but into the slab buffer of the
 // rank that owns row y -- slab_d[kx][y - d*ny][z] -- through peer memory (NVLink): the backward
 // exchange of the slab-decomposed FFT rides on this kernel's stores, tile by tile.
-template <int N, int L, int T, bool INV, bool PEER = false>
+template <int N, int L, int T, bool INV, bool PEER = false, bool TMA = false>
 __global__ void __launch_bounds__(T, (N * L <= 4096) ? 2 : 1)
-k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes, const __grid_constant__ PeerMap pm = PeerMap())
+k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes, const __grid_constant__ PeerMap pm = PeerMap(),
+	const __grid_constant__ TileMap tmap = TileMap())
 {
 	using P = FastPlan<N>;
 	using G = TileGeom<N, L>;
-	extern __shared__ float2 sm[];
+	extern __shared__ __align__(128) float2 sm[];
 	float2 *tw = sm + 2 * G::elems;
+	__shared__ __align__(8) unsigned long long bars[2];
+	if constexpr (TMA) {
+		static_assert(L > 8, "TMA tiles need dense (unskewed) shared rows");
+		if (threadIdx.x == 0) {
+			mbar_init(&bars[0], 1);
+			mbar_init(&bars[1], 1);
+			asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+		}
+	}
 	load_tw<N>(tw, g_tw);
+	if constexpr (TMA) __syncthreads();
 	PlaneTw<N, L, T> pt;
 	// measured: register twiddles pay in the transposing passes (-3 %) but not here, where the 28 extra
 	// live registers push this kernel into spills (94.8 -> 97.9 us)
@@ -484,15 +540,26 @@ k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int 
 	if constexpr (kRt) pt.load(g_tw);
 	const int tpp = Z / L, ntiles = nplanes * tpp;
 	auto ptr_of = [&](int t) { return spec + (long long)(t / tpp + plane0) * N * Z + (long long)(t % tpp) * L; };
+	auto tma_issue = [&](int t, int buf) { tma_tile_load<N, L>(sm + buf * G::elems, &tmap, (t / tpp + plane0) * N, (t % tpp) * L, &bars[buf]); };
 	int t = blockIdx.x, cur = 0;
-	if (t < ntiles) tile_load_async<N, L, T>(sm, ptr_of(t), Z);
-	cp_async_commit();
-	for (; t < ntiles; t += gridDim.x, cur ^= 1) {
-		cp_async_wait<0>();
-		__syncthreads();
-		const int tn = t + gridDim.x;
-		if (tn < ntiles) tile_load_async<N, L, T>(sm + (cur ^ 1) * G::elems, ptr_of(tn), Z);
+	if constexpr (TMA) {
+		if (t < ntiles && threadIdx.x == 0) tma_issue(t, 0);
+	} else {
+		if (t < ntiles) tile_load_async<N, L, T>(sm, ptr_of(t), Z);
 		cp_async_commit();
+	}
+	for (int it = 0; t < ntiles; t += gridDim.x, cur ^= 1, it++) {
+		const int tn = t + gridDim.x;
+		if constexpr (TMA) {
+			mbar_wait(&bars[cur], (it >> 1) & 1); // this buffer's (it / 2)-th fill has landed
+			__syncthreads();                       // everybody is done with the other buffer (previous tile)
+			if (tn < ntiles && threadIdx.x == 0) tma_issue(tn, cur ^ 1);
+		} else {
+			cp_async_wait<0>();
+			__syncthreads();
+			if (tn < ntiles) tile_load_async<N, L, T>(sm + (cur ^ 1) * G::elems, ptr_of(tn), Z);
+			cp_async_commit();
+		}
 		float2 *tile = sm + cur * G::elems;
 		if constexpr (PEER) {
 			static_assert(INV, "the exchange follows the inverse pass");
