@@ -302,6 +302,33 @@ def main():
             roofline["kernels_note"] = "kernel-level HBM bytes (what each launch must read + write), CUDA events around every launch"
         except Exception as e:
             roofline["kernels"] = {"error": str(e)}
+    registration = None
+    if world == 1:
+        try:   # the other kernel of the hot path: fused warp + ZNCC cost, same volume size (8 N bytes per evaluation)
+            m = np.array([0.9994, 0.0349, 0, -5.1, -0.0349, 0.9994, 0, 6.3, 0, 0, 1, 1.75], np.float32)   # 2 deg about z + shift
+            r = device.Reg(shape)
+            r.set_images(d_img, d_img)
+            r.prepare()
+            registration = {"what": "k_zncc: trilinear warp + ZNCC sums (double accumulation), K candidate matrices per launch",
+                            "algorithmic_bytes_per_evaluation": 8 * n_img}
+            for K in (1, 8):
+                mats = np.stack([m] * K)
+                mats[:, 3] += 0.1 * np.arange(K, dtype=np.float32)
+                r.cost(mats)
+                torch.cuda.synchronize()
+                ta, tb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ta.record(stream)
+                for _ in range(5):
+                    r.cost(mats, stream=stream)
+                tb.record(stream)
+                torch.cuda.synchronize()
+                ms_eval = ta.elapsed_time(tb) / 5 / K
+                registration[f"K{K}"] = {"ms_per_evaluation": ms_eval, "GBps": 8 * n_img / (ms_eval * 1e-3) / 1e9,
+                                         "frac_of_peak": 8 * n_img / (ms_eval * 1e-3) / 1e9 / peak}
+            registration["note"] = "issue-bound (ncu: 78 % issue slots, DRAM 18 %); includes the per-launch D2H of the 2K sums"
+            r.close()
+        except Exception as e:
+            registration = {"error": str(e)}
     yard = None
     if world == 1 and not args.no_yardstick:
         try:
@@ -326,7 +353,7 @@ def main():
         "config": {"workload": f"deconSingleView RL {shape[2]}x{shape[1]}x{shape[0]} float32, {args.iters} iterations (BASELINE config 2)",
                    "fft_box": list(d.fft_shape), "psf": f"{args.psf}^3 Gaussian", "per_rank": "one volume per rank, no data-path collective",
                    "l2": "inputs larger than L2 (256 MiB volume, 126 MB L2); no explicit flush"},
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "yardstick": yard,
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "yardstick": yard, "registration": registration,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

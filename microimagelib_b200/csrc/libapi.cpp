@@ -68,6 +68,7 @@ struct DeconCache {
 	int device = -1, nviews = 0;
 	unsigned int im[3] = {0, 0, 0}, psf[3] = {0, 0, 0};
 	unsigned long long psf_hash = 0;
+	float free_mb_after = -1.f; // free device memory when the handle was last left in place
 };
 DeconCache g_cache[2];
 std::mutex g_cache_mu;
@@ -94,15 +95,21 @@ int decon_common(int nviews, float *h_decon, float *const h_img[2], unsigned int
 		return bad_mode_rc;
 	}
 	cuda_fatal(cudaSetDevice(deviceNum), "cudaSetDevice");
-	deconRecords[1] = free_mb();
+	// cudaMemGetInfo is a kernel-mode round trip measured at anything from 0.1 to 30 ms per call here, and
+	// the reference issues it four times per deconvolution for its memory records.  This library changes
+	// the device's free memory only when it creates or replaces the cached handle, so the records are
+	// re-queried on those calls only; otherwise the figures of the call that left the handle in place
+	// are reported.
+	std::lock_guard<std::mutex> lock(g_cache_mu);
+	DeconCache &c = g_cache[nviews - 1];
+	const bool same_handle = cache_enabled() && c.h && c.device == deviceNum && c.nviews == nviews && c.free_mb_after >= 0;
+	deconRecords[1] = same_handle ? c.free_mb_after : free_mb();
 	printf("...GPU free memory(at beginning) is %.0f MBites\n", deconRecords[1]);
 	// Every mode runs the all-on-GPU path: 180 GB of HBM holds the largest documented case
 	// (1024x1024x512 dual view, about 9 x 2 GiB) and this backend has no CPU path.
 	deconRecords[0] = 1;
 	const double t1 = now_s();
 
-	std::lock_guard<std::mutex> lock(g_cache_mu);
-	DeconCache &c = g_cache[nviews - 1];
 	const size_t npsf = (size_t)psfSize[0] * psfSize[1] * psfSize[2];
 	unsigned long long hash = fnv1a(&flagUnmatch, sizeof flagUnmatch);
 	for (int v = 0; v < nviews; v++) {
@@ -124,18 +131,19 @@ int decon_common(int nviews, float *h_decon, float *const h_img[2], unsigned int
 	// cudaMemGetInfo is a kernel-mode round trip that was measured at up to 30 ms right after the loop;
 	// when the cached handle is reused nothing is allocated or released during the call, so the later
 	// memory records equal the first one and are not queried again.
-	deconRecords[2] = hit ? deconRecords[1] : free_mb();
+	deconRecords[2] = (hit && same_handle) ? deconRecords[1] : free_mb();
 	printf("...GPU free memory(after mallocing) is %.0f MBites\n", deconRecords[2]);
 	for (int v = 0; v < nviews; v++) fatal_if(milb_decon_set_image(c.h, v, h_img[v], 0, nullptr), "****Image preparation failed !!!!*****");
 	const double t2 = now_s();
 	fatal_if(milb_decon_run(c.h, itNumForDecon, flagConstInitial ? 1 : 0, nullptr), "decon iterration error");
 	fatal_if(milb_decon_get_result(c.h, h_decon, 0, nullptr), "decon result transfer");
 	const double t3 = now_s();
-	deconRecords[4] = hit ? deconRecords[1] : free_mb();
+	deconRecords[4] = (hit && same_handle) ? deconRecords[1] : free_mb();
 	printf("...GPU free memory (after processing) is %.0f MBites\n", deconRecords[4]);
 	if (!cache_enabled()) { milb_decon_destroy(c.h); c.h = nullptr; }
 	const double t_end = now_s();
-	deconRecords[5] = (hit && cache_enabled()) ? deconRecords[1] : free_mb();
+	deconRecords[5] = (hit && same_handle) ? deconRecords[1] : free_mb();
+	c.free_mb_after = cache_enabled() ? deconRecords[5] : -1.f;
 	printf("GPU free memory (after variable released): %.0f MBites\n", deconRecords[5]);
 	deconRecords[6] = (float)(t1 - t_start);
 	deconRecords[7] = (float)(t2 - t1);
