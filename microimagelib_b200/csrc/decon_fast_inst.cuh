@@ -28,7 +28,13 @@ constexpr size_t SMP3 = (size_t)(3 * TileGeom<N, PL>::elems + N) * sizeof(float2
 #ifndef MILB_X_WIDE
 #define MILB_X_WIDE 0
 #endif
-constexpr int XL = (MILB_X_WIDE ? 8192 : 4096) / N, XT = MILB_X_WIDE ? 1024 : 512;
+// MILB_X_NARROW: 2048-point tiles, 256 threads, 4 CTAs/SM (more CTAs to hide each other's barriers, narrower rows)
+#ifndef MILB_X_NARROW
+#define MILB_X_NARROW 0
+#endif
+constexpr bool kXNarrow = MILB_X_NARROW && (2048 / N >= 4);
+constexpr int XL = (MILB_X_WIDE ? 8192 : kXNarrow ? 2048 : 4096) / N, XT = MILB_X_WIDE ? 1024 : kXNarrow ? 256 : 512;
+constexpr int XCTAS = (XT <= 256) ? 4 : (XT <= 512) ? 2 : 1;
 constexpr size_t SMX = (size_t)(2 * N * XL + 2 * (N / 2 + 1) * XL + N) * sizeof(float2);
 int g_ctas = 0, g_sms = 0; // persistent grids
 int g_cap = 0;              // override (FastAxisOps::grid_cap)
@@ -100,7 +106,7 @@ int setup()
 void xpass(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const float2 *tw, long long M, cudaStream_t st)
 {
 	if (mode != XF_FWD_REAL && (M % XL) == 0) {
-		const int ntiles = (int)(M / XL), cap = (XT <= 512 ? 2 : 1) * g_sms, grid = ntiles < cap ? ntiles : cap;
+		const int ntiles = (int)(M / XL), cap = XCTAS * g_sms, grid = ntiles < cap ? ntiles : cap;
 		if (mode == XF_RATIO) k_xpassP<N, XL, XT, XF_RATIO><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles);
 		else if (mode == XF_UPDATE) k_xpassP<N, XL, XT, XF_UPDATE><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles);
 		else k_xpassP<N, XL, XT, XF_UPDATE_LAST><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles);
@@ -123,7 +129,7 @@ void xpass_peer(int mode, float2 *vol_io, const float2 *aux, const float4 *spec,
 		k_xpassF<N, L, T, XF_FWD_REAL, true><<<(unsigned)(M / L), T, SM1, st>>>(vol_io, aux, sp, tw, M, *pm);
 		return;
 	}
-	const int ntiles = (int)(M / XL), cap = (XT <= 512 ? 2 : 1) * g_sms, grid = ntiles < cap ? ntiles : cap;
+	const int ntiles = (int)(M / XL), cap = XCTAS * g_sms, grid = ntiles < cap ? ntiles : cap;
 	if (mode == XF_RATIO) k_xpassP<N, XL, XT, XF_RATIO, true><<<grid, XT, SMX, st>>>(vol_io, aux, sp, tw, M, ntiles, *pm);
 	else if (mode == XF_UPDATE) k_xpassP<N, XL, XT, XF_UPDATE, true><<<grid, XT, SMX, st>>>(vol_io, aux, sp, tw, M, ntiles, *pm);
 	else k_xpassP<N, XL, XT, XF_UPDATE_LAST><<<grid, XT, SMX, st>>>(vol_io, aux, sp, tw, M, ntiles); // no spectrum output

@@ -777,7 +777,7 @@ k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 // As soon as a landing buffer has been consumed the next tile's rows are already requested, so the
 // spectrum and aux loads of tile t+1 overlap the butterflies of tile t.
 template <int N, int L, int T, int MODE, bool PEER = false>
-__global__ void __launch_bounds__(T, (T <= 512) ? 2 : 1)
+__global__ void __launch_bounds__(T, (T <= 256) ? 4 : (T <= 512) ? 2 : 1)
 k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M, int ntiles,
 	const __grid_constant__ PeerMap pm = PeerMap())
 {
