@@ -33,8 +33,10 @@ constexpr size_t SMP3 = (size_t)(3 * TileGeom<N, PL>::elems + N) * sizeof(float2
 #define MILB_X_NARROW 0
 #endif
 constexpr bool kXNarrow = MILB_X_NARROW && (2048 / N >= 4);
-constexpr int XL = (MILB_X_WIDE ? 8192 : kXNarrow ? 2048 : 4096) / N, XT = MILB_X_WIDE ? 1024 : kXNarrow ? 256 : 512;
-constexpr int XCTAS = (XT <= 256) ? 4 : (XT <= 512) ? 2 : 1;
+constexpr int R0 = FastPlan<N>::r0;                 // radix of the register-fused stage of the X pass: one butterfly per thread
+constexpr int TXF = (N / R0) * L;                   // threads of the non-persistent X pass
+constexpr int XL = (MILB_X_WIDE ? 8192 : kXNarrow ? 2048 : 4096) / N, XT = (N / R0) * XL;
+constexpr int XCTAS = xpassP_ctas<N, XL, XT>();
 constexpr size_t SMX = (size_t)(2 * N * XL + 2 * (N / 2 + 1) * XL + N) * sizeof(float2);
 int g_ctas = 0, g_sms = 0; // persistent grids
 int g_cap = 0;              // override (FastAxisOps::grid_cap)
@@ -67,14 +69,14 @@ template <typename K> int optin(K k, size_t bytes)
 int setup()
 {
 	int bad = 0;
-	bad |= optin(k_xpassF<N, L, T, XF_FWD_REAL>, SM1);
-	bad |= optin(k_xpassF<N, L, T, XF_RATIO>, SM1);
-	bad |= optin(k_xpassF<N, L, T, XF_UPDATE>, SM1);
-	bad |= optin(k_xpassF<N, L, T, XF_UPDATE_LAST>, SM1);
+	bad |= optin(k_xpassF<N, L, TXF, XF_FWD_REAL>, SM1);
+	bad |= optin(k_xpassF<N, L, TXF, XF_RATIO>, SM1);
+	bad |= optin(k_xpassF<N, L, TXF, XF_UPDATE>, SM1);
+	bad |= optin(k_xpassF<N, L, TXF, XF_UPDATE_LAST>, SM1);
 	bad |= optin(k_xpassP<N, XL, XT, XF_RATIO>, SMX);
 	bad |= optin(k_xpassP<N, XL, XT, XF_UPDATE>, SMX);
 	bad |= optin(k_xpassP<N, XL, XT, XF_UPDATE_LAST>, SMX);
-	bad |= optin(k_xpassF<N, L, T, XF_FWD_REAL, true>, SM1);
+	bad |= optin(k_xpassF<N, L, TXF, XF_FWD_REAL, true>, SM1);
 	bad |= optin(k_xpassP<N, XL, XT, XF_RATIO, true>, SMX);
 	bad |= optin(k_xpassP<N, XL, XT, XF_UPDATE, true>, SMX);
 	bad |= optin(k_ypassF<N, PL, PT, true, true>, SMP2);
@@ -114,10 +116,10 @@ void xpass(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const floa
 	}
 	const unsigned grid = (unsigned)(M / L);
 	switch (mode) {
-	case XF_FWD_REAL: k_xpassF<N, L, T, XF_FWD_REAL><<<grid, T, SM1, st>>>(vol_io, aux, spec, tw, M); break;
-	case XF_RATIO: k_xpassF<N, L, T, XF_RATIO><<<grid, T, SM1, st>>>(vol_io, aux, spec, tw, M); break;
-	case XF_UPDATE: k_xpassF<N, L, T, XF_UPDATE><<<grid, T, SM1, st>>>(vol_io, aux, spec, tw, M); break;
-	default: k_xpassF<N, L, T, XF_UPDATE_LAST><<<grid, T, SM1, st>>>(vol_io, aux, spec, tw, M); break;
+	case XF_FWD_REAL: k_xpassF<N, L, TXF, XF_FWD_REAL><<<grid, TXF, SM1, st>>>(vol_io, aux, spec, tw, M); break;
+	case XF_RATIO: k_xpassF<N, L, TXF, XF_RATIO><<<grid, TXF, SM1, st>>>(vol_io, aux, spec, tw, M); break;
+	case XF_UPDATE: k_xpassF<N, L, TXF, XF_UPDATE><<<grid, TXF, SM1, st>>>(vol_io, aux, spec, tw, M); break;
+	default: k_xpassF<N, L, TXF, XF_UPDATE_LAST><<<grid, TXF, SM1, st>>>(vol_io, aux, spec, tw, M); break;
 	}
 }
 
@@ -126,7 +128,7 @@ void xpass_peer(int mode, float2 *vol_io, const float2 *aux, const float4 *spec,
 {
 	float4 *sp = const_cast<float4 *>(spec);
 	if (mode == XF_FWD_REAL) {
-		k_xpassF<N, L, T, XF_FWD_REAL, true><<<(unsigned)(M / L), T, SM1, st>>>(vol_io, aux, sp, tw, M, *pm);
+		k_xpassF<N, L, TXF, XF_FWD_REAL, true><<<(unsigned)(M / L), TXF, SM1, st>>>(vol_io, aux, sp, tw, M, *pm);
 		return;
 	}
 	const int ntiles = (int)(M / XL), cap = XCTAS * g_sms, grid = ntiles < cap ? ntiles : cap;

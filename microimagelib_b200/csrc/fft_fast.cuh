@@ -29,8 +29,24 @@ template <int N> struct FastPlan;
 		static constexpr int r0 = A, r1 = B, r2 = C, r3 = D;  \
 	};
 MILB_FAST_PLAN(64, 2, 8, 8, 1, 1)
+#ifndef MILB_PLAN128_R16
+#define MILB_PLAN128_R16 0
+#endif
+#if MILB_PLAN128_R16
+MILB_FAST_PLAN(128, 2, 8, 16, 1, 1)
+#else
 MILB_FAST_PLAN(128, 3, 8, 4, 4, 1)
+#endif
+// MILB_PLAN256_R16: 16 x 16 instead of 8 x 8 x 4 -- one shared-memory exchange fewer per direction; in the X pass
+// (the 512x512x256 bench box has X = 256) that is two of its ten shared-memory round trips
+#ifndef MILB_PLAN256_R16
+#define MILB_PLAN256_R16 1
+#endif
+#if MILB_PLAN256_R16
+MILB_FAST_PLAN(256, 2, 16, 16, 1, 1)
+#else
 MILB_FAST_PLAN(256, 3, 8, 8, 4, 1)
+#endif
 MILB_FAST_PLAN(512, 3, 8, 8, 8, 1)
 // MILB_PLAN1024_R16: three stages (one radix-16, fft_core.h bfly16) instead of four.  Measured at
 // 1024x1024x512: Y inverse 1100 -> 885 us, but Y forward 1178 -> 1248 and Z conv 1924 -> 2173 us
@@ -38,7 +54,9 @@ MILB_FAST_PLAN(512, 3, 8, 8, 8, 1)
 #ifndef MILB_PLAN1024_R16
 #define MILB_PLAN1024_R16 0
 #endif
-#if MILB_PLAN1024_R16
+#if MILB_PLAN1024_R16 == 2
+MILB_FAST_PLAN(1024, 3, 16, 16, 4, 1)
+#elif MILB_PLAN1024_R16
 MILB_FAST_PLAN(1024, 3, 8, 16, 8, 1)
 #else
 MILB_FAST_PLAN(1024, 4, 8, 8, 4, 4)
@@ -695,16 +713,17 @@ k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 	const __grid_constant__ PeerMap pm = PeerMap())
 {
 	using P = FastPlan<N>;
-	static_assert(P::r0 == 8 && (N / 8) * L == T, "stage 0 must be one radix-8 butterfly per thread");
+	constexpr int R0 = P::r0;
+	static_assert((N / R0) * L == T, "stage 0 must be one butterfly per thread");
 	extern __shared__ float2 sm[];
 	float2 *tile = sm, *tw = sm + N * L;
 	load_tw<N>(tw, g_tw);
 	__syncthreads();
 	const long long col0 = (long long)blockIdx.x * L;
 	constexpr int half = N / 2;
-	constexpr int M0 = N / 8;
+	constexpr int M0 = N / R0;
 	const int lane = threadIdx.x % L, q = threadIdx.x / L;
-	float2 v[8];
+	float2 v[R0];
 
 	if (MODE != XF_FWD_REAL) {
 		// half spectrum -> packed complex pencil in position order
@@ -722,22 +741,22 @@ k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 		inv_head_smem<N, L, T>(tile, tw);
 		// inverse stage 0 in registers -> natural-order samples x = q + j*M0
 #pragma unroll
-		for (int j = 0; j < 8; j++) v[j] = tile[(q + j * M0) * L + lane];
+		for (int j = 0; j < R0; j++) v[j] = tile[(q + j * M0) * L + lane];
 #pragma unroll
-		for (int j = 1; j < 8; j++) v[j] = cmulc(v[j], tw[q * j]);
-		bfly8<true>(v);
+		for (int j = 1; j < R0; j++) v[j] = cmulc(v[j], tw[q * j]);
+		fbfly<R0, true>(v);
 		if (MODE == XF_RATIO) {
-			float2 a[8];
+			float2 a[R0];
 #pragma unroll
-			for (int j = 0; j < 8; j++) a[j] = aux[(long long)(q + j * M0) * M + col0 + lane];
+			for (int j = 0; j < R0; j++) a[j] = aux[(long long)(q + j * M0) * M + col0 + lane];
 #pragma unroll
-			for (int j = 0; j < 8; j++) { v[j].x = a[j].x / v[j].x; v[j].y = a[j].y / v[j].y; } // div3Dkernel
+			for (int j = 0; j < R0; j++) { v[j].x = a[j].x / v[j].x; v[j].y = a[j].y / v[j].y; } // div3Dkernel
 		} else {
-			float2 e[8];
+			float2 e[R0];
 #pragma unroll
-			for (int j = 0; j < 8; j++) e[j] = vol_io[(long long)(q + j * M0) * M + col0 + lane];
+			for (int j = 0; j < R0; j++) e[j] = vol_io[(long long)(q + j * M0) * M + col0 + lane];
 #pragma unroll
-			for (int j = 0; j < 8; j++) {
+			for (int j = 0; j < R0; j++) {
 				e[j].x *= v[j].x; e[j].y *= v[j].y;                                   // multi3Dkernel
 				e[j].x = (e[j].x > SMALLVALUE_FAST) ? e[j].x : SMALLVALUE_FAST;       // maxvalue3Dgpukernel
 				e[j].y = (e[j].y > SMALLVALUE_FAST) ? e[j].y : SMALLVALUE_FAST;
@@ -748,14 +767,14 @@ k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 		}
 	} else {
 #pragma unroll
-		for (int j = 0; j < 8; j++) v[j] = vol_io[(long long)(q + j * M0) * M + col0 + lane];
+		for (int j = 0; j < R0; j++) v[j] = vol_io[(long long)(q + j * M0) * M + col0 + lane];
 	}
 	// forward stage 0 in the same registers
-	bfly8<false>(v);
+	fbfly<R0, false>(v);
 #pragma unroll
-	for (int j = 1; j < 8; j++) v[j] = cmul(v[j], tw[q * j]);
+	for (int j = 1; j < R0; j++) v[j] = cmul(v[j], tw[q * j]);
 #pragma unroll
-	for (int j = 0; j < 8; j++) tile[(q + j * M0) * L + lane] = v[j];
+	for (int j = 0; j < R0; j++) tile[(q + j * M0) * L + lane] = v[j];
 	__syncthreads();
 	fwd_tail_smem<N, L, T>(tile, tw);
 	// packed pencil -> two half spectra (even / odd z column of the pair)
@@ -768,6 +787,15 @@ k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 	if constexpr (PEER) __threadfence_system();
 }
 
+// CTAs per SM of the persistent X pass: limited by its shared memory (working tile + two landing buffers) and threads
+template <int N, int L, int T> constexpr int xpassP_ctas()
+{
+	constexpr long smem = (long)(2 * N * L + 2 * (N / 2 + 1) * L + N) * 8 + 1024;
+	constexpr int by_smem = (int)(232448 / smem), by_thr = 2048 / T;
+	constexpr int c = by_smem < by_thr ? by_smem : by_thr;
+	return c < 1 ? 1 : (c > 4 ? 4 : c);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Persistent fused X pencils with prefetch (RATIO / UPDATE / UPDATE_LAST).
 // One CTA per SM, T = (N/8)*L threads, tiles of L column pairs.  Three shared buffers:
@@ -777,14 +805,15 @@ k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 // As soon as a landing buffer has been consumed the next tile's rows are already requested, so the
 // spectrum and aux loads of tile t+1 overlap the butterflies of tile t.
 template <int N, int L, int T, int MODE, bool PEER = false>
-__global__ void __launch_bounds__(T, (T <= 256) ? 4 : (T <= 512) ? 2 : 1)
+__global__ void __launch_bounds__(T, xpassP_ctas<N, L, T>())
 k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M, int ntiles,
 	const __grid_constant__ PeerMap pm = PeerMap())
 {
 	using P = FastPlan<N>;
-	static_assert(P::r0 == 8 && (N / 8) * L == T, "stage 0 must be one radix-8 butterfly per thread");
+	constexpr int R0 = P::r0;
+	static_assert((N / R0) * L == T, "stage 0 must be one butterfly per thread");
 	extern __shared__ float2 sm[];
-	constexpr int half = N / 2, M0 = N / 8;
+	constexpr int half = N / 2, M0 = N / R0;
 	float2 *W = sm;
 	float4 *SL = (float4 *)(sm + N * L);
 	float2 *AL = sm + N * L + 2 * (half + 1) * L;
@@ -859,21 +888,21 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 		inv_head_smem<N, L, T>(W, tw);
 		cp_async_wait<1>(); // aux of this tile landed (the next spectrum may still be in flight)
 		__syncthreads();
-		float2 v[8];
+		float2 v[R0];
 #pragma unroll
-		for (int j = 0; j < 8; j++) v[j] = W[(q + j * M0) * L + lane];
+		for (int j = 0; j < R0; j++) v[j] = W[(q + j * M0) * L + lane];
 #pragma unroll
-		for (int j = 1; j < 8; j++) v[j] = cmulc(v[j], tw[q * j]);
-		bfly8<true>(v);
+		for (int j = 1; j < R0; j++) v[j] = cmulc(v[j], tw[q * j]);
+		fbfly<R0, true>(v);
 		if (MODE == XF_RATIO) {
 #pragma unroll
-			for (int j = 0; j < 8; j++) {
+			for (int j = 0; j < R0; j++) {
 				const float2 a = AL[(q + j * M0) * L + lane];
 				v[j].x = a.x / v[j].x; v[j].y = a.y / v[j].y; // div3Dkernel
 			}
 		} else {
 #pragma unroll
-			for (int j = 0; j < 8; j++) {
+			for (int j = 0; j < R0; j++) {
 				float2 e = AL[(q + j * M0) * L + lane];
 				e.x *= v[j].x; e.y *= v[j].y;                                   // multi3Dkernel
 				e.x = (e.x > SMALLVALUE_FAST) ? e.x : SMALLVALUE_FAST;          // maxvalue3Dgpukernel
@@ -883,11 +912,11 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 			}
 		}
 		if (MODE != XF_UPDATE_LAST) {
-			bfly8<false>(v);
+			fbfly<R0, false>(v);
 #pragma unroll
-			for (int j = 1; j < 8; j++) v[j] = cmul(v[j], tw[q * j]);
+			for (int j = 1; j < R0; j++) v[j] = cmul(v[j], tw[q * j]);
 #pragma unroll
-			for (int j = 0; j < 8; j++) W[(q + j * M0) * L + lane] = v[j];
+			for (int j = 0; j < R0; j++) W[(q + j * M0) * L + lane] = v[j];
 		}
 		__syncthreads(); // AL consumed by everybody
 		if (tn < ntiles) load_aux(tn);
