@@ -20,7 +20,9 @@ constexpr int PL = kWide ? 2 * L : L;
 #ifndef MILB_PLANE_HALF_THREADS
 #define MILB_PLANE_HALF_THREADS 1
 #endif
-constexpr int PT = (kWide && !MILB_PLANE_HALF_THREADS) ? 2 * T : T;
+// a plan with a radix-32 stage: 8192 points / 32 = 256 butterflies -> 256 threads, up to 255 registers each
+constexpr bool kR32 = (FastPlan<N>::r0 == 32 || FastPlan<N>::r1 == 32);
+constexpr int PT = kR32 ? 256 : (kWide && !MILB_PLANE_HALF_THREADS) ? 2 * T : T;
 constexpr size_t SM1 = (size_t)(N * L + N) * sizeof(float2);                                  // X pass: one tile
 constexpr size_t SMP2 = (size_t)(2 * TileGeom<N, PL>::elems + N) * sizeof(float2);           // plane pass: 2 landing buffers
 constexpr size_t SMP3 = (size_t)(3 * TileGeom<N, PL>::elems + N) * sizeof(float2);           // + transposition / OTF buffer

@@ -137,6 +137,28 @@ template <bool INV> MILB_HD void bfly16(float2 *v)
 	}
 }
 
+// radix-32: one radix-2 layer with the w32^j twiddles on the odd half, then two radix-16 butterflies
+template <bool INV> MILB_HD void bfly32(float2 *v)
+{
+	// (cos, sin) of 2 pi j / 32, j = 0..15
+	const float cs[16][2] = {{1.0f, 0.0f}, {0.98078528040323043f, 0.19509032201612825f}, {0.92387953251128674f, 0.38268343236508978f}, {0.83146961230254524f, 0.55557023301960218f}, {0.70710678118654757f, 0.70710678118654746f}, {0.55557023301960229f, 0.83146961230254524f}, {0.38268343236508984f, 0.92387953251128674f}, {0.19509032201612833f, 0.98078528040323043f}, {0.0f, 1.0f}, {-0.19509032201612819f, 0.98078528040323043f}, {-0.38268343236508973f, 0.92387953251128674f}, {-0.55557023301960196f, 0.83146961230254546f}, {-0.70710678118654746f, 0.70710678118654757f}, {-0.83146961230254535f, 0.55557023301960218f}, {-0.92387953251128674f, 0.38268343236508989f}, {-0.98078528040323043f, 0.19509032201612861f}};
+	float2 a[16], b[16];
+#pragma unroll
+	for (int j = 0; j < 16; j++) {
+		a[j] = cadd(v[j], v[j + 16]);
+		b[j] = csub(v[j], v[j + 16]);
+	}
+#pragma unroll
+	for (int j = 1; j < 16; j++) b[j] = cmul(b[j], make_float2(cs[j][0], INV ? cs[j][1] : -cs[j][1]));
+	bfly16<INV>(a); // X[2k]
+	bfly16<INV>(b); // X[2k+1]
+#pragma unroll
+	for (int k = 0; k < 16; k++) {
+		v[2 * k] = a[k];
+		v[2 * k + 1] = b[k];
+	}
+}
+
 // naive length-r DFT using the axis twiddle table (r divides n): w_r^t = tw[t * (n / r)]
 template <bool INV> MILB_HD void bfly_generic(float2 *v, int r, const float2 *tw, int n)
 {

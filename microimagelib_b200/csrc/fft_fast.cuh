@@ -47,7 +47,16 @@ MILB_FAST_PLAN(256, 2, 16, 16, 1, 1)
 #else
 MILB_FAST_PLAN(256, 3, 8, 8, 4, 1)
 #endif
+// MILB_PLAN512_R32: 16 x 32 instead of 8 x 8 x 8 (256 threads per wide tile: one radix-32 or two radix-16
+// butterflies per thread and stage)
+#ifndef MILB_PLAN512_R32
+#define MILB_PLAN512_R32 1
+#endif
+#if MILB_PLAN512_R32
+MILB_FAST_PLAN(512, 2, 16, 32, 1, 1)
+#else
 MILB_FAST_PLAN(512, 3, 8, 8, 8, 1)
+#endif
 // MILB_PLAN1024_R16: three stages (one radix-16, fft_core.h bfly16) instead of four.  Measured at
 // 1024x1024x512: Y inverse 1100 -> 885 us, but Y forward 1178 -> 1248 and Z conv 1924 -> 2173 us
 // (register pressure in the transposing passes): 13.28 -> 13.49 ms per iteration, so it stays off.
@@ -80,6 +89,7 @@ template <int R, bool INV> __device__ __forceinline__ void fbfly(float2 (&v)[R])
 	if constexpr (R == 2) bfly2<INV>(v[0], v[1]);
 	else if constexpr (R == 4) bfly4<INV>(v[0], v[1], v[2], v[3]);
 	else if constexpr (R == 8) bfly8<INV>(v);
+	else if constexpr (R == 32) bfly32<INV>(v);
 	else bfly16<INV>(v);
 }
 
