@@ -135,7 +135,7 @@ def test_device_resident_handle_matches_host_api():
     d.close()
 
 
-@pytest.mark.parametrize("shape", [(64, 128, 256), (256, 64, 128), (128, 512, 64), (64, 64, 1024)])
+@pytest.mark.parametrize("shape", [(64, 128, 256), (256, 64, 128), (128, 512, 64), (64, 64, 1024), (512, 64, 128), (1024, 64, 64), (128, 256, 512)])
 def test_fast_pow2_path_matches_generic_path(shape, monkeypatch):
     """The power-of-two fast kernels (fft_fast.cuh) and the generic mixed-radix kernels
     (fft_kernels.cuh) are independent implementations of the same loop."""
