@@ -77,4 +77,19 @@ int emul_c2r_pair(int n, const float *A, const float *B, float *a, float *b)
 	for (int i = 0; i < n; i++) { a[i] = c[i].x; b[i] = c[i].y; }
 	return 0;
 }
+
+// the register butterflies of the fast kernels (natural order in and out): r in {2, 4, 8, 16, 32}
+int emul_bfly(int r, float *data /* r complex, interleaved */, int inverse)
+{
+	float2 *v = (float2 *)data;
+	switch (r) {
+	case 2: if (inverse) bfly2<true>(v[0], v[1]); else bfly2<false>(v[0], v[1]); break;
+	case 4: if (inverse) bfly4<true>(v[0], v[1], v[2], v[3]); else bfly4<false>(v[0], v[1], v[2], v[3]); break;
+	case 8: if (inverse) bfly8<true>(v); else bfly8<false>(v); break;
+	case 16: if (inverse) bfly16<true>(v); else bfly16<false>(v); break;
+	case 32: if (inverse) bfly32<true>(v); else bfly32<false>(v); break;
+	default: return -1;
+	}
+	return 0;
+}
 }

@@ -62,3 +62,16 @@ def test_two_real_pencils_in_one_complex(lib, n):
 def test_unsupported_prime_factor_is_rejected(lib):
     radix = (C.c_int * 8)()
     assert lib.emul_plan(64 * 67, radix, None) == -1
+
+
+@pytest.mark.parametrize("r", [2, 4, 8, 16, 32])
+def test_register_butterflies_are_dfts(lib, r):
+    """bfly2/4/8/16/32 (fft_core.h), the in-register transforms of the fast kernels' stages: natural order in
+    and out, forward = DFT, inverse = un-normalised inverse DFT."""
+    rng = np.random.default_rng(100 + r)
+    x = (rng.standard_normal(r) + 1j * rng.standard_normal(r)).astype(np.complex64)
+    for inverse in (0, 1):
+        d = x.copy()
+        assert lib.emul_bfly(r, d.ctypes.data_as(F), inverse) == 0
+        ref = np.fft.ifft(x.astype(np.complex128)) * r if inverse else np.fft.fft(x.astype(np.complex128))
+        assert np.linalg.norm(d - ref) / np.linalg.norm(ref) < 3e-7
