@@ -29,8 +29,9 @@ template <int N> struct FastPlan;
 		static constexpr int r0 = A, r1 = B, r2 = C, r3 = D;  \
 	};
 MILB_FAST_PLAN(64, 2, 8, 8, 1, 1)
+// MILB_PLAN128_R16: 8 x 16 instead of 8 x 4 x 4 (X pass at X = 128: 105 -> 88 us on a 128x512x512 box)
 #ifndef MILB_PLAN128_R16
-#define MILB_PLAN128_R16 0
+#define MILB_PLAN128_R16 1
 #endif
 #if MILB_PLAN128_R16
 MILB_FAST_PLAN(128, 2, 8, 16, 1, 1)
@@ -52,7 +53,9 @@ MILB_FAST_PLAN(256, 3, 8, 8, 4, 1)
 #ifndef MILB_PLAN512_R32
 #define MILB_PLAN512_R32 1
 #endif
-#if MILB_PLAN512_R32
+#if MILB_PLAN512_R32 == 2
+MILB_FAST_PLAN(512, 2, 32, 16, 1, 1)
+#elif MILB_PLAN512_R32
 MILB_FAST_PLAN(512, 2, 16, 32, 1, 1)
 #else
 MILB_FAST_PLAN(512, 3, 8, 8, 8, 1)
