@@ -217,6 +217,10 @@ extern "C" int milb_dslab_planes_peer(milb_dslab_t *h, void *S, void *S2, const 
 	// gets side_ctas of them and the next chunk's transforms get the rest; only the first transforms and
 	// the last exchange pass have the machine to themselves.
 	int *cap_y = oy->grid_cap, *cap_z = oz->grid_cap;
+	struct CapReset { // the grid caps are process-wide launcher state: never leave them set, whatever path returns
+		int *a, *b;
+		~CapReset() { *a = 0; *b = 0; }
+	} cap_reset{cap_y, cap_z};
 	for (int c = 0; c < C; c++) {
 		const int p0 = (int)((long long)h->np * c / C), p1 = (int)((long long)h->np * (c + 1) / C);
 		*cap_y = *cap_z = (c == 0) ? 0 : sms - h->side_ctas;
