@@ -174,3 +174,30 @@ def test_libapi_reg2d_choices():
     assert st == 0 and int(rec[5]) == o["n_eval"] and np.abs(tmx - o["tmx"]).max() <= 1e-3
     reg, tmx, st, rec = libapi.reg2d(img, src, regChoice=0, flagTmx=True, iTmx=[1, 0, 4, 0, 1, -3])
     assert st == 0 and np.array_equal(reg, ro.affine2d(src, [1, 0, 4, 0, 1, -3], img.shape))
+
+
+def test_phasor_peak_in_the_first_column_reports_z_zero_like_max3dgpu():
+    """max3Dgpu never reads the z index of column (0, 0) of the shifted correlation volume (src/api_subfunc.cu:453-466):
+    a shift of exactly (-sx/2, -sy/2, dz) therefore comes back with z = -sz/2.  Oracle and CUDA restate the quirk."""
+    from microimagelib_b200 import device
+    from oracle import reg_oracle as ro
+    v = _vol((16, 24, 32), seed=21)
+    moved = np.roll(v, (3, -12, -16), axis=(0, 1, 2))           # (dz, dy, dx) = (3, -sy/2, -sx/2)
+    got, want = device.phasor(v, moved), ro.phasor(v, moved)
+    assert got == want
+    assert got[0] in (-16, 16) and got[1] in (-12, 12)            # the alias comparison may flip the half-extent shifts
+
+
+def test_libapi_registration_mode_and_choice_errors():
+    """return codes of the reference for unsupported combinations (src/api_reg.cpp:390-393, 514, 583-586, 596-599; :220-236)"""
+    from microimagelib_b200 import libapi
+    v = _vol((16, 24, 32), seed=22)
+    assert libapi.reg3d(v, v, regChoice=2, regMethod=1, gpuMemMode=0)[2] == -1      # CPU registration "under developing"
+    assert libapi.reg3d(v, v, regChoice=2, regMethod=1, gpuMemMode=3)[2] == 1       # wrong gpuMemMode
+    assert libapi.reg3d(v, v, regChoice=7, regMethod=1)[2] == 1                     # wrong registration choice
+    assert libapi.reg3d(v, v, regChoice=4, regMethod=1, gpuMemMode=2)[2] == -1      # 2-D MIP pre-alignment not in mode 2
+    img = v[0]
+    assert libapi.reg2d(img, img, regChoice=9)[2] == 1
+    assert libapi.reg2d(img, img[:, :-2].copy(), regChoice=3)[2] == 1               # phasor needs equal sizes
+    reg, tmx, st, rec = libapi.reg3d(v, v, regChoice=0, regMethod=3, inputTmx=False) # choice 0 without a matrix: copy
+    assert st == 0 and np.array_equal(reg, v)
