@@ -157,3 +157,25 @@ def test_fast_pow2_path_matches_generic_path(shape, monkeypatch):
                 assert np.array_equal(d.result(), outs["fast"])
         d.close()
     assert rel_l2(outs["fast"], outs["generic"]) <= 2e-6
+
+
+def test_edge_inputs_zero_iterations_clamp_and_padded_dualview():
+    """zero iterations return the (clamped) initial estimate; zeros and negative voxels are raised to 0.01
+    (src/api_subfunc.cu:3380); dual view on a padded, non-power-of-two box with unmatched back projectors."""
+    from microimagelib_b200 import libapi
+    from oracle import decon_oracle as do
+    img, psf = _case((24, 40, 56), (13, 13, 13), (2, 2, 2))
+    img = img - np.float32(np.percentile(img, 60))                 # 60 % of the voxels are now <= 0
+    got, st, _ = libapi.decon_singleview(img, psf, 0)
+    assert st == 0 and np.array_equal(got, np.maximum(img, np.float32(0.01)))
+    assert np.array_equal(got, do.decon_singleview(img, psf, 0))
+    got, st, _ = libapi.decon_singleview(img, psf, 4)
+    assert rel_l2(got, do.decon_singleview(img, psf, 4)) <= TOL and got.min() >= np.float32(0.01)
+    shape = (40, 100, 72)                                           # box 64 x 128 x 128 after padding
+    pa, pb = synth.gaussian_psf((21, 21, 21), (3, 2, 2)), synth.gaussian_psf((21, 21, 21), (2, 2, 3))
+    ba, bb = synth.gaussian_psf((21, 21, 21), (1.5, 1, 1)), synth.gaussian_psf((21, 21, 21), (1, 1, 1.5))
+    a = synth.bead_image(shape, pa, density=1 / 2048.0, seed=7)
+    b = synth.bead_image(shape, pb, density=1 / 2048.0, seed=7, noise_seed=8)
+    got, st, _ = libapi.decon_dualview(a, b, pa, pb, 4, flagUnmatch=True, psf_bp1=ba, psf_bp2=bb)
+    ref = do.decon_dualview(a, b, pa, pb, 4, unmatch=True, psf_bp1=ba, psf_bp2=bb)
+    assert st == 0 and rel_l2(got, ref) <= TOL
