@@ -7,9 +7,9 @@ namespace {
 constexpr int N = MILB_FAST_N;
 constexpr int T = 512;
 constexpr int L = 4096 / N;
-// plane passes: tile of PL pencils, PT threads.  The wide tile (8192 points, 1024 threads, one CTA
-// per SM) gives 128-byte global rows at N = 512; measured 9 % faster per iteration than 4096-point
-// tiles at 2 CTAs/SM.  PL must not exceed the shortest possible row (64).
+// plane passes: tile of PL pencils, PT threads.  The wide tile (8192 points, one CTA per SM) gives
+// 128-byte global rows at N = 512; measured 9 % faster per iteration than 4096-point tiles at
+// 2 CTAs/SM.  PL must not exceed the shortest possible row (64).
 #ifndef MILB_PLANE_WIDE
 #define MILB_PLANE_WIDE 1
 #endif
@@ -26,7 +26,7 @@ constexpr int PT = kR32 ? 256 : (kWide && !MILB_PLANE_HALF_THREADS) ? 2 * T : T;
 constexpr size_t SM1 = (size_t)(N * L + N) * sizeof(float2);                                  // X pass: one tile
 constexpr size_t SMP2 = (size_t)(2 * TileGeom<N, PL>::elems + N) * sizeof(float2);           // plane pass: 2 landing buffers
 constexpr size_t SMP3 = (size_t)(3 * TileGeom<N, PL>::elems + N) * sizeof(float2);           // + transposition / OTF buffer
-// persistent X pass: 8192-point tiles, 1024 threads, working tile + spectrum landing + aux landing
+// persistent X pass: working tile + spectrum landing + aux landing buffers; MILB_X_WIDE: 8192-point tiles
 #ifndef MILB_X_WIDE
 #define MILB_X_WIDE 0
 #endif

@@ -1,19 +1,20 @@
 // Power-of-two fast path of the pencil FFT passes (N in {64,128,256,512,1024} per axis).
 //
 // Same algorithm and the same position-order spectrum as the generic engine (fft_core.h), but
-// with compile-time lengths and radices: every butterfly lives in registers, the first stage
-// of a pass reads global memory directly and the last one writes it directly, stages exchange
-// through one shared-memory tile, and all three passes are "column" passes whose lanes run
-// along the contiguous axis, so twiddles depend only on the butterfly row.
+// with compile-time lengths and radices (FastPlan<N>: 8x8, 8x16, 16x16, 16x32, 8x8x4x4): every
+// butterfly (radix 2..32) lives in registers, stages exchange through one shared-memory tile, and
+// all passes are "column" passes whose lanes run along the contiguous axis, so twiddles depend
+// only on the butterfly row.  The kernels are persistent (a CTA walks tiles), the next tile is
+// fetched while the current one is transformed (cp.async, or TMA + mbarrier in the Y-inverse pass).
 //
 // Data flow of one convolution  S <- F^-1( F(S) * OTF )  on the kx-planes (Y x Z complex each):
-//   k_ypassT  : S [y][z]   --Y forward-->  S2 [z][ky']     (transposed through shared memory)
-//   k_zconvT  : S2 [z][ky'] --Z forward, * OTF, Z inverse--> S [ky'][z]   (transposed back)
-//   k_ypass<INV>: S [ky'][z] --Y inverse--> S [y][z]        (in place)
+//   k_ypassT      : S [y][z]    --Y forward-->  S2 [z][ky']     (transposed through shared memory)
+//   k_zconvT      : S2 [z][ky'] --Z forward, * OTF, Z inverse--> S [ky'][z]   (transposed back)
+//   k_ypassF<INV> : S [ky'][z]  --Y inverse-->  S [y][z]        (in place; PEER: rows go to their owners' slabs)
 // so no pass ever transforms along the contiguous axis, and the OTF (kept in the [z'][ky'] layout
 // the data has at the multiply) is read with fully coalesced loads.
-//   k_xpassF  : the fused X pencils: C2R inverse -> ratio | update+clamp -> R2C forward.
-// Run plane-chunk by plane-chunk the three plane passes keep their intermediates in the 126 MB L2.
+//   k_xpassP / k_xpassF : the fused X pencils: C2R inverse -> ratio | update+clamp -> R2C forward
+//                         (persistent with prefetch / one tile per CTA; PEER: spectrum rows go to their owners' planes).
 #pragma once
 #include <cuda.h>
 
