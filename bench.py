@@ -7,13 +7,17 @@
     python bench.py --impl reference ...      # the CPU arm (oracle port of the reference's FFTW path)
 
 One "step" = one pass of the hot path over one synthetic volume: the full iteration loop of
-deconSingleView (BASELINE config 2: 512x512x256 float32 beads + Gaussian PSF, 50 iterations).
+deconSingleView on the metric's own configuration, 512^3 float32 beads + Gaussian PSF, 50 iterations
+(BASELINE.json metric "RL voxel-iters/sec at 512^3"); BASELINE config 2 (512x512x256) rides along as a
+second record ("config2") of the same JSON line.
   value : N_fft * iterations * steps * ranks / device time, inputs resident in HBM (CUDA events)
   e2e   : the same metric through the reference-facing call libapi.decon_singleview with HOST
           buffers: H2D of the image, the loop, D2H of the result inside the timed region
   roofline : algorithmic bytes of the loop (56 * N_fft per single-view iteration)
           / measured loop time, against the measured HBM copy peak (MEASURED_PEAKS.json)
-  cpu_baseline : the oracle's numpy/pocketfft port of decon_singleview_OTF0 on the host cores
+  cpu_baseline : the oracle's numpy/pocketfft port of decon_singleview_OTF0 on the host cores; its
+          output doubles as the in-run parity check ("parity": rel-L2 of the CUDA result against it)
+  traffic : DRAM bytes per iteration measured in this run by an ncu side-run of the same loop
 N > 1: every rank deconvolves its own volume (time points of spimFusionBatch shard with no
 data-path collective) -> weak scaling; time = max over ranks.
 """
@@ -39,7 +43,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--shape", default="256,512,512", help="slices,H,W")
+    ap.add_argument("--shape", default="512,512,512", help="slices,H,W")
+    ap.add_argument("--shape2", default="256,512,512", help="second record (BASELINE config 2); empty = skip")
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu side-run that measures DRAM bytes per iteration")
+    ap.add_argument("--no-refgpu", action="store_true", help="skip the reference's own GPU path (oracle/_ref) as an in-run yardstick")
     ap.add_argument("--iters", type=int, default=50)
     ap.add_argument("--psf", type=int, default=65)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -117,7 +124,26 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_port_rate(img, psf, iters, threads=None):
+def snap(n):
+    """snapTransformSize (reference src/api_subfunc.cu:57-87): the FFT extent of an image extent."""
+    n = (n + 15) // 16 * 16
+    low = 1 << (n.bit_length() - 1)
+    if low == n:
+        return n
+    return low * 2 if low * 2 <= 128 else (n + 63) // 64 * 64
+
+
+def workload_config(shape, iters, psf_n):
+    """The `config` object both arms print (same keys, same values)."""
+    tag = "the metric's 512^3 configuration" if tuple(shape) == (512, 512, 512) else \
+        "BASELINE config 2" if tuple(shape) == (256, 512, 512) else "custom shape"
+    return {"workload": f"deconSingleView RL {shape[2]}x{shape[1]}x{shape[0]} float32, {iters} iterations ({tag})",
+            "fft_box": [snap(s) for s in shape], "psf": f"{psf_n}^3 Gaussian", "iterations": iters,
+            "per_rank": "one volume per rank, no data-path collective",
+            "l2": "inputs larger than L2 (>= 256 MiB per volume, 126 MB L2); no explicit flush"}
+
+
+def cpu_port_rate(img, psf, iters, threads=None, want_result=False):
     """The oracle's port of the reference CPU loop, timed on the host: voxel-iters/s."""
     import numpy as np
     from oracle import decon_oracle as do
@@ -125,11 +151,14 @@ def cpu_port_rate(img, psf, iters, threads=None):
         os.environ["MILB_ORACLE_THREADS"] = str(threads)
     fshape = do.fft_shape_for(img.shape)
     otf, otf_bp = do.gen_otf_pair(psf, fshape)
-    A = np.maximum(img, do.SMALLVALUE)
+    A = np.maximum(do.pad_stack(img, fshape) if tuple(fshape) != tuple(img.shape) else img, do.SMALLVALUE)
     t0 = time.perf_counter()
-    do.rl_single(A, otf, otf_bp, iters)
+    E = do.rl_single(A, otf, otf_bp, iters)
     dt = time.perf_counter() - t0
-    return float(np.prod(fshape)) * iters / dt, dt
+    rate = float(np.prod(fshape)) * iters / dt
+    if want_result:
+        return rate, dt, (do.crop_stack(E, img.shape) if tuple(fshape) != tuple(img.shape) else E)
+    return rate, dt
 
 
 def run_reference(args, shape, rank, world):
@@ -137,8 +166,12 @@ def run_reference(args, shape, rank, world):
     be built here, so this is the oracle port (kind "port") with all host threads."""
     if rank != 0:
         return
-    import numpy as np
     cores = os.cpu_count() or 1
+    # torch.distributed.run exports OMP_NUM_THREADS=1 to its workers, which makes numpy / pocketfft 2.7x slower than
+    # the same call from a shell; the CPU arm always uses every host core (set before numpy is imported)
+    for k in ("OMP_NUM_THREADS", "MKL_NUM_THREADS", "OPENBLAS_NUM_THREADS"):
+        os.environ[k] = str(cores)
+    import numpy as np
     img, psf = make_inputs(shape, args.psf, 0)
     sample_iters = 1
     for _ in range(min(args.warmup, 1)):
@@ -148,16 +181,16 @@ def run_reference(args, shape, rank, world):
         r, dt = cpu_port_rate(img, psf, sample_iters, cores)
         rates.append(r)
         times.append(dt)
-    n_fft = float(np.prod(shape))
+    n_fft = float(np.prod([snap(s) for s in shape]))
     value = n_fft * sample_iters * len(times) / sum(times)
     line = {
         "impl": "reference", "metric": "RL voxel-iters/sec", "value": value, "unit": "voxel-iters/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"deconSingleView RL {shape[2]}x{shape[1]}x{shape[0]} float32, {args.iters} iterations (BASELINE config 2)",
-                   "psf": f"{args.psf}^3 Gaussian", "sampled": f"{sample_iters} of the {args.iters} iterations per step (rate does not depend on the iteration index)"},
+        "config": workload_config(shape, args.iters, args.psf),
         "cpu_baseline": {"value": value, "unit": "voxel-iters/s", "cores": cores, "kind": "port",
-                         "sample": f"{sample_iters} RL iteration(s) of the same volume per step, numpy + scipy.fft (pocketfft) float32"},
+                         "sample": f"{sample_iters} of the {args.iters} RL iterations of the same volume per step (the rate does not depend on the "
+                                   "iteration index), numpy + scipy.fft (pocketfft) float32; one host, all cores: does not scale with --gpus"},
         "e2e": {"value": value, "unit": "voxel-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -174,6 +207,96 @@ def bind_to_gpu_numa_node(index):
         return sorted(os.sched_getaffinity(0))[:2] + [len(os.sched_getaffinity(0))]
     except Exception as e:  # best effort
         return str(e)
+
+
+def measure_traffic(shape, timeout_s=240):
+    """DRAM bytes per RL iteration of THIS build, measured now: an ncu side-run (dram__bytes_read.sum +
+    dram__bytes_write.sum per launch) of scripts/prof_run.py, 3 iterations, the middle one is reported."""
+    import csv
+    import shutil
+    import tempfile
+    ncu = shutil.which("ncu") or "/usr/local/cuda/bin/ncu"
+    if not os.path.exists(ncu):
+        return None, "ncu not found"
+    tmp = tempfile.mkdtemp(prefix="milb_traffic_")
+    log = os.path.join(tmp, "t.csv")
+    env = dict(os.environ, PROBE_ITERS="3", PROBE_SHAPE=",".join(str(s) for s in shape), PROBE_NOISE="0")
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
+           "-k", "regex:k_planes_fused|k_ypassT|k_zconvT|k_ypassF|k_xpassP|k_xpass|k_ypass|k_zpass", "--csv", "--log-file", log,
+           sys.executable, os.path.join(ROOT, "scripts", "prof_run.py")]
+    try:
+        r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout_s)
+    except Exception as e:
+        return None, f"ncu side-run failed: {e}"
+    if r.returncode != 0 or not os.path.exists(log):
+        return None, "ncu side-run failed: " + (r.stderr or r.stdout)[-200:]
+    rows = []
+    with open(log) as f:
+        lines = [ln for ln in f if ln.startswith('"')]
+    per = {}
+    order = []
+    for row in csv.DictReader(lines):
+        i = int(row["ID"])
+        if i not in per:
+            per[i] = {"kernel": row["Kernel Name"], "bytes": 0.0, "us": None}
+            order.append(i)
+        v = float(row["Metric Value"].replace(",", ""))
+        unit = row.get("Metric Unit", "")
+        if row["Metric Name"].startswith("dram__bytes"):
+            per[i]["bytes"] += v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1)
+        else:
+            per[i]["us"] = v * {"ns": 1e-3, "us": 1, "ms": 1e3, "nsecond": 1e-3, "usecond": 1, "msecond": 1e3}.get(unit, 1e-3)
+    # the loop kernels: drop the OTF-generation / first forward launches by keeping the last 3 * L launches, L per iteration
+    loop = [per[i] for i in order if "k_xpassF" not in per[i]["kernel"] and "fwd" not in per[i]["kernel"]]
+    n_x = sum(1 for k in loop if "xpass" in k["kernel"])
+    if n_x < 6:
+        return None, f"unexpected launch list ({len(loop)} loop launches)"
+    # iterations end with an X pass; 2 X passes per iteration -> split at every second one, walking backwards
+    iters, curk, seen = [], [], 0
+    for k in reversed(loop):
+        if "xpass" in k["kernel"]:
+            if seen == 2:
+                iters.append(list(reversed(curk)))
+                curk, seen = [], 0
+            seen += 1
+        curk.append(k)
+        if len(iters) == 2:
+            break
+    mid = iters[1] if len(iters) > 1 else iters[0]
+    try:
+        shutil.rmtree(tmp)
+    except Exception:
+        pass
+    return {"dram_bytes_per_iteration": sum(k["bytes"] for k in mid),
+            "kernels": [{"kernel": k["kernel"][:60], "dram_bytes": k["bytes"], "us_under_ncu": k["us"]} for k in mid]}, \
+        "ncu side-run in this bench run: dram__bytes_read.sum + dram__bytes_write.sum of the 2nd of 3 iterations"
+
+
+def device_loop(d, iters, steps, warmup, stream, barrier, world, local_rank, clocks=None):
+    """W warm-up runs, then `steps` timed runs of the full iteration loop (CUDA events on the launching stream)."""
+    import torch
+    import torch.distributed as dist
+    from microimagelib_b200 import device
+    for _ in range(warmup):
+        d.run(iters, stream=stream)
+    barrier()
+    if clocks:
+        clocks.start()
+    l0 = device.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(steps):
+        d.run(iters, stream=stream)
+    ev1.record(stream)
+    barrier()
+    launches = device.launch_count() - l0
+    ms = ev0.elapsed_time(ev1)
+    clk = clocks.stop() if clocks else None
+    t = torch.tensor([ms], dtype=torch.float64, device=torch.device("cuda", local_rank))
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item()), launches, clk
 
 
 def main():
@@ -193,7 +316,7 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
-    numa = bind_to_gpu_numa_node(local_rank)   # the end-to-end leg moves 2 x 256 MiB over PCIe per step
+    numa = bind_to_gpu_numa_node(local_rank)   # the end-to-end leg moves 2 x 512 MiB over PCIe per step
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
@@ -215,30 +338,12 @@ def main():
     d.set_image(0, d_img, stream)
 
     # ---- device-resident loop ------------------------------------------------------------------
-    for _ in range(args.warmup):
-        d.run(args.iters, stream=stream)
-    barrier()
-    clocks = ClockSampler(local_rank)
-    clocks.start()
-    l0 = device.launch_count()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        d.run(args.iters, stream=stream)
-    ev1.record(stream)
-    barrier()
-    launches = device.launch_count() - l0
-    ms = ev0.elapsed_time(ev1)
-    clk = clocks.stop()
-    t = torch.tensor([ms], dtype=torch.float64, device=torch.device("cuda", local_rank))
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
+    ms_max, launches, clk = device_loop(d, args.iters, args.steps, args.warmup, stream, barrier, world, local_rank, ClockSampler(local_rank))
     value = n_fft * args.iters * args.steps * world / (ms_max * 1e-3)
 
     # ---- end to end through the reference-facing API (host buffers) -----------------------------
     e2e = None
+    h_out = None
     if not args.no_e2e:
         h_img = torch.from_numpy(img).pin_memory().numpy()
         h_out = torch.empty(shape, dtype=torch.float32).pin_memory().numpy()
@@ -275,43 +380,96 @@ def main():
             dist.destroy_process_group()
         return
 
-    # ---- yardstick + CPU baseline (rank 0, N = 1 only) ------------------------------------------
+    # ---- everything below: rank 0 only, after the timed regions -----------------------------------
     peak, peak_src = peak_hbm()
     ms_iter = ms_max / (args.steps * args.iters)
     achieved = ALG_BYTES_PER_VOXEL_ITER * n_fft / (ms_iter * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_iteration")
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                "peak_source": peak_src, "launch": "one single-view RL iteration = 6 plane-pass launches + 2 fused X-pass launches",
+    fused = bool(d.plane_stage_fused()) if hasattr(d, "plane_stage_fused") else False
+    launch_desc = ("one single-view RL iteration = 2 fused plane-stage launches (k_planes_fused) + 2 fused X-pass launches (k_xpassP)" if fused
+                   else "one single-view RL iteration = 6 plane-pass launches + 2 fused X-pass launches")
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "peak_source": peak_src, "frac_of_nominal_8TBps": achieved / 8000.0, "launch": launch_desc,
                 "algorithmic_bytes_per_launch": ALG_BYTES_PER_VOXEL_ITER * n_fft, "ms_per_launch": ms_iter}
+    if world == 1 and not args.no_traffic:
+        tr, how = measure_traffic(shape)
+        if tr:
+            roofline["traffic"] = tr["dram_bytes_per_iteration"]
+            roofline["traffic_per_voxel"] = tr["dram_bytes_per_iteration"] / n_fft
+            roofline["traffic_kernels"] = tr["kernels"]
+        roofline["traffic_source"] = how
     if world == 1:
         try:                                             # per-kernel break-down: kernel-level bytes / measured launch time
             kms = d.time_kernels(5, stream=stream)
             nspec = float(d.fft_shape[0] // 2 + 1) * d.fft_shape[1] * d.fft_shape[2]
-            rows = [("k_ypassT (Y forward, transposing)", 16 * nspec, kms[0], 2), ("k_zconvT (Z forward * OTF, Z inverse)", 24 * nspec, kms[1], 2),
-                    ("k_ypassF (Y inverse)", 16 * nspec, kms[2], 2), ("k_xpassP ratio (C2R, A/T, R2C)", 16 * nspec + 4 * n_fft, kms[3], 1),
-                    ("k_xpassP update (C2R, E*T clamp, R2C)", 16 * nspec + 8 * n_fft, kms[4], 1)]
+            if fused:
+                rows = [("k_planes_fused (Y forward, Z forward * OTF, Z inverse, Y inverse; intermediates in L2)", 24 * nspec, kms[0], 2)]
+            else:
+                rows = [("k_ypassT (Y forward, transposing)", 16 * nspec, kms[0], 2), ("k_zconvT (Z forward * OTF, Z inverse)", 24 * nspec, kms[1], 2),
+                        ("k_ypassF (Y inverse)", 16 * nspec, kms[2], 2)]
+            rows += [("k_xpassP ratio (C2R, A/T, R2C)", 16 * nspec + 4 * n_fft, kms[3], 1),
+                     ("k_xpassP update (C2R, E*T clamp, R2C)", 16 * nspec + 8 * n_fft, kms[4], 1)]
             roofline["kernels"] = [{"kernel": k, "launches_per_iteration": n, "bytes_per_launch": b, "ms_per_launch": float(ms),
                                     "GBps": b / (float(ms) * 1e-3) / 1e9, "frac_of_peak": b / (float(ms) * 1e-3) / 1e9 / peak}
                                    for k, b, ms, n in rows]
-            roofline["kernels_note"] = "kernel-level HBM bytes (what each launch must read + write), CUDA events around every launch"
+            roofline["kernels_note"] = "HBM bytes each launch must read + write (compulsory, L2-resident hand-overs excluded), CUDA events around every launch"
         except Exception as e:
             roofline["kernels"] = {"error": str(e)}
+
+    # ---- CPU baseline (oracle port) and, from the same computation, the in-run parity check ---------
+    cpu = parity = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        si = 2
+        rate, dt, ref_vol = cpu_port_rate(img, psf, si, cores, want_result=True)
+        cpu = {"value": rate, "unit": "voxel-iters/s", "cores": cores, "kind": "port",
+               "sample": f"{si} RL iterations of the same {shape[2]}x{shape[1]}x{shape[0]} volume ({dt:.1f} s), numpy + scipy.fft "
+                         "(pocketfft) float32 restatement of decon_singleview_OTF0; the reference's FFTW path cannot be built here"}
+        d.run(si, stream=stream)
+        got = d.result()
+        got = got.cpu().numpy() if hasattr(got, "cpu") else np.asarray(got)
+        err = float(np.linalg.norm(got.astype(np.float64) - ref_vol) / np.linalg.norm(ref_vol.astype(np.float64)))
+        parity = {"rel_l2": err, "tolerance": 1e-4, "ok": bool(err <= 1e-4), "against": f"oracle/decon_oracle.py (CPU), same volume, {si} iterations",
+                  "what": "final estimate of the CUDA loop vs the CPU restatement of the reference loop"}
+        del ref_vol, got
+
+    # ---- the reference's own GPU path on this GPU (oracle/_ref, checker + yardstick; after all timed regions) ----
+    refgpu = None
+    if world == 1 and not args.no_refgpu:
+        try:
+            from oracle import ref_gpu
+            if ref_gpu.available() and h_out is not None:
+                R = ref_gpu.api()
+                ours = h_out.copy()
+                R.decon_singleview(img, psf, 2, deviceNum=local_rank)           # warm-up (cuFFT plans, context)
+                t0 = time.perf_counter()
+                rout, rst, rrec = R.decon_singleview(img, psf, args.iters, deviceNum=local_rank)
+                rdt = time.perf_counter() - t0
+                rerr = float(np.linalg.norm(ours.astype(np.float64) - rout) / np.linalg.norm(rout.astype(np.float64)))
+                refgpu = {"what": "the reference's own decon_singleview (cuFFT + its kernels, oracle/_ref/libapi_ref.so) on this GPU, same host "
+                                  "buffers, same iteration count; pageable host memory as the reference allocates it",
+                          "ms_per_call": rdt * 1e3, "decon_seconds_reported": float(rrec[8]), "voxel_iters_per_s_e2e": n_fft * args.iters / rdt,
+                          "ms_per_iteration_loop_only": float(rrec[8]) * 1e3 / args.iters,
+                          "parity_rel_l2_ours_vs_reference": rerr, "iterations": args.iters, "ok": bool(rerr <= 1e-4),
+                          "e2e_speedup_ours_vs_reference_gpu": (rdt * 1e3) / e2e["ms_per_step"] if e2e else None}
+                if parity is not None:
+                    parity["rel_l2_vs_reference_gpu"] = rerr
+                del ours, rout
+        except Exception as e:
+            refgpu = {"error": str(e)[:300]}
+
     registration = None
     if world == 1:
-        try:   # the other kernel of the hot path: fused warp + ZNCC cost, same volume size (8 N bytes per evaluation)
+        try:   # the other kernel of the hot path: fused warp + ZNCC cost at BASELINE config 4's size (8 N bytes per evaluation)
+            rshape = (256, 512, 512)
+            n_reg = float(np.prod(rshape))
             m = np.array([0.9994, 0.0349, 0, -5.1, -0.0349, 0.9994, 0, 6.3, 0, 0, 1, 1.75], np.float32)   # 2 deg about z + shift
-            r = device.Reg(shape)
-            r.set_images(d_img, d_img)
+            r = device.Reg(rshape)
+            vol = d_img[:rshape[0]].contiguous()
+            r.set_images(vol, vol)
             r.prepare()
-            registration = {"what": "k_zncc: trilinear warp + ZNCC sums (double accumulation), K candidate matrices per launch",
-                            "algorithmic_bytes_per_evaluation": 8 * n_img}
-            for K in (1, 8):
+            registration = {"what": "k_zncc: trilinear warp + ZNCC sums (double accumulation), K candidate matrices per launch, 512x512x256",
+                            "algorithmic_bytes_per_evaluation": 8 * n_reg}
+            for K in (1, 4, 8):
                 mats = np.stack([m] * K)
                 mats[:, 3] += 0.1 * np.arange(K, dtype=np.float32)
                 r.cost(mats)
@@ -323,10 +481,10 @@ def main():
                 tb.record(stream)
                 torch.cuda.synchronize()
                 ms_eval = ta.elapsed_time(tb) / 5 / K
-                registration[f"K{K}"] = {"ms_per_evaluation": ms_eval, "GBps": 8 * n_img / (ms_eval * 1e-3) / 1e9,
-                                         "frac_of_peak": 8 * n_img / (ms_eval * 1e-3) / 1e9 / peak}
-            registration["note"] = "issue-bound (ncu: 78 % issue slots, DRAM 18 %); includes the per-launch D2H of the 2K sums"
+                registration[f"K{K}"] = {"ms_per_evaluation": ms_eval, "GBps": 8 * n_reg / (ms_eval * 1e-3) / 1e9,
+                                         "frac_of_peak": 8 * n_reg / (ms_eval * 1e-3) / 1e9 / peak}
             r.close()
+            del vol
         except Exception as e:
             registration = {"error": str(e)}
     yard = None
@@ -338,22 +496,36 @@ def main():
                     "voxel_iters_per_s": n_fft / (yms * 1e-3), "speedup_vs_yardstick": yms / ms_iter}
         except Exception as e:  # the yardstick is informative only
             yard = {"error": str(e)}
-    cpu = None
-    if world == 1 and not args.no_cpu_baseline:
-        cores = os.cpu_count() or 1
-        si = 2
-        rate, dt = cpu_port_rate(img, psf, si, cores)
-        cpu = {"value": rate, "unit": "voxel-iters/s", "cores": cores, "kind": "port",
-               "sample": f"{si} RL iterations of the same {shape[2]}x{shape[1]}x{shape[0]} volume ({dt:.1f} s), numpy + scipy.fft "
-                         "(pocketfft) float32 restatement of decon_singleview_OTF0; the reference's FFTW path cannot be built here"}
+
+    # ---- second record: BASELINE config 2 (device-resident loop only) ----------------------------
+    config2 = None
+    if world == 1 and args.shape2 and args.shape2 != args.shape:
+        try:
+            del d
+            torch.cuda.empty_cache()
+            shape2 = tuple(int(s) for s in args.shape2.split(","))
+            img2, _ = make_inputs(shape2, args.psf, rank)
+            d2 = device.Decon(shape2, 1)
+            d2.set_psf(0, psf)
+            d2.set_image(0, torch.from_numpy(img2).cuda(), stream)
+            ms2, _, _ = device_loop(d2, args.iters, args.steps, args.warmup, stream, barrier, world, local_rank)
+            n2 = float(np.prod(d2.fft_shape))
+            it2 = ms2 / (args.steps * args.iters)
+            a2 = ALG_BYTES_PER_VOXEL_ITER * n2 / (it2 * 1e-3) / 1e9
+            config2 = {"config": workload_config(shape2, args.iters, args.psf), "value": n2 * args.iters * args.steps / (ms2 * 1e-3),
+                       "unit": "voxel-iters/s", "ms_per_step": ms2 / args.steps, "ms_per_iteration": it2,
+                       "roofline": {"bound": "hbm", "achieved": a2, "peak": peak, "unit": "GB/s", "frac": a2 / peak, "frac_of_nominal_8TBps": a2 / 8000.0}}
+            del d2
+        except Exception as e:
+            config2 = {"error": str(e)[:300]}
+
+    cfg = workload_config(shape, args.iters, args.psf)
     line = {
         "metric": "RL voxel-iters/sec", "value": value, "unit": "voxel-iters/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"deconSingleView RL {shape[2]}x{shape[1]}x{shape[0]} float32, {args.iters} iterations (BASELINE config 2)",
-                   "fft_box": list(d.fft_shape), "psf": f"{args.psf}^3 Gaussian", "per_rank": "one volume per rank, no data-path collective",
-                   "l2": "inputs larger than L2 (256 MiB volume, 126 MB L2); no explicit flush"},
-        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "yardstick": yard, "registration": registration,
+        "dtype": "f32", "data": "synthetic", "config": cfg,
+        "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity": parity, "cpu_baseline": cpu,
+        "reference_gpu_yardstick": refgpu, "yardstick": yard, "registration": registration, "config2": config2,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -59,8 +59,12 @@ int milb_decon_run(milb_decon_t *h, int iterations, int const_init, void *stream
 /* replaces cropgpu + D2H, src/api_decon.cpp:237-243 */
 int milb_decon_get_result(milb_decon_t *h, float *out, int on_device, void *stream);
 
-/* tuning: planes of the half spectrum processed per L2-resident chunk (0 = whole volume) */
+/* tuning: planes of the half spectrum processed per launch of the three plane passes (0 = whole volume; any other
+ * value also switches the fused plane stage off) */
 int milb_decon_set_chunk_planes(milb_decon_t *h, int planes);
+/* 1 if the loop runs the plane stage of a convolution (cufftExecR2C's Y/Z part, multicomplex3Dkernel, cufftExecC2R's
+ * Y/Z part; src/api_subfunc.cu:3406-3413) as ONE persistent launch whose intermediates stay in L2 (square planes) */
+int milb_decon_plane_stage_fused(const milb_decon_t *h);
 
 /* yardstick: the same loop through cuFFT + unfused element-wise kernels, i.e. the reference's own
  * launch structure (src/api_subfunc.cu:3404-3416) on this GPU.  Used by bench.py only. */

@@ -60,6 +60,7 @@ CAPI_PROTOS = {
     "milb_decon_run": (C.c_int, [_VP, C.c_int, C.c_int, _VP]),
     "milb_decon_get_result": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "milb_decon_set_chunk_planes": (C.c_int, [_VP, C.c_int]),
+    "milb_decon_plane_stage_fused": (C.c_int, [_VP]),
     "milb_decon_run_cufft_yardstick": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _F]),
     "milb_decon_time_kernels": (C.c_int, [_VP, C.c_int, _F, _VP]),
     "milb_dslab_create": (C.c_int, [C.POINTER(_VP), _U, C.c_int, C.c_int, C.c_int]),

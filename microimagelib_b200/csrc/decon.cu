@@ -258,6 +258,23 @@ int milb_decon_create(milb_decon_t **out, int nviews, const unsigned int *imSize
 	}
 	cudaError_t e = cudaSuccess;
 	if (h->fast) e = cudaMalloc(&h->S2, sizeof(float2) * h->nspec);
+	if (h->fast && e == cudaSuccess && h->Y == h->Z && milb_fast_ops(h->Y)->planes_fused) {
+		// fused plane stage (one persistent launch per convolution, intermediates L2-resident): MILB_PLANES_FUSED=0 switches
+		// back to three launches; MILB_FUSE_GROUP = planes per pipeline group (ring = 4 groups)
+		const char *fe = getenv("MILB_PLANES_FUSED"), *ge = getenv("MILB_FUSE_GROUP"), *re = getenv("MILB_FUSE_RING");
+		if (!(fe && fe[0] == '0')) {
+			PlaneFuse &f = h->fuse;
+			f.planes = h->X / 2 + 1;
+			const long long plane_bytes = (long long)h->Y * h->Z * sizeof(float2);
+			int g = ge ? atoi(ge) : (int)((8ll << 20) / plane_bytes); // groups of about 8 MB
+			f.group = g < 1 ? 1 : (g > f.planes ? f.planes : g);
+			f.ring_planes = re ? atoi(re) : 4 * f.group;
+			if (f.ring_planes < 2 * f.group) f.ring_planes = 2 * f.group;
+			e = cudaMalloc(&f.ring, (size_t)f.ring_planes * plane_bytes);
+			if (e == cudaSuccess) e = cudaMalloc(&f.counters, sizeof(unsigned) * 2 * f.planes);
+			if (e == cudaSuccess) e = cudaMemset(f.counters, 0, sizeof(unsigned) * 2 * f.planes);
+		}
+	}
 	for (int v = 0; v < nviews && e == cudaSuccess; v++) {
 		e = cudaMalloc(&h->A[v], sizeof(float) * h->nreal);
 		if (e == cudaSuccess) e = cudaMalloc(&h->otf[v], sizeof(float2) * h->nspec);
@@ -288,6 +305,8 @@ void milb_decon_destroy(milb_decon_t *h)
 	if (h->stage) cudaFree(h->stage);
 	if (h->S) cudaFree(h->S);
 	if (h->S2) cudaFree(h->S2);
+	if (h->fuse.ring) cudaFree(h->fuse.ring);
+	if (h->fuse.counters) cudaFree(h->fuse.counters);
 	if (h->d_sums) cudaFree(h->d_sums);
 	free_axis_plan(h->px);
 	free_axis_plan(h->py);
@@ -301,6 +320,8 @@ int milb_decon_fft_size(const milb_decon_t *h, unsigned int *fftSize)
 	fftSize[0] = h->Z; fftSize[1] = h->Y; fftSize[2] = h->X;
 	return MILB_OK;
 }
+
+int milb_decon_plane_stage_fused(const milb_decon_t *h) { return (h && h->fuse.ring && h->chunk_planes == 0) ? 1 : 0; }
 
 int milb_decon_set_chunk_planes(milb_decon_t *h, int planes)
 {
@@ -338,11 +359,25 @@ static void plane_stage(milb_decon *h, const float2 *otf, float scale, cudaStrea
 	if (h->fast) {
 		// S [y][z] -Y fwd-> S2 [z][ky'] -Z fwd * otf Z inv-> S [ky'][z] -Y inv-> S [y][z], chunk by chunk in L2
 		const FastAxisOps *oy = milb_fast_ops(h->Y), *oz = milb_fast_ops(h->Z);
+		if (otf && h->fuse.ring && h->chunk_planes == 0 && oy->planes_fused(h->S, otf, h->py.d_tw, &h->fuse, st)) {
+			milb_count_launches(1);
+			return;
+		}
+		// experiment (MILB_RING_PLANES=R, with MILB_CHUNK_PLANES=c): the transposed planes of a chunk live in a
+		// ring of R plane slots of S2 instead of their own planes, so the scratch stays L2-resident
+		static const int ring = getenv("MILB_RING_PLANES") ? atoi(getenv("MILB_RING_PLANES")) : 0;
+		const long long pe = (long long)h->Y * h->Z;
 		for (int p0 = 0; p0 < planes; p0 += chunk) {
 			const int np = (p0 + chunk <= planes) ? chunk : planes - p0;
-			oy->passT(h->S, h->S2, h->py.d_tw, h->Z, p0, np, st);
+			float2 *s2 = h->S2;
+			const float2 *otf_c = otf;
+			if (otf && ring >= chunk && chunk < planes) {
+				const int slot0 = ((p0 / chunk) % (ring / chunk)) * chunk;
+				s2 = h->S2 + (long long)(slot0 - p0) * pe;
+			}
+			oy->passT(h->S, s2, h->py.d_tw, h->Z, p0, np, st);
 			if (otf) {
-				oz->convT(h->S2, h->S, otf, h->pz.d_tw, h->Y, p0, np, st);
+				oz->convT(s2, h->S, otf_c, h->pz.d_tw, h->Y, p0, np, st);
 				oy->pass_inv(h->S, h->py.d_tw, h->Z, p0, np, st);
 				milb_count_launches(3);
 			} else {
@@ -524,23 +559,31 @@ int milb_decon_time_kernels(milb_decon_t *h, int reps, float *ms5, void *stream)
 	cudaEvent_t ev[9];
 	for (auto &e : ev) MILB_CUDA_TRY(cudaEventCreate(&e));
 	double acc[5] = {0, 0, 0, 0, 0};
+	const bool fused = h->fuse.ring && h->chunk_planes == 0;
 	launch_xpass<X_FWD_REAL>(h, h->E, nullptr, st);
 	for (int r = 0; r < reps; r++) {
 		int k = 0;
 		MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
 		for (int half = 0; half < 2; half++) {
 			const float2 *otf = half ? h->otf_bp[0] : h->otf[0];
-			oy->passT(h->S, h->S2, h->py.d_tw, h->Z, 0, planes, st);
-			MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
-			oz->convT(h->S2, h->S, otf, h->pz.d_tw, h->Y, 0, planes, st);
-			MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
-			oy->pass_inv(h->S, h->py.d_tw, h->Z, 0, planes, st);
-			MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+			if (fused) { // one launch: its time is reported in slot 0, slots 1 and 2 stay zero
+				oy->planes_fused(h->S, otf, h->py.d_tw, &h->fuse, st);
+				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+			} else {
+				oy->passT(h->S, h->S2, h->py.d_tw, h->Z, 0, planes, st);
+				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+				oz->convT(h->S2, h->S, otf, h->pz.d_tw, h->Y, 0, planes, st);
+				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+				oy->pass_inv(h->S, h->py.d_tw, h->Z, 0, planes, st);
+				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+			}
 			if (half == 0) launch_xpass<X_RATIO>(h, nullptr, h->A[0], st);
 			else launch_xpass<X_UPDATE>(h, h->E, nullptr, st);
 			MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
 		}
-		milb_count_launches(6);
+		milb_count_launches(fused ? 2 : 6);
 		MILB_CUDA_TRY(cudaStreamSynchronize(st));
 		float t[8];
 		for (int i = 0; i < 8; i++) MILB_CUDA_TRY(cudaEventElapsedTime(&t[i], ev[i], ev[i + 1]));

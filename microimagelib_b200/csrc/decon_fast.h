@@ -13,6 +13,14 @@ struct PeerMap {
 	int Y, Z;        // plane extents in complex elements
 };
 
+// Scheduling state of the fused plane stage (fft_fast.cuh k_planes_fused), owned by a deconvolution handle.
+struct PlaneFuse {
+	float2 *ring = nullptr;        // ring_planes x n x n complex: transposed-plane scratch that stays L2-resident
+	unsigned *counters = nullptr;  // 2 x planes: per-plane tiles finished by phase A / phase B, cumulative over launches
+	unsigned launches = 0;
+	int planes = 0, group = 0, ring_planes = 0;
+};
+
 struct FastAxisOps {
 	int n = 0;                 // FFT length
 	int lanes = 0;             // pencils per CTA
@@ -34,6 +42,9 @@ struct FastAxisOps {
 	// persistent-grid override for the plane passes (0 = one CTA per SM): lets two plane kernels share the
 	// machine side by side (dslab.cu runs the link-bound peer-store pass next to the next chunk's transforms)
 	int *grid_cap = nullptr;
+	// square planes (n x n): Y forward, Z forward * otf, Z inverse, Y inverse of all planes in ONE persistent launch whose
+	// intermediates stay in L2 (k_planes_fused); returns false if the kernel cannot run (not enough co-resident CTAs)
+	bool (*planes_fused)(float2 *S, const float2 *otf, const float2 *tw, PlaneFuse *pf, cudaStream_t st) = nullptr;
 	// in-place forward only, scaled (OTF generation)
 	void (*fwd_scaled)(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, float scale, cudaStream_t st) = nullptr;
 };

@@ -41,6 +41,7 @@ constexpr int XL = (MILB_X_WIDE ? 8192 : kXNarrow ? 2048 : 4096) / N, XT = (N / 
 constexpr int XCTAS = xpassP_ctas<N, XL, XT>();
 constexpr size_t SMX = (size_t)(2 * N * XL + 2 * (N / 2 + 1) * XL + N) * sizeof(float2);
 int g_ctas = 0, g_sms = 0; // persistent grids
+int g_fused_per_sm = 0, g_fused_ctas = 0; // co-resident CTAs of the fused plane stage (its tiles wait for each other)
 int g_cap = 0;              // override (FastAxisOps::grid_cap)
 inline int plane_grid(int tiles) { const int c = (g_cap > 0 && g_cap < g_ctas) ? g_cap : g_ctas; return tiles < c ? tiles : c; }
 
@@ -86,6 +87,12 @@ int setup()
 	bad |= optin(k_ypassF<N, PL, PT, true>, SMP2);
 	bad |= optin(k_zconvT<N, PL, PT, true>, SMP3);
 	bad |= optin(k_zconvT<N, PL, PT, false>, SMP3);
+	bad |= optin(k_planes_fused<N, PL, PT>, SMP3);
+	g_fused_ctas = 0;
+	if (!bad) {
+		int per_sm = 0;
+		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_planes_fused<N, PL, PT>, PT, SMP3) == cudaSuccess) g_fused_per_sm = per_sm;
+	}
 	if constexpr (kTmaTiles) {
 		bad |= optin(k_ypassF<N, PL, PT, true, false, true>, SMP2);
 		bad |= optin(k_ypassF<N, PL, PT, true, true, true>, SMP2);
@@ -104,6 +111,7 @@ int setup()
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	g_ctas = ((N * PL <= 4096) ? 2 : 1) * sms;
 	g_sms = sms;
+	g_fused_ctas = g_fused_per_sm * sms;
 	return bad;
 }
 
@@ -177,6 +185,25 @@ void convT(float2 *in, float2 *out, const float2 *otf, const float2 *tw, int col
 	k_zconvT<N, PL, PT, true><<<plane_grid(tiles), PT, SMP3, st>>>(in, out, otf, tw, cols, plane0, nplanes, 1.0f);
 }
 
+bool planes_fused(float2 *S, const float2 *otf, const float2 *tw, PlaneFuse *pf, cudaStream_t st)
+{
+	if (g_fused_ctas < 1 || !pf || !pf->ring || !pf->counters) return false;
+	constexpr int TPP = N / PL;
+	PlaneSched sc;
+	sc.doneA = pf->counters;
+	sc.doneB = pf->counters + pf->planes;
+	pf->launches++;
+	sc.target = pf->launches * (unsigned)TPP;
+	sc.planes = pf->planes;
+	sc.group = pf->group;
+	sc.ring = pf->ring_planes;
+	const long long total = plane_total_tickets(pf->planes, pf->group, TPP);
+	const int cap = (g_cap > 0 && g_cap < g_fused_ctas) ? g_cap : g_fused_ctas;
+	const int grid = (int)(total < cap ? total : cap);
+	k_planes_fused<N, PL, PT><<<grid, PT, SMP3, st>>>(S, pf->ring, otf, tw, sc);
+	return true;
+}
+
 void fwd_scaled(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, float scale, cudaStream_t st)
 {
 	const int tiles = (cols / PL) * nplanes;
@@ -190,6 +217,6 @@ const FastAxisOps *MILB_CAT(milb_fast_ops_, MILB_FAST_N)()
 {
 	static FastAxisOps ops;
 	ops.n = N; ops.lanes = L; ops.setup = setup; ops.xpass = xpass; ops.passT = passT; ops.pass_inv = pass_inv;
-	ops.convT = convT; ops.fwd_scaled = fwd_scaled; ops.xpass_peer = xpass_peer; ops.pass_inv_peer = pass_inv_peer; ops.grid_cap = &g_cap;
+	ops.convT = convT; ops.fwd_scaled = fwd_scaled; ops.planes_fused = planes_fused; ops.xpass_peer = xpass_peer; ops.pass_inv_peer = pass_inv_peer; ops.grid_cap = &g_cap;
 	return &ops;
 }

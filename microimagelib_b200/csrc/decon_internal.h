@@ -5,6 +5,7 @@
 
 #include <cuda_runtime.h>
 
+#include "decon_fast.h"
 #include "fft_core.h"
 
 struct AxisPlan {
@@ -29,6 +30,7 @@ struct milb_decon {
 	float2 *S = nullptr;
 	float2 *S2 = nullptr;          // fast path: transposed planes [kx][z][ky']
 	float2 *otf[2] = {nullptr, nullptr}, *otf_bp[2] = {nullptr, nullptr};
+	PlaneFuse fuse;                // fast path, square planes: state of the fused plane stage (ring == nullptr: three launches)
 	double *d_sums = nullptr;      // [0..1] sums, [2..] reduction scratch
 	bool have_psf[2] = {false, false}, have_img[2] = {false, false};
 	// raw PSFs kept on the host for the cuFFT yardstick: [view][0 = forward, 1 = back projector]

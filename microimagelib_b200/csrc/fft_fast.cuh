@@ -20,6 +20,7 @@
 
 #include "decon_fast.h"
 #include "fft_core.h"
+#include "plane_sched.h"
 
 #define SMALLVALUE_FAST 0.01f // src/api_subfunc.cu:24
 
@@ -697,6 +698,157 @@ k_zconvT(float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__rest
 		}
 		__syncthreads();
 		store_transposed<N, L, T>(tile2, out + (long long)(t / tpp + plane0) * N * Yc + (long long)(t % tpp) * L * N, N);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Fused plane stage: ONE persistent launch runs  Y forward -> Z forward * OTF, Z inverse -> Y inverse  of every kx
+// plane (square planes, N = Y = Z), so that the two intermediate hand-overs between the phases stay in L2 instead of
+// making a round trip through HBM each (3 launches: 28 B/voxel of DRAM traffic per convolution; fused: the plane is
+// read once, the OTF is read once and the plane is written once -> 12 B/voxel).
+//
+//   phase A (Y forward):  S plane p [y][z]  ->  ring slot (p mod ring) [z][ky']   (transposed through shared memory)
+//   phase B (Z conv):     ring slot [z][ky'], * otf plane p, -> S plane p [ky'][z] (transposed back)
+//   phase C (Y inverse):  S plane p [ky'][z] -> S plane p [y][z]                   (in place)
+//
+// The ring is a small scratch (a few groups of planes) that is rewritten before L2 ever evicts it, and plane p of S is
+// rewritten by phase B and re-read by phase C while still resident.  Work is a static list of "tickets" in software-
+// pipeline order -- step s = { A of plane group s, B of group s-1, C of group s-2 } -- dealt round-robin to the
+// CTAs (ticket = blockIdx.x + i * gridDim.x).  A tile of phase B (C) needs ALL tiles of phase A (B) of its plane:
+// per-plane completion counters in global memory (release: stores, barrier, __threadfence, atomicAdd by one thread;
+// acquire: relaxed poll, then the dependent cp.async).  By the pipeline order a ticket's producers were dealt three
+// group-phases earlier, so the polls almost never wait; every ticket only depends on earlier tickets and all CTAs are
+// co-resident (grid <= resident CTAs), so the scheme cannot deadlock.  A poll that never succeeds traps instead of hanging.
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
+{
+	unsigned v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void spin_until(const unsigned *p, unsigned target)
+{
+	for (unsigned n = 0; (int)(ld_relaxed_u32(p) - target) < 0; n++) {
+		__nanosleep(64);
+		if (n > (1u << 24)) __trap();
+	}
+	__threadfence();
+}
+
+template <int N, int L, int T>
+__global__ void __launch_bounds__(T, (N * L <= 4096) ? 2 : 1)
+k_planes_fused(float2 *__restrict__ S, float2 *__restrict__ ring, const float2 *__restrict__ otf, const float2 *__restrict__ g_tw,
+	const __grid_constant__ PlaneSched sc)
+{
+	using P = FastPlan<N>;
+	using G = TileGeom<N, L>;
+	constexpr int TPP = N / L;
+	extern __shared__ float2 sm[];
+	float2 *tile2 = sm + 2 * G::elems, *tw = sm + 3 * G::elems; // tile2: transposition buffer, and the OTF landing buffer of phase B
+	load_tw<N>(tw, g_tw);
+	PlaneTw<N, L, T> pt;
+	constexpr bool kRt = PlaneTw<N, L, T>::kUse;
+	if constexpr (kRt) pt.load(g_tw);
+	constexpr long long pe = (long long)N * N;
+	const int total = plane_total_tickets(sc.planes, sc.group, TPP);
+	auto src_of = [&](const PlaneWork &w) -> const float2 * {
+		return (w.phase == 1 ? ring + (long long)(w.plane % sc.ring) * pe : S + (long long)w.plane * pe) + w.tile * L;
+	};
+	auto dep_of = [&](const PlaneWork &w) -> const unsigned * {
+		int dp;
+		const int k = plane_dependency(w, sc.ring, &dp);
+		return k == 0 ? nullptr : (k == 1 ? sc.doneA : sc.doneB) + dp;
+	};
+	int t = blockIdx.x;
+	PlaneWork cur;
+	while (t < total && !plane_ticket(t, sc.planes, sc.group, TPP, cur)) t += gridDim.x;
+	if (t >= total) return;
+	if (const unsigned *d = dep_of(cur)) spin_until(d, sc.target);
+	tile_load_async<N, L, T>(sm, src_of(cur), N);
+	cp_async_commit();
+	for (int buf = 0;; buf ^= 1) {
+		unsigned *sig = nullptr; // completion counter of this tile's plane and phase
+		int tn = t + gridDim.x;
+		PlaneWork nx;
+		while (tn < total && !plane_ticket(tn, sc.planes, sc.group, TPP, nx)) tn += gridDim.x;
+		const bool have_next = tn < total;
+		const unsigned *ndep = have_next ? dep_of(nx) : nullptr;
+		cp_async_wait<0>();
+		__syncthreads(); // this tile has landed; everybody is done with the previous tile
+		const unsigned nv = ndep ? ld_relaxed_u32(ndep) : sc.target; // polled now, looked at after the first stage
+		float2 *tile = sm + buf * G::elems;
+		const long long poff = (long long)cur.plane * pe;
+		if (cur.phase == 1) tile_load_async<N, L, T>(tile2, otf + poff + cur.tile * L, N);
+		cp_async_commit();
+		if (cur.phase == 2) {
+			inv_but_last<N, L, T, false>(tile, tw);
+		} else {
+			if constexpr (kRt) fwd_but_last_rt<N, L, T>(tile, pt);
+			else fwd_but_last<N, L, T>(tile, tw);
+		}
+		bool issued = !have_next;
+		if (have_next && (int)(nv - sc.target) >= 0) {
+			tile_load_async<N, L, T>(sm + (buf ^ 1) * G::elems, src_of(nx), N);
+			issued = true;
+		}
+		cp_async_commit();
+		if (cur.phase == 0) {
+			fwd_last<N, L, T>(tile, tw, [tile2](int r, int l, float2 v) { tile2[swz<L>(r, l)] = v; });
+			__syncthreads();
+			store_transposed<N, L, T>(tile2, ring + (long long)(cur.plane % sc.ring) * pe + (long long)cur.tile * L * N, N);
+			sig = sc.doneA + cur.plane;
+		} else if (cur.phase == 1) {
+			cp_async_wait<1>(); // the OTF tile (older group) has landed; the next data tile may still fly
+			__syncthreads();
+			{ // last forward stage, OTF product and first inverse stage share one register butterfly
+				constexpr int R = (P::S == 2) ? P::r1 : (P::S == 3) ? P::r2 : P::r3;
+				constexpr int NB = (N / R) * L, IT = (NB + T - 1) / T;
+#pragma unroll
+				for (int it = 0; it < IT; it++) {
+					const int bl = threadIdx.x + it * T;
+					if ((NB % T) != 0 && bl >= NB) break;
+					const int lane = bl % L, base = (bl / L) * R;
+					float2 v[R];
+#pragma unroll
+					for (int j = 0; j < R; j++) v[j] = tile[prow<L>(base + j) * L + lane];
+					fbfly<R, false>(v);
+#pragma unroll
+					for (int j = 0; j < R; j++) v[j] = cmul(v[j], tile2[prow<L>(base + j) * L + lane]); // multicomplex3Dkernel
+					fbfly<R, true>(v);
+#pragma unroll
+					for (int j = 0; j < R; j++) tile[prow<L>(base + j) * L + lane] = v[j];
+				}
+				__syncthreads();
+			}
+			if constexpr (kRt) {
+				inv_but_last_rt<N, L, T, true>(tile, tw, pt);
+				sstage_rt_to<N, L, T, P::r0, N, true>(tile, pt.s0, [tile2](int r, int l, float2 v) { tile2[swz<L>(r, l)] = v; });
+			} else {
+				inv_but_last<N, L, T, true>(tile, tw);
+				sstage_to<N, L, T, P::r0, N, true>(tile, tw, [tile2](int r, int l, float2 v) { tile2[swz<L>(r, l)] = v; });
+			}
+			__syncthreads();
+			store_transposed<N, L, T>(tile2, S + poff + (long long)cur.tile * L * N, N);
+			sig = sc.doneB + cur.plane;
+		} else {
+			float2 *p = S + poff + cur.tile * L;
+			sstage_to<N, L, T, P::r0, N, true>(tile, tw, [p](int r, int l, float2 v) { p[(long long)r * N + l] = v; });
+			sig = nullptr;
+		}
+		if (sig) { // release: every thread's stores, barrier, fence + counter increment by one thread
+			__syncthreads();
+			if (threadIdx.x == 0) {
+				__threadfence();
+				atomicAdd(sig, 1u);
+			}
+		}
+		if (!issued) { // the next tile's producers were not done when polled: wait for them now (after this tile's signal is out)
+			spin_until(ndep, sc.target);
+			tile_load_async<N, L, T>(sm + (buf ^ 1) * G::elems, src_of(nx), N);
+		}
+		cp_async_commit();
+		if (!have_next) break;
+		cur = nx;
+		t = tn;
 	}
 }
 

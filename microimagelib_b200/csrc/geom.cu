@@ -142,9 +142,9 @@ __global__ void k_warp_u16_point(unsigned short *__restrict__ out, const unsigne
 		const long long t = i / sx;
 		const int y = (int)(t % sy), z = (int)(t / sy);
 		const float fx = (float)x, fy = (float)y, fz = (float)z;
-		float tx = __fadd_rn(__fadd_rn(__fmaf_rn(a[2], fz, __fmaf_rn(a[1], fy, __fmul_rn(a[0], fx))), a[3]), 0.5f);
-		float ty = __fadd_rn(__fadd_rn(__fmaf_rn(a[6], fz, __fmaf_rn(a[5], fy, __fmul_rn(a[4], fx))), a[7]), 0.5f);
-		float tz = __fadd_rn(__fadd_rn(__fmaf_rn(a[10], fz, __fmaf_rn(a[9], fy, __fmul_rn(a[8], fx))), a[11]), 0.5f);
+		float tx = __fadd_rn(__fadd_rn(__fmaf_rn(a[2], fz, __fmaf_rn(a[0], fx, __fmul_rn(a[1], fy))), a[3]), 0.5f); // contraction order of the reference build (tex_sw.cuh aff_coord)
+		float ty = __fadd_rn(__fadd_rn(__fmaf_rn(a[6], fz, __fmaf_rn(a[4], fx, __fmul_rn(a[5], fy))), a[7]), 0.5f); // contraction order of the reference build (tex_sw.cuh aff_coord)
+		float tz = __fadd_rn(__fadd_rn(__fmaf_rn(a[10], fz, __fmaf_rn(a[8], fx, __fmul_rn(a[9], fy))), a[11]), 0.5f); // contraction order of the reference build (tex_sw.cuh aff_coord)
 		unsigned short r = 0;
 		if (tx >= 0 && tx < (float)sx2 && ty >= 0 && ty < (float)sy2 && tz >= 0 && tz < (float)sz2) {
 			const int xi = min((int)floorf(tx), sx2 - 1), yi = min((int)floorf(ty), sy2 - 1), zi = min((int)floorf(tz), sz2 - 1);

@@ -58,12 +58,13 @@ __device__ __forceinline__ float tex3d_linear(const float *__restrict__ v, int s
 	return __fmul_rn(acc, 1.0f / 256.0f);
 }
 
-// a0*x + a1*y + a2*z + a3 + 0.5 with the contraction nvcc -fmad=true gives the reference
-// expression (include/cukernel.cuh:510-512): mul, fma, fma, add, add.
+// a0*x + a1*y + a2*z + a3 + 0.5 with the contraction nvcc (12.9, -fmad=true) gives the reference
+// expression (include/cukernel.cuh:510-512), read off the SASS of the reference build (oracle/_ref):
+// FMUL a1*y, FFMA a0*x + t, FFMA a2*z + t, FADD a3, FADD 0.5.
 __device__ __forceinline__ float aff_coord(const float *a, float fx, float fy, float fz)
 {
-	float t = __fmul_rn(a[0], fx);
-	t = __fmaf_rn(a[1], fy, t);
+	float t = __fmul_rn(a[1], fy);
+	t = __fmaf_rn(a[0], fx, t);
 	t = __fmaf_rn(a[2], fz, t);
 	t = __fadd_rn(t, a[3]);
 	return __fadd_rn(t, 0.5f);
@@ -90,11 +91,12 @@ __device__ __forceinline__ float tex2d_linear(const float *__restrict__ v, int s
 	return __fmul_rn(acc, 1.0f / 256.0f);
 }
 
-// a0*x + a1*y + a2 + 0.5 (include/cukernel.cuh:564-565, 579-580): mul, fma, add, add.
+// a0*x + a1*y + a2 + 0.5 (include/cukernel.cuh:564-565, 579-580) as the reference build contracts it:
+// FMUL a1*y, FFMA a0*x + t, FADD a2, FADD 0.5.
 __device__ __forceinline__ float aff_coord2d(const float *a, float fx, float fy)
 {
-	float t = __fmul_rn(a[0], fx);
-	t = __fmaf_rn(a[1], fy, t);
+	float t = __fmul_rn(a[1], fy);
+	t = __fmaf_rn(a[0], fx, t);
 	t = __fadd_rn(t, a[2]);
 	return __fadd_rn(t, 0.5f);
 }

@@ -104,10 +104,15 @@ class Decon:
         return float(ms.value)
 
     def time_kernels(self, reps=5, stream=None):
-        """average ms per launch of (Y-forward, Z-conv, Y-inverse, X ratio, X update), CUDA events around every launch"""
+        """average ms per launch of (Y-forward, Z-conv, Y-inverse, X ratio, X update), CUDA events around every launch;
+        with the fused plane stage slot 0 is the whole stage and slots 1, 2 are zero"""
         ms = np.zeros(5, np.float32)
         _check(self.lib.milb_decon_time_kernels(self._h, int(reps), ms.ctypes.data_as(_F), _stream(stream)), "milb_decon_time_kernels")
         return ms
+
+    def plane_stage_fused(self):
+        """True if the plane stage of a convolution runs as one persistent launch (k_planes_fused)"""
+        return bool(self.lib.milb_decon_plane_stage_fused(self._h))
 
     def set_chunk_planes(self, planes):
         _check(self.lib.milb_decon_set_chunk_planes(self._h, int(planes)), "milb_decon_set_chunk_planes")

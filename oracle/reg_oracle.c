@@ -69,13 +69,15 @@ static inline float tex3d_linear(const float *v, long long sx, long long sy, lon
 }
 
 /* Affine coordinate: d_aff[0]*ix + d_aff[1]*iy + d_aff[2]*iz + d_aff[3] + 0.5
- * (include/cukernel.cuh:510-512).  nvcc's default -fmad=true contracts the float sum
- * left to right: mul, fma, fma, add; the "+0.5" is a double add narrowed to float, which
- * equals a correctly rounded float add.  fmaf() restates the contraction.               */
+ * (include/cukernel.cuh:510-512).  PINNED on the reference itself: nvcc 12.9 (-fmad=true, the
+ * reference Makefile's flags) compiles this expression in affinetransformkernel and corrkernel to
+ *     FMUL t = a1*iy;  FFMA t = a0*ix + t;  FFMA t = a2*iz + t;  FADD t += a3;  FADD t += 0.5
+ * (cuobjdump -sass oracle/_ref/libapi_ref.so): the a1*iy product is the one that is rounded on its
+ * own.  The "+0.5" is a double add narrowed to float, which equals a correctly rounded float add.  */
 static inline float aff_coord(const float *a, float ix, float iy, float iz)
 {
-	float t = a[0] * ix;
-	t = fmaf(a[1], iy, t);
+	float t = a[1] * iy;
+	t = fmaf(a[0], ix, t);
 	t = fmaf(a[2], iz, t);
 	t = t + a[3];
 	return (float)((double)t + 0.5);
@@ -247,11 +249,12 @@ static inline float tex2d_linear(const float *v, long long sx, long long sy, flo
 	return acc * (1.0f / 256.0f);
 }
 
-/* d_aff[0]*ix + d_aff[1]*iy + d_aff[2] + 0.5 under nvcc's contraction: mul, fma, add, add */
+/* d_aff[0]*ix + d_aff[1]*iy + d_aff[2] + 0.5 as nvcc 12.9 contracts it in affineTransform2Dkernel /
+ * corr2Dkernel of the reference build: FMUL a1*iy, FFMA a0*ix + t, FADD a2, FADD 0.5 */
 static inline float aff_coord2d(const float *a, float ix, float iy)
 {
-	float t = a[0] * ix;
-	t = fmaf(a[1], iy, t);
+	float t = a[1] * iy;
+	t = fmaf(a[0], ix, t);
 	t = t + a[2];
 	return (float)((double)t + 0.5);
 }

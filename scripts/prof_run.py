@@ -9,7 +9,7 @@ from microimagelib_b200 import device, synth
 
 shape = tuple(int(x) for x in os.environ.get("PROBE_SHAPE", "256,512,512").split(","))
 psf = synth.gaussian_psf((65, 65, 65), (4, 2, 2))
-img = synth.bead_image(shape, psf, noise=False)
+img = synth.bead_image(shape, psf, noise=False)  # noise-free: faster to generate, same kernels
 d = device.Decon(shape, 1)
 d.set_psf(0, psf)
 d.set_image(0, torch.from_numpy(img).cuda())

@@ -1,9 +1,26 @@
 // CPU emulation of the device FFT stages (fft_core.h) for tests/test_fft_emulation.py.
 // Test code: builds with plain g++, no CUDA.
 #include "../../microimagelib_b200/csrc/fft_plan.h"
+#include "../../microimagelib_b200/csrc/plane_sched.h"
 #include <string.h>
 
 extern "C" {
+
+// schedule of the fused plane stage: out[ticket] = {valid, phase, plane, tile, dep kind, dep plane}
+int emul_plane_tickets(int planes, int group, int tpp, int ring, int *out, int cap)
+{
+	const int total = plane_total_tickets(planes, group, tpp);
+	if (total > cap) return -total;
+	for (int t = 0; t < total; t++) {
+		PlaneWork w;
+		const bool ok = plane_ticket(t, planes, group, tpp, w);
+		int dp = -1;
+		const int k = ok ? plane_dependency(w, ring, &dp) : 0;
+		int *o = out + 6 * t;
+		o[0] = ok; o[1] = w.phase; o[2] = w.plane; o[3] = w.tile; o[4] = k; o[5] = dp;
+	}
+	return total;
+}
 
 int emul_plan(int n, int *radix, int *pos)
 {
