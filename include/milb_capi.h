@@ -59,6 +59,17 @@ int milb_decon_run(milb_decon_t *h, int iterations, int const_init, void *stream
 /* replaces cropgpu + D2H, src/api_decon.cpp:237-243 */
 int milb_decon_get_result(milb_decon_t *h, float *out, int on_device, void *stream);
 
+/* cache support for decon_singleview / decon_dualview (libapi.cpp keeps one prepared handle per device and view count):
+ * does the handle still own device memory (0 after cudaDeviceReset), drop its host side without cudaFree, and were its
+ * OTFs built from exactly these PSF bytes */
+int milb_decon_alive(const milb_decon_t *h);
+void milb_decon_abandon(milb_decon_t *h);
+int milb_decon_psf_matches(const milb_decon_t *h, int view, const float *psf, const float *psf_bp, const unsigned int *psfSize, int unmatched);
+/* frees every deconvolution context decon_singleview / decon_dualview keep cached between calls (all devices).  The
+ * reference frees everything per call (src/api_decon.cpp:245-262); this library keeps the prepared OTFs and buffers of
+ * the last call per (device, view count) until this is called, the process exits, or MILB_DECON_CACHE=0 is set. */
+void milb_decon_cache_release(void);
+
 /* tuning: planes of the half spectrum processed per launch of the three plane passes (0 = whole volume; any other
  * value also switches the fused plane stage off) */
 int milb_decon_set_chunk_planes(milb_decon_t *h, int planes);
@@ -129,6 +140,11 @@ int milb_reg_set_images(milb_reg_t *h, const float *target, const float *source,
 /* mean removal of both volumes and sqrt(sum t^2); if pre_tmx != NULL the source is first warped
  * by it (src/api_subfunc.cu:2817-2868).  Returns valueStatic in *sd_t. */
 int milb_reg_prepare(milb_reg_t *h, const float *pre_tmx, float *sd_t, void *stream);
+/* How the cost kernel samples the source: 1 (default) = the texture unit on a cudaArray, i.e. the reference's own
+ * tex3D(tex, tx, ty, tz) (include/cukernel.cuh:546) -- each sample is the float the reference gets; 0 = the software
+ * restatement of that fetch, bit-identical to the CPU oracle (the parity twin; env MILB_ZNCC_FETCH=sw selects it at
+ * creation).  Call before milb_reg_prepare. */
+int milb_reg_set_fetch(milb_reg_t *h, int hardware);
 /* K cost evaluations in one launch: costs[k] = -ZNCC for matrices[12*k..] ; +2 when sum s^2 == 0.
  * Replaces costfunc -> corrfunc -> corrkernel + sumgpu1D, src/api_subfunc.cu:954-988, 2377-2388. */
 int milb_reg_cost(milb_reg_t *h, const float *matrices, int K, float *costs, void *stream);

@@ -61,6 +61,10 @@ CAPI_PROTOS = {
     "milb_decon_get_result": (C.c_int, [_VP, _VP, C.c_int, _VP]),
     "milb_decon_set_chunk_planes": (C.c_int, [_VP, C.c_int]),
     "milb_decon_plane_stage_fused": (C.c_int, [_VP]),
+    "milb_decon_alive": (C.c_int, [_VP]),
+    "milb_decon_abandon": (None, [_VP]),
+    "milb_decon_psf_matches": (C.c_int, [_VP, C.c_int, _VP, _VP, _U, C.c_int]),
+    "milb_decon_cache_release": (None, []),
     "milb_decon_run_cufft_yardstick": (C.c_int, [_VP, C.c_int, C.c_int, _VP, _F]),
     "milb_decon_time_kernels": (C.c_int, [_VP, C.c_int, _F, _VP]),
     "milb_dslab_create": (C.c_int, [C.POINTER(_VP), _U, C.c_int, C.c_int, C.c_int]),
@@ -83,6 +87,7 @@ CAPI_PROTOS = {
     "milb_reg_destroy": (None, [_VP]),
     "milb_reg_set_images": (C.c_int, [_VP, _VP, _VP, C.c_int, _VP]),
     "milb_reg_prepare": (C.c_int, [_VP, _F, _F, _VP]),
+    "milb_reg_set_fetch": (C.c_int, [_VP, C.c_int]),
     "milb_reg_cost": (C.c_int, [_VP, _F, C.c_int, _F, _VP]),
     "milb_reg_cost_sums": (C.c_int, [_VP, _F, C.c_int, _D, _D, _VP]),
     "milb_reg_warp_source": (C.c_int, [_VP, _F, _VP, C.c_int, _VP]),

@@ -172,19 +172,25 @@ __global__ void __launch_bounds__(256) k_reduce_partial(const float *__restrict_
 	if (threadIdx.x == 0) partial[blockIdx.x] = sh[0];
 }
 
-__global__ void k_reduce_final(const double *__restrict__ partial, int np, double *__restrict__ out)
+// one block: strided partial sums per thread, then a shared-memory tree -- a fixed order, so results are reproducible
+__global__ void __launch_bounds__(256) k_reduce_final(const double *__restrict__ partial, int np, double *__restrict__ out)
 {
-	if (threadIdx.x == 0 && blockIdx.x == 0) {
-		double s = 0;
-		for (int i = 0; i < np; i++) s += partial[i];
-		out[0] = s;
+	__shared__ double sh[256];
+	double s = 0;
+	for (int i = threadIdx.x; i < np; i += 256) s += partial[i];
+	sh[threadIdx.x] = s;
+	__syncthreads();
+	for (int w = 128; w > 0; w >>= 1) {
+		if (threadIdx.x < w) sh[threadIdx.x] += sh[threadIdx.x + w];
+		__syncthreads();
 	}
+	if (threadIdx.x == 0) out[0] = sh[0];
 }
 
 int milb_sum_f64_async(const float *d_in, long long n, double *d_scratch, double *d_out, cudaStream_t st)
 {
 	k_reduce_partial<false><<<MILB_REDUCE_BLOCKS, 256, 0, st>>>(d_in, n, d_scratch);
-	k_reduce_final<<<1, 32, 0, st>>>(d_scratch, MILB_REDUCE_BLOCKS, d_out);
+	k_reduce_final<<<1, 256, 0, st>>>(d_scratch, MILB_REDUCE_BLOCKS, d_out);
 	milb_count_launches(2);
 	MILB_CUDA_TRY(cudaGetLastError());
 	return MILB_OK;
@@ -193,7 +199,7 @@ int milb_sum_f64_async(const float *d_in, long long n, double *d_scratch, double
 int milb_sumsq_f64_async(const float *d_in, long long n, double *d_scratch, double *d_out, cudaStream_t st)
 {
 	k_reduce_partial<true><<<MILB_REDUCE_BLOCKS, 256, 0, st>>>(d_in, n, d_scratch);
-	k_reduce_final<<<1, 32, 0, st>>>(d_scratch, MILB_REDUCE_BLOCKS, d_out);
+	k_reduce_final<<<1, 256, 0, st>>>(d_scratch, MILB_REDUCE_BLOCKS, d_out);
 	milb_count_launches(2);
 	MILB_CUDA_TRY(cudaGetLastError());
 	return MILB_OK;
@@ -259,17 +265,24 @@ int milb_decon_create(milb_decon_t **out, int nviews, const unsigned int *imSize
 	cudaError_t e = cudaSuccess;
 	if (h->fast) e = cudaMalloc(&h->S2, sizeof(float2) * h->nspec);
 	if (h->fast && e == cudaSuccess && h->Y == h->Z && milb_fast_ops(h->Y)->planes_fused) {
-		// fused plane stage (one persistent launch per convolution, intermediates L2-resident): MILB_PLANES_FUSED=0 switches
-		// back to three launches; MILB_FUSE_GROUP = planes per pipeline group (ring = 4 groups)
-		const char *fe = getenv("MILB_PLANES_FUSED"), *ge = getenv("MILB_FUSE_GROUP"), *re = getenv("MILB_FUSE_RING");
-		if (!(fe && fe[0] == '0')) {
+		// Fused plane stage (one persistent launch per convolution, hand-overs L2-resident; fft_fast.cuh k_planes_fused).
+		// Measured on B200 at 512x512x256: DRAM traffic of the stage 1.75 -> 1.03 GB per convolution, but 375 us against
+		// 356 us for the three launches -- with one 8192-point tile per SM the tiles are bound by the SM (shared-memory pipe,
+		// barriers), not by HBM, so saving the round trips does not pay yet.  Opt-in: MILB_PLANES_FUSED=1;
+		// MILB_FUSE_RING = planes of the scratch ring (default about 32 MB); MILB_FUSE_SPLIT="a,b" = share of the CTAs on
+		// phase A / phase B.
+		const char *fe = getenv("MILB_PLANES_FUSED"), *re = getenv("MILB_FUSE_RING"), *se = getenv("MILB_FUSE_SPLIT");
+		if (fe && fe[0] == '1') {
 			PlaneFuse &f = h->fuse;
 			f.planes = h->X / 2 + 1;
 			const long long plane_bytes = (long long)h->Y * h->Z * sizeof(float2);
-			int g = ge ? atoi(ge) : (int)((8ll << 20) / plane_bytes); // groups of about 8 MB
-			f.group = g < 1 ? 1 : (g > f.planes ? f.planes : g);
-			f.ring_planes = re ? atoi(re) : 4 * f.group;
-			if (f.ring_planes < 2 * f.group) f.ring_planes = 2 * f.group;
+			long long r = re ? atoll(re) : (32ll << 20) / plane_bytes;
+			r = r < 2 ? 2 : r;
+			f.ring_planes = (int)(r > f.planes ? f.planes : r);
+			if (se) {
+				float a = 0, b = 0;
+				if (sscanf(se, "%f,%f", &a, &b) == 2 && a > 0 && b > 0 && a + b < 1) { f.share[0] = a; f.share[1] = b; }
+			}
 			e = cudaMalloc(&f.ring, (size_t)f.ring_planes * plane_bytes);
 			if (e == cudaSuccess) e = cudaMalloc(&f.counters, sizeof(unsigned) * 2 * f.planes);
 			if (e == cudaSuccess) e = cudaMemset(f.counters, 0, sizeof(unsigned) * 2 * f.planes);
@@ -312,6 +325,30 @@ void milb_decon_destroy(milb_decon_t *h)
 	free_axis_plan(h->py);
 	free_axis_plan(h->pz);
 	delete h;
+}
+
+// 1 if the handle's device memory still exists (0 after the application reset the device)
+int milb_decon_alive(const milb_decon_t *h)
+{
+	if (!h || !h->E) return 0;
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, h->E) != cudaSuccess) { cudaGetLastError(); return 0; }
+	return a.type == cudaMemoryTypeDevice ? 1 : 0;
+}
+
+// releases the host side of a handle whose device memory went away with its context (no cudaFree)
+void milb_decon_abandon(milb_decon_t *h) { delete h; }
+
+// 1 if the PSF(s) given are byte-identical to the ones view `view` was prepared with
+int milb_decon_psf_matches(const milb_decon_t *h, int view, const float *psf, const float *psf_bp, const unsigned int *psfSize, int unmatched)
+{
+	if (!h || view < 0 || view >= h->nviews || !psf || !psfSize || !h->have_psf[view]) return 0;
+	const int pz = (int)psfSize[0], py = (int)psfSize[1], px = (int)psfSize[2];
+	if (px != h->psf_dims[0] || py != h->psf_dims[1] || pz != h->psf_dims[2] || (unmatched != 0) != h->unmatched) return 0;
+	const size_t n = (size_t)px * py * pz;
+	if (h->raw_psf[view][0].size() != n || memcmp(h->raw_psf[view][0].data(), psf, n * sizeof(float))) return 0;
+	if (unmatched && (!psf_bp || h->raw_psf[view][1].size() != n || memcmp(h->raw_psf[view][1].data(), psf_bp, n * sizeof(float)))) return 0;
+	return 1;
 }
 
 int milb_decon_fft_size(const milb_decon_t *h, unsigned int *fftSize)

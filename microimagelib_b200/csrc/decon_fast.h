@@ -18,7 +18,8 @@ struct PlaneFuse {
 	float2 *ring = nullptr;        // ring_planes x n x n complex: transposed-plane scratch that stays L2-resident
 	unsigned *counters = nullptr;  // 2 x planes: per-plane tiles finished by phase A / phase B, cumulative over launches
 	unsigned launches = 0;
-	int planes = 0, group = 0, ring_planes = 0;
+	int planes = 0, ring_planes = 0;
+	float share[2] = {0.285f, 0.46f}; // fraction of the CTAs that run phase A / phase B (the rest run phase C)
 };
 
 struct FastAxisOps {

@@ -187,19 +187,26 @@ void convT(float2 *in, float2 *out, const float2 *otf, const float2 *tw, int col
 
 bool planes_fused(float2 *S, const float2 *otf, const float2 *tw, PlaneFuse *pf, cudaStream_t st)
 {
-	if (g_fused_ctas < 1 || !pf || !pf->ring || !pf->counters) return false;
+	if (g_fused_ctas < 3 || !pf || !pf->ring || !pf->counters) return false;
 	constexpr int TPP = N / PL;
+	const int cap = (g_cap > 0 && g_cap < g_fused_ctas) ? g_cap : g_fused_ctas;
+	const long long tiles = (long long)pf->planes * TPP;
+	const int grid = (int)(3 * tiles < cap ? 3 * tiles : cap);
+	if (grid < 3) return false;
+	// roles: CTAs per phase in proportion to the phases' measured cost per tile (Y forward : Z conv : Y inverse)
+	int nA = (int)(grid * pf->share[0] + 0.5f), nB = (int)(grid * pf->share[1] + 0.5f);
+	nA = nA < 1 ? 1 : nA;
+	nB = nB < 1 ? 1 : nB;
+	if (nA + nB > grid - 1) { nB = grid - 1 - nA; if (nB < 1) { nB = 1; nA = grid - 2; } }
 	PlaneSched sc;
 	sc.doneA = pf->counters;
 	sc.doneB = pf->counters + pf->planes;
 	pf->launches++;
 	sc.target = pf->launches * (unsigned)TPP;
 	sc.planes = pf->planes;
-	sc.group = pf->group;
 	sc.ring = pf->ring_planes;
-	const long long total = plane_total_tickets(pf->planes, pf->group, TPP);
-	const int cap = (g_cap > 0 && g_cap < g_fused_ctas) ? g_cap : g_fused_ctas;
-	const int grid = (int)(total < cap ? total : cap);
+	sc.nA = nA;
+	sc.nB = nB;
 	k_planes_fused<N, PL, PT><<<grid, PT, SMP3, st>>>(S, pf->ring, otf, tw, sc);
 	return true;
 }

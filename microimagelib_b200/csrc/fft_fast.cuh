@@ -711,14 +711,21 @@ k_zconvT(float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__rest
 //   phase B (Z conv):     ring slot [z][ky'], * otf plane p, -> S plane p [ky'][z] (transposed back)
 //   phase C (Y inverse):  S plane p [ky'][z] -> S plane p [y][z]                   (in place)
 //
-// The ring is a small scratch (a few groups of planes) that is rewritten before L2 ever evicts it, and plane p of S is
-// rewritten by phase B and re-read by phase C while still resident.  Work is a static list of "tickets" in software-
-// pipeline order -- step s = { A of plane group s, B of group s-1, C of group s-2 } -- dealt round-robin to the
-// CTAs (ticket = blockIdx.x + i * gridDim.x).  A tile of phase B (C) needs ALL tiles of phase A (B) of its plane:
-// per-plane completion counters in global memory (release: stores, barrier, __threadfence, atomicAdd by one thread;
-// acquire: relaxed poll, then the dependent cp.async).  By the pipeline order a ticket's producers were dealt three
-// group-phases earlier, so the polls almost never wait; every ticket only depends on earlier tickets and all CTAs are
-// co-resident (grid <= resident CTAs), so the scheme cannot deadlock.  A poll that never succeeds traps instead of hanging.
+// The ring is a small scratch (a few planes) that is rewritten before L2 ever evicts it, and plane p of S is rewritten
+// by phase B and re-read by phase C while still resident.  The CTAs are split into three ROLES (blockIdx ranges sized by
+// the phases' cost, PlaneSched::nA / nB): a CTA only ever runs one phase -- its own tight double-buffered loop, its own
+// part of the instruction cache -- and the three groups form a dataflow pipeline over the planes: every role walks the
+// tiles of planes 0, 1, 2, ... dealt round-robin within the role.  A tile of phase B (C) needs ALL tiles of phase A (B)
+// of its plane, and phase A may only overwrite ring slot p mod ring once phase B has consumed plane p - ring:
+// per-plane completion counters in global memory.
+//   release: a tile's stores, then -- one tile later, just before the NEXT tile's stores, when none of the signalling
+//            thread's own accesses are in flight any more, so the fence does not stall the CTA -- barrier-ordered
+//            __threadfence + atomicAdd by one thread;
+//   acquire: relaxed poll issued one tile ahead, made CTA-uniform by the tile's top barrier (__syncthreads_and), then the
+//            dependent cp.async.  A dependency that is not ready when polled is waited for at the end of the tile (after
+//            the CTA's pending signal has been sent, so CTAs never wait on each other's unsent signals).
+// All CTAs are co-resident (grid <= resident CTAs) and every dependency points to an earlier plane or an earlier phase of
+// the same plane, so the pipeline cannot deadlock; a poll that never succeeds traps instead of hanging the GPU.
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
 {
 	unsigned v;
@@ -733,6 +740,14 @@ __device__ __forceinline__ void spin_until(const unsigned *p, unsigned target)
 	}
 	__threadfence();
 }
+__device__ __forceinline__ void plane_signal(unsigned *&sig)
+{
+	if (sig && threadIdx.x == 0) {
+		__threadfence();
+		atomicAdd(sig, 1u);
+	}
+	sig = nullptr;
+}
 
 template <int N, int L, int T>
 __global__ void __launch_bounds__(T, (N * L <= 4096) ? 2 : 1)
@@ -745,58 +760,79 @@ k_planes_fused(float2 *__restrict__ S, float2 *__restrict__ ring, const float2 *
 	extern __shared__ float2 sm[];
 	float2 *tile2 = sm + 2 * G::elems, *tw = sm + 3 * G::elems; // tile2: transposition buffer, and the OTF landing buffer of phase B
 	load_tw<N>(tw, g_tw);
-	PlaneTw<N, L, T> pt;
-	constexpr bool kRt = PlaneTw<N, L, T>::kUse;
-	if constexpr (kRt) pt.load(g_tw);
 	constexpr long long pe = (long long)N * N;
-	const int total = plane_total_tickets(sc.planes, sc.group, TPP);
-	auto src_of = [&](const PlaneWork &w) -> const float2 * {
-		return (w.phase == 1 ? ring + (long long)(w.plane % sc.ring) * pe : S + (long long)w.plane * pe) + w.tile * L;
+	// role of this CTA and its rank within the role
+	int phase, rank, nrole;
+	plane_role((int)blockIdx.x, (int)gridDim.x, sc.nA, sc.nB, &phase, &rank, &nrole);
+	const int ntiles = sc.planes * TPP;
+	auto src_of = [&](int j) -> const float2 * {
+		const int p = j / TPP, ti = j - p * TPP;
+		return (phase == 1 ? ring + (long long)(p % sc.ring) * pe : S + (long long)p * pe) + ti * L;
 	};
-	auto dep_of = [&](const PlaneWork &w) -> const unsigned * {
+	auto dep_of = [&](int j) -> const unsigned * {
+		PlaneWork w = {phase, j / TPP, 0};
 		int dp;
 		const int k = plane_dependency(w, sc.ring, &dp);
 		return k == 0 ? nullptr : (k == 1 ? sc.doneA : sc.doneB) + dp;
 	};
-	int t = blockIdx.x;
-	PlaneWork cur;
-	while (t < total && !plane_ticket(t, sc.planes, sc.group, TPP, cur)) t += gridDim.x;
-	if (t >= total) return;
-	if (const unsigned *d = dep_of(cur)) spin_until(d, sc.target);
-	tile_load_async<N, L, T>(sm, src_of(cur), N);
+	auto poll = [&](int j) -> unsigned { // counter value a tile waits for (sc.target: nothing to wait for)
+		if (j >= ntiles) return sc.target;
+		const unsigned *d = dep_of(j);
+		return d ? ld_relaxed_u32(d) : sc.target;
+	};
+	int j = rank;
+	if (j >= ntiles) return;
+	if (const unsigned *d = dep_of(j)) spin_until(d, sc.target);
+	tile_load_async<N, L, T>(sm, src_of(j), N);
 	cp_async_commit();
-	for (int buf = 0;; buf ^= 1) {
-		unsigned *sig = nullptr; // completion counter of this tile's plane and phase
-		int tn = t + gridDim.x;
-		PlaneWork nx;
-		while (tn < total && !plane_ticket(tn, sc.planes, sc.group, TPP, nx)) tn += gridDim.x;
-		const bool have_next = tn < total;
-		const unsigned *ndep = have_next ? dep_of(nx) : nullptr;
-		cp_async_wait<0>();
-		__syncthreads(); // this tile has landed; everybody is done with the previous tile
-		const unsigned nv = ndep ? ld_relaxed_u32(ndep) : sc.target; // polled now, looked at after the first stage
-		float2 *tile = sm + buf * G::elems;
-		const long long poff = (long long)cur.plane * pe;
-		if (cur.phase == 1) tile_load_async<N, L, T>(tile2, otf + poff + cur.tile * L, N);
-		cp_async_commit();
-		if (cur.phase == 2) {
-			inv_but_last<N, L, T, false>(tile, tw);
-		} else {
-			if constexpr (kRt) fwd_but_last_rt<N, L, T>(tile, pt);
+	unsigned pv = poll(j + nrole);   // dependency of the next tile, looked at at the top of this one
+	unsigned *sig = nullptr;          // completion counter of the previous tile, not yet signalled
+
+	if (phase == 0) {
+		PlaneTw<N, L, T> pt;
+		if constexpr (PlaneTw<N, L, T>::kUse) pt.load(g_tw);
+		for (int buf = 0; j < ntiles; j += nrole, buf ^= 1) {
+			const int jn = j + nrole;
+			cp_async_wait<0>();
+			const bool ready = __syncthreads_and((int)(pv - sc.target) >= 0) && jn < ntiles;
+			if (ready) tile_load_async<N, L, T>(sm + (buf ^ 1) * G::elems, src_of(jn), N);
+			cp_async_commit();
+			pv = poll(jn + nrole);
+			float2 *tile = sm + buf * G::elems;
+			if constexpr (PlaneTw<N, L, T>::kUse) fwd_but_last_rt<N, L, T>(tile, pt);
 			else fwd_but_last<N, L, T>(tile, tw);
-		}
-		bool issued = !have_next;
-		if (have_next && (int)(nv - sc.target) >= 0) {
-			tile_load_async<N, L, T>(sm + (buf ^ 1) * G::elems, src_of(nx), N);
-			issued = true;
-		}
-		cp_async_commit();
-		if (cur.phase == 0) {
 			fwd_last<N, L, T>(tile, tw, [tile2](int r, int l, float2 v) { tile2[swz<L>(r, l)] = v; });
 			__syncthreads();
-			store_transposed<N, L, T>(tile2, ring + (long long)(cur.plane % sc.ring) * pe + (long long)cur.tile * L * N, N);
-			sig = sc.doneA + cur.plane;
-		} else if (cur.phase == 1) {
+			plane_signal(sig);
+			const int p = j / TPP, ti = j - p * TPP;
+			store_transposed<N, L, T>(tile2, ring + (long long)(p % sc.ring) * pe + (long long)ti * L * N, N);
+			sig = sc.doneA + p;
+			if (!ready && jn < ntiles) {
+				__syncthreads();
+				plane_signal(sig);
+				if (const unsigned *d = dep_of(jn)) spin_until(d, sc.target);
+				tile_load_async<N, L, T>(sm + (buf ^ 1) * G::elems, src_of(jn), N);
+				cp_async_commit();
+				pv = poll(jn + nrole);
+			}
+		}
+	} else if (phase == 1) {
+		PlaneTw<N, L, T> pt;
+		constexpr bool kRt = PlaneTw<N, L, T>::kUse;
+		if constexpr (kRt) pt.load(g_tw);
+		for (int buf = 0; j < ntiles; j += nrole, buf ^= 1) {
+			const int jn = j + nrole;
+			const int p = j / TPP, ti = j - p * TPP;
+			cp_async_wait<0>();
+			const bool ready = __syncthreads_and((int)(pv - sc.target) >= 0) && jn < ntiles;
+			tile_load_async<N, L, T>(tile2, otf + (long long)p * pe + ti * L, N);
+			cp_async_commit();
+			if (ready) tile_load_async<N, L, T>(sm + (buf ^ 1) * G::elems, src_of(jn), N);
+			cp_async_commit();
+			pv = poll(jn + nrole);
+			float2 *tile = sm + buf * G::elems;
+			if constexpr (kRt) fwd_but_last_rt<N, L, T>(tile, pt);
+			else fwd_but_last<N, L, T>(tile, tw);
 			cp_async_wait<1>(); // the OTF tile (older group) has landed; the next data tile may still fly
 			__syncthreads();
 			{ // last forward stage, OTF product and first inverse stage share one register butterfly
@@ -809,13 +845,13 @@ k_planes_fused(float2 *__restrict__ S, float2 *__restrict__ ring, const float2 *
 					const int lane = bl % L, base = (bl / L) * R;
 					float2 v[R];
 #pragma unroll
-					for (int j = 0; j < R; j++) v[j] = tile[prow<L>(base + j) * L + lane];
+					for (int q = 0; q < R; q++) v[q] = tile[prow<L>(base + q) * L + lane];
 					fbfly<R, false>(v);
 #pragma unroll
-					for (int j = 0; j < R; j++) v[j] = cmul(v[j], tile2[prow<L>(base + j) * L + lane]); // multicomplex3Dkernel
+					for (int q = 0; q < R; q++) v[q] = cmul(v[q], tile2[prow<L>(base + q) * L + lane]); // multicomplex3Dkernel
 					fbfly<R, true>(v);
 #pragma unroll
-					for (int j = 0; j < R; j++) tile[prow<L>(base + j) * L + lane] = v[j];
+					for (int q = 0; q < R; q++) tile[prow<L>(base + q) * L + lane] = v[q];
 				}
 				__syncthreads();
 			}
@@ -827,29 +863,41 @@ k_planes_fused(float2 *__restrict__ S, float2 *__restrict__ ring, const float2 *
 				sstage_to<N, L, T, P::r0, N, true>(tile, tw, [tile2](int r, int l, float2 v) { tile2[swz<L>(r, l)] = v; });
 			}
 			__syncthreads();
-			store_transposed<N, L, T>(tile2, S + poff + (long long)cur.tile * L * N, N);
-			sig = sc.doneB + cur.plane;
-		} else {
-			float2 *p = S + poff + cur.tile * L;
-			sstage_to<N, L, T, P::r0, N, true>(tile, tw, [p](int r, int l, float2 v) { p[(long long)r * N + l] = v; });
-			sig = nullptr;
-		}
-		if (sig) { // release: every thread's stores, barrier, fence + counter increment by one thread
-			__syncthreads();
-			if (threadIdx.x == 0) {
-				__threadfence();
-				atomicAdd(sig, 1u);
+			plane_signal(sig);
+			store_transposed<N, L, T>(tile2, S + (long long)p * pe + (long long)ti * L * N, N);
+			sig = sc.doneB + p;
+			if (!ready && jn < ntiles) {
+				__syncthreads();
+				plane_signal(sig);
+				if (const unsigned *d = dep_of(jn)) spin_until(d, sc.target);
+				tile_load_async<N, L, T>(sm + (buf ^ 1) * G::elems, src_of(jn), N);
+				cp_async_commit();
+				pv = poll(jn + nrole);
 			}
 		}
-		if (!issued) { // the next tile's producers were not done when polled: wait for them now (after this tile's signal is out)
-			spin_until(ndep, sc.target);
-			tile_load_async<N, L, T>(sm + (buf ^ 1) * G::elems, src_of(nx), N);
+	} else {
+		for (int buf = 0; j < ntiles; j += nrole, buf ^= 1) {
+			const int jn = j + nrole;
+			const int p = j / TPP, ti = j - p * TPP;
+			cp_async_wait<0>();
+			const bool ready = __syncthreads_and((int)(pv - sc.target) >= 0) && jn < ntiles;
+			if (ready) tile_load_async<N, L, T>(sm + (buf ^ 1) * G::elems, src_of(jn), N);
+			cp_async_commit();
+			pv = poll(jn + nrole);
+			float2 *tile = sm + buf * G::elems;
+			inv_but_last<N, L, T, false>(tile, tw);
+			float2 *o = S + (long long)p * pe + ti * L;
+			sstage_to<N, L, T, P::r0, N, true>(tile, tw, [o](int r, int l, float2 v) { o[(long long)r * N + l] = v; });
+			if (!ready && jn < ntiles) { // nobody waits for phase C: nothing to signal
+				if (const unsigned *d = dep_of(jn)) spin_until(d, sc.target);
+				tile_load_async<N, L, T>(sm + (buf ^ 1) * G::elems, src_of(jn), N);
+				cp_async_commit();
+				pv = poll(jn + nrole);
+			}
 		}
-		cp_async_commit();
-		if (!have_next) break;
-		cur = nx;
-		t = tn;
 	}
+	__syncthreads();
+	plane_signal(sig);
 }
 
 // Where row k of the tile's output spectrum goes.  !PEER: my own half spectrum, spec[k*M + col0 ..].

@@ -53,30 +53,65 @@ float free_mb()
 
 double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
-unsigned long long fnv1a(const void *p, size_t n, unsigned long long h = 1469598103934665603ull)
-{
-	const unsigned char *b = (const unsigned char *)p;
-	for (size_t i = 0; i < n; i++) { h ^= b[i]; h *= 1099511628211ull; }
-	return h;
-}
-
-// One cached deconvolution context per (device, nviews): the batch app calls decon_dualview once
-// per time point with the same sizes and PSFs (src/spim_fusion_batch.cpp:881); the reference
-// re-allocates and recomputes all OTFs every call, here they are kept while the key matches.
+// Cached deconvolution contexts, one per (device, nviews): the batch app calls decon_dualview once per time point with
+// the same sizes and PSFs (src/spim_fusion_batch.cpp:881); the reference re-allocates and recomputes all OTFs every
+// call, here they are kept while the key matches.
+//   - A caller CHECKS OUT the entry of its (device, nviews) under the mutex and works on it unlocked, so calls on
+//     different devices / threads do not serialise; a second caller of the same key simply builds its own context.
+//   - A hit is confirmed by comparing the caller's PSF bytes with the copy the handle keeps (milb_decon_psf_matches),
+//     not by a hash.
+//   - milb_decon_cache_release() frees everything (also registered with atexit); MILB_DECON_CACHE=0 restores the
+//     reference's allocate-and-free-per-call behaviour.  If the application reset the device in between, the stale entry
+//     is detected (its pointers are no longer device memory) and dropped without being freed.
 struct DeconCache {
 	milb_decon_t *h = nullptr;
 	int device = -1, nviews = 0;
 	unsigned int im[3] = {0, 0, 0}, psf[3] = {0, 0, 0};
-	unsigned long long psf_hash = 0;
+	bool unmatch = false;
 	float free_mb_after = -1.f; // free device memory when the handle was last left in place
 };
-DeconCache g_cache[2];
+std::vector<DeconCache> g_cache;
 std::mutex g_cache_mu;
+bool g_cache_atexit = false;
 
 bool cache_enabled()
 {
 	const char *e = getenv("MILB_DECON_CACHE");
 	return !(e && e[0] == '0');
+}
+
+// takes the entry of (device, nviews) out of the cache (h == nullptr if there is none)
+DeconCache cache_checkout(int device, int nviews)
+{
+	std::lock_guard<std::mutex> lock(g_cache_mu);
+	for (size_t i = 0; i < g_cache.size(); i++)
+		if (g_cache[i].device == device && g_cache[i].nviews == nviews) {
+			DeconCache c = g_cache[i];
+			g_cache.erase(g_cache.begin() + i);
+			return c;
+		}
+	DeconCache c;
+	c.device = device;
+	c.nviews = nviews;
+	return c;
+}
+
+// puts an entry back; an entry another thread stored for the same key meanwhile is released
+void cache_checkin(const DeconCache &c)
+{
+	milb_decon_t *drop = nullptr;
+	{
+		std::lock_guard<std::mutex> lock(g_cache_mu);
+		if (!g_cache_atexit) { g_cache_atexit = true; atexit(milb_decon_cache_release); }
+		for (size_t i = 0; i < g_cache.size(); i++)
+			if (g_cache[i].device == c.device && g_cache[i].nviews == c.nviews) {
+				drop = g_cache[i].h;
+				g_cache.erase(g_cache.begin() + i);
+				break;
+			}
+		g_cache.push_back(c);
+	}
+	if (drop) milb_decon_destroy(drop);
 }
 
 int decon_common(int nviews, float *h_decon, float *const h_img[2], unsigned int *imSize, float *const h_psf[2],
@@ -95,14 +130,19 @@ int decon_common(int nviews, float *h_decon, float *const h_img[2], unsigned int
 		return bad_mode_rc;
 	}
 	cuda_fatal(cudaSetDevice(deviceNum), "cudaSetDevice");
-	// cudaMemGetInfo is a kernel-mode round trip measured at anything from 0.1 to 30 ms per call here, and
-	// the reference issues it four times per deconvolution for its memory records.  This library changes
-	// the device's free memory only when it creates or replaces the cached handle, so the records are
-	// re-queried on those calls only; otherwise the figures of the call that left the handle in place
-	// are reported.
-	std::lock_guard<std::mutex> lock(g_cache_mu);
-	DeconCache &c = g_cache[nviews - 1];
-	const bool same_handle = cache_enabled() && c.h && c.device == deviceNum && c.nviews == nviews && c.free_mb_after >= 0;
+	const bool use_cache = cache_enabled();
+	DeconCache c = use_cache ? cache_checkout(deviceNum, nviews) : DeconCache();
+	c.device = deviceNum;
+	c.nviews = nviews;
+	if (c.h && !milb_decon_alive(c.h)) { // the application reset the device: the old allocations are gone with the context
+		milb_decon_abandon(c.h);
+		c.h = nullptr;
+	}
+	// cudaMemGetInfo is a kernel-mode round trip measured at anything from 0.1 to 30 ms per call here, and the reference
+	// issues it four times per deconvolution for its memory records.  This library changes the device's free memory only
+	// when it creates or replaces the cached handle, so the records are re-queried on those calls only; otherwise the
+	// figures of the call that left the handle in place are reported (deconRecords[1..5] are then equal).
+	const bool same_handle = c.h && c.free_mb_after >= 0;
 	deconRecords[1] = same_handle ? c.free_mb_after : free_mb();
 	printf("...GPU free memory(at beginning) is %.0f MBites\n", deconRecords[1]);
 	// Every mode runs the all-on-GPU path: 180 GB of HBM holds the largest documented case
@@ -110,27 +150,19 @@ int decon_common(int nviews, float *h_decon, float *const h_img[2], unsigned int
 	deconRecords[0] = 1;
 	const double t1 = now_s();
 
-	const size_t npsf = (size_t)psfSize[0] * psfSize[1] * psfSize[2];
-	unsigned long long hash = fnv1a(&flagUnmatch, sizeof flagUnmatch);
-	for (int v = 0; v < nviews; v++) {
-		hash = fnv1a(h_psf[v], npsf * sizeof(float), hash);
-		if (flagUnmatch) hash = fnv1a(h_psf_bp[v], npsf * sizeof(float), hash);
-	}
-	const bool hit = cache_enabled() && c.h && c.device == deviceNum && c.nviews == nviews &&
-		!memcmp(c.im, imSize, sizeof c.im) && !memcmp(c.psf, psfSize, sizeof c.psf) && c.psf_hash == hash;
+	bool hit = c.h && !memcmp(c.im, imSize, sizeof c.im) && !memcmp(c.psf, psfSize, sizeof c.psf) && c.unmatch == flagUnmatch;
+	for (int v = 0; v < nviews && hit; v++)
+		hit = milb_decon_psf_matches(c.h, v, h_psf[v], flagUnmatch ? h_psf_bp[v] : nullptr, psfSize, flagUnmatch ? 1 : 0) == 1;
 	if (!hit) {
 		if (c.h) { milb_decon_destroy(c.h); c.h = nullptr; }
 		fatal_if(milb_decon_create(&c.h, nviews, imSize), "****Memory allocating fails... GPU out of memory !!!!*****");
 		for (int v = 0; v < nviews; v++)
 			fatal_if(milb_decon_set_psf(c.h, v, h_psf[v], flagUnmatch ? h_psf_bp[v] : nullptr, psfSize, flagUnmatch ? 1 : 0, 0, nullptr),
 				"****PSF and OTF preparation failed !!!!*****");
-		c.device = deviceNum; c.nviews = nviews; c.psf_hash = hash;
+		c.unmatch = flagUnmatch;
 		memcpy(c.im, imSize, sizeof c.im);
 		memcpy(c.psf, psfSize, sizeof c.psf);
 	}
-	// cudaMemGetInfo is a kernel-mode round trip that was measured at up to 30 ms right after the loop;
-	// when the cached handle is reused nothing is allocated or released during the call, so the later
-	// memory records equal the first one and are not queried again.
 	deconRecords[2] = (hit && same_handle) ? deconRecords[1] : free_mb();
 	printf("...GPU free memory(after mallocing) is %.0f MBites\n", deconRecords[2]);
 	for (int v = 0; v < nviews; v++) fatal_if(milb_decon_set_image(c.h, v, h_img[v], 0, nullptr), "****Image preparation failed !!!!*****");
@@ -140,11 +172,14 @@ int decon_common(int nviews, float *h_decon, float *const h_img[2], unsigned int
 	const double t3 = now_s();
 	deconRecords[4] = (hit && same_handle) ? deconRecords[1] : free_mb();
 	printf("...GPU free memory (after processing) is %.0f MBites\n", deconRecords[4]);
-	if (!cache_enabled()) { milb_decon_destroy(c.h); c.h = nullptr; }
+	if (!use_cache) { milb_decon_destroy(c.h); c.h = nullptr; }
 	const double t_end = now_s();
 	deconRecords[5] = (hit && same_handle) ? deconRecords[1] : free_mb();
-	c.free_mb_after = cache_enabled() ? deconRecords[5] : -1.f;
 	printf("GPU free memory (after variable released): %.0f MBites\n", deconRecords[5]);
+	if (use_cache) {
+		c.free_mb_after = deconRecords[5];
+		cache_checkin(c);
+	}
 	deconRecords[6] = (float)(t1 - t_start);
 	deconRecords[7] = (float)(t2 - t1);
 	deconRecords[8] = (float)(t3 - t2);
@@ -159,6 +194,24 @@ extern "C" {
 // ---------------------------------------------------------------------------------------------
 // deconvolution
 // ---------------------------------------------------------------------------------------------
+// frees every cached deconvolution context (all devices); safe to call at any time, also registered with atexit
+void milb_decon_cache_release(void)
+{
+	std::vector<DeconCache> all;
+	{
+		std::lock_guard<std::mutex> lock(g_cache_mu);
+		all.swap(g_cache);
+	}
+	int cur = 0;
+	const bool have_dev = cudaGetDevice(&cur) == cudaSuccess;
+	for (auto &c : all) {
+		if (!c.h) continue;
+		if (cudaSetDevice(c.device) == cudaSuccess && milb_decon_alive(c.h)) milb_decon_destroy(c.h);
+		else milb_decon_abandon(c.h);
+	}
+	if (have_dev) cudaSetDevice(cur);
+}
+
 int decon_singleview(float *h_decon, float *h_img, unsigned int *imSize, float *h_psf, unsigned int *psfSize, bool flagConstInitial,
 	int itNumForDecon, int deviceNum, int gpuMemMode, bool verbose, float *deconRecords, bool flagUnmatch, float *h_psf_bp)
 {

@@ -1,11 +1,6 @@
-// Work list of the fused plane stage (fft_fast.cuh k_planes_fused): which (phase, plane, tile) a ticket is, and which
-// completion counter it waits for.  __host__ __device__ so that tests/test_plane_sched.py checks the schedule on the CPU
-// (coverage, dependency order, ring-slot reuse) before it runs on a GPU.
-//
-// Tickets are laid out in software-pipeline order over groups of `group` planes:
-//   step s = { phase A (Y forward) of group s | phase B (Z conv) of group s-1 | phase C (Y inverse) of group s-2 },
-// `tpp` tiles per plane and phase.  Tickets whose group does not exist (pipeline fill / drain, tail of the last group)
-// are holes that the CTAs skip.
+// Scheduling rules of the fused plane stage (fft_fast.cuh k_planes_fused): which role a CTA has, which tiles it walks and
+// which completion counter a tile waits for.  __host__ __device__ so that tests/test_plane_sched.py replays the pipeline
+// on the CPU (coverage, progress without deadlock, ring-slot reuse) before it runs on a GPU.
 #pragma once
 #if defined(__CUDACC__)
 #define MILB_PS_HD __host__ __device__ __forceinline__
@@ -16,28 +11,23 @@
 struct PlaneSched {
 	unsigned *doneA, *doneB; // per plane: tiles finished by phase A / B, cumulative over launches of this handle
 	unsigned target;         // value a plane's counter has once the phase is complete in THIS launch (launches * tiles per plane)
-	int planes, group, ring; // kx planes, planes per pipeline group, ring slots (planes)
+	int planes, ring;        // kx planes, ring slots (planes) of the transposed-plane scratch
+	int nA, nB;              // CTAs [0, nA) run phase A, [nA, nA + nB) phase B, the rest phase C
 };
 struct PlaneWork {
 	int phase, plane, tile;
 };
 
-MILB_PS_HD int plane_total_tickets(int planes, int group, int tpp) { return ((planes + group - 1) / group + 2) * 3 * group * tpp; }
-
-// false: the ticket is a hole
-MILB_PS_HD bool plane_ticket(int ticket, int planes, int group, int tpp, PlaneWork &w)
+// CTA b of a grid of `grid`: its phase (0 A: Y forward, 1 B: Z conv, 2 C: Y inverse), its rank within the role and the
+// role's size.  The role walks tiles j = rank, rank + nrole, ... of [0, planes * tiles_per_plane), plane = j / tiles_per_plane.
+MILB_PS_HD void plane_role(int b, int grid, int nA, int nB, int *phase, int *rank, int *nrole)
 {
-	const int per_phase = group * tpp, per_step = 3 * per_phase;
-	const int step = ticket / per_step, r = ticket - step * per_step;
-	w.phase = r / per_phase;
-	const int q = r - w.phase * per_phase;
-	const int g = step - w.phase;
-	w.plane = g * group + q / tpp;
-	w.tile = q % tpp;
-	return g >= 0 && w.plane < planes;
+	*phase = b < nA ? 0 : (b < nA + nB ? 1 : 2);
+	*rank = *phase == 0 ? b : (*phase == 1 ? b - nA : b - nA - nB);
+	*nrole = *phase == 0 ? nA : (*phase == 1 ? nB : grid - nA - nB);
 }
 
-// What a ticket waits for: 0 nothing, 1 phase A of plane *dep_plane, 2 phase B of plane *dep_plane.
+// What a tile waits for: 0 nothing, 1 phase A of plane *dep_plane, 2 phase B of plane *dep_plane.
 //   A(p) overwrites ring slot p mod ring: the slot's previous user, plane p - ring, must have been consumed by its phase B
 //   B(p) reads every tile phase A wrote for plane p;  C(p) reads every tile phase B wrote for plane p
 MILB_PS_HD int plane_dependency(const PlaneWork &w, int ring, int *dep_plane)

@@ -41,9 +41,14 @@ __global__ void __launch_bounds__(256) k_affine_warp(float *__restrict__ out, co
 // ---- fused warp + ZNCC sums (a14), K candidate matrices per launch -------------------------------
 // Tiles of 32(x) x 8(y) x ZT(z) target voxels; a block walks its tiles in a fixed order and every
 // thread owns fixed voxels, so the double-precision partial sums are reproducible run to run.
+//
+// HW = true: the source is sampled by the texture unit from a cudaArray (linear filter, clamp addressing, un-normalised
+// coordinates) -- exactly the reference's mechanism (include/cukernel.cuh:546, src/api_subfunc.cu:885-895), so each sample
+// is the very float the reference's tex3D returns, and the eight gathers + fixed-point weights leave the SM's issue slots.
+// HW = false: the software restatement of that fetch (tex_sw.cuh), bit-identical to the CPU oracle; kept as the parity twin.
 #define REG_ZT 8
-template <int K>
-__global__ void __launch_bounds__(256) k_zncc(const float *__restrict__ tgt, const float *__restrict__ src, int sx, int sy, int sz,
+template <int K, bool HW>
+__global__ void __launch_bounds__(256) k_zncc(const float *__restrict__ tgt, const float *__restrict__ src, cudaTextureObject_t tex, int sx, int sy, int sz,
 	AffBatch aff, double *__restrict__ partial /* [gridDim.x][K][2] */)
 {
 	__shared__ double sh[8][K][2];
@@ -64,7 +69,7 @@ __global__ void __launch_bounds__(256) k_zncc(const float *__restrict__ tgt, con
 		const int z_end = min(sz, (bz + 1) * REG_ZT);
 		const long long pl = (long long)sx * sy;
 		const float *tp = tgt + (x + (long long)y * sx + (long long)(bz * REG_ZT) * pl);
-		for (int z = bz * REG_ZT; z < z_end; z++, tp += pl) { // (unrolling by 2 costs occupancy: 0.40 -> 0.45 ms)
+		for (int z = bz * REG_ZT; z < z_end; z++, tp += pl) { // (unrolling costs more than it gives: software fetch x2 0.40 -> 0.45 ms; hardware fetch x4 K=8 0.17 -> 0.24 ms)
 			const float fz = (float)z;
 			const float t = *tp;
 #pragma unroll
@@ -72,8 +77,10 @@ __global__ void __launch_bounds__(256) k_zncc(const float *__restrict__ tgt, con
 				const float *a = aff.m[k];
 				const float cx = aff_coord(a + 0, fx, fy, fz), cy = aff_coord(a + 4, fx, fy, fz), cz = aff_coord(a + 8, fx, fy, fz);
 				float s = 0.f;
-				if (cx > 0 && cx < fsx && cy > 0 && cy < fsy && cz > 0 && cz < fsz)
-					s = tex3d_linear(src, sx, sy, sz, cx, cy, cz);
+				if (cx > 0 && cx < fsx && cy > 0 && cy < fsy && cz > 0 && cz < fsz) {
+					if constexpr (HW) s = tex3D<float>(tex, cx, cy, cz);
+					else s = tex3d_linear(src, sx, sy, sz, cx, cy, cz);
+				}
 				ss[k] = fma((double)s, (double)s, ss[k]); // exact product, one rounding == (double)s*s then +=
 				st[k] = fma((double)s, (double)t, st[k]);
 			}
@@ -138,6 +145,10 @@ struct milb_reg {
 	int grid = 0;
 	float sd_t = 0.f;
 	bool have_images = false, prepared = false;
+	// hardware fetch path: the mean-removed source as a 3-D cudaArray behind a linear-filter texture object
+	cudaArray_t src_arr = nullptr;
+	cudaTextureObject_t src_tex = 0;
+	bool hw_fetch = true;        // MILB_ZNCC_FETCH=sw or milb_reg_set_fetch(h, 0): software restatement (bit-identical to the oracle)
 };
 
 static int reg_grid_for(long long n) { long long b = cdiv_ll(n, 256); return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
@@ -150,6 +161,10 @@ int milb_reg_create(milb_reg_t **out, const unsigned int *sizeT)
 	h->n = (long long)h->sx * h->sy * h->sz;
 	const long long ntiles = (long long)((h->sx + 31) / 32) * ((h->sy + 7) / 8) * ((h->sz + REG_ZT - 1) / REG_ZT);
 	h->grid = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
+	{
+		const char *fe = getenv("MILB_ZNCC_FETCH");
+		h->hw_fetch = !(fe && (fe[0] == 's' || fe[0] == '0'));
+	}
 	cudaError_t e = cudaMalloc(&h->tgt_raw, sizeof(float) * h->n);
 	if (e == cudaSuccess) e = cudaMalloc(&h->src_raw, sizeof(float) * h->n);
 	if (e == cudaSuccess) e = cudaMalloc(&h->tgt_dm, sizeof(float) * h->n);
@@ -174,6 +189,8 @@ void milb_reg_destroy(milb_reg_t *h)
 	cudaFree(h->tgt_raw); cudaFree(h->src_raw); cudaFree(h->tgt_dm); cudaFree(h->src_dm); cudaFree(h->tmp);
 	cudaFree(h->d_red); cudaFree(h->d_partial); cudaFree(h->d_out);
 	if (h->h_out) cudaFreeHost(h->h_out);
+	if (h->src_tex) cudaDestroyTextureObject(h->src_tex);
+	if (h->src_arr) cudaFreeArray(h->src_arr);
 	delete h;
 }
 
@@ -202,6 +219,41 @@ static int launch_warp(float *out, const float *src, int sx, int sy, int sz, int
 	return MILB_OK;
 }
 
+// the mean-removed source -> cudaArray + texture object {linear filter, clamp, un-normalised coordinates}
+static int reg_bind_source_texture(milb_reg *h, cudaStream_t st)
+{
+	if (!h->src_arr) {
+		cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+		MILB_CUDA_TRY(cudaMalloc3DArray(&h->src_arr, &desc, make_cudaExtent(h->sx, h->sy, h->sz)));
+		cudaResourceDesc rd;
+		memset(&rd, 0, sizeof rd);
+		rd.resType = cudaResourceTypeArray;
+		rd.res.array.array = h->src_arr;
+		cudaTextureDesc td;
+		memset(&td, 0, sizeof td);
+		td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+		td.filterMode = cudaFilterModeLinear;
+		td.readMode = cudaReadModeElementType;
+		td.normalizedCoords = 0;
+		MILB_CUDA_TRY(cudaCreateTextureObject(&h->src_tex, &rd, &td, nullptr));
+	}
+	cudaMemcpy3DParms cp = {0};
+	cp.srcPtr = make_cudaPitchedPtr((void *)h->src_dm, h->sx * sizeof(float), h->sx, h->sy);
+	cp.dstArray = h->src_arr;
+	cp.extent = make_cudaExtent(h->sx, h->sy, h->sz);
+	cp.kind = cudaMemcpyDeviceToDevice;
+	MILB_CUDA_TRY(cudaMemcpy3DAsync(&cp, st));
+	return MILB_OK;
+}
+
+int milb_reg_set_fetch(milb_reg_t *h, int hardware)
+{
+	if (!h) return MILB_ERR_ARG;
+	if ((hardware != 0) != h->hw_fetch) h->prepared = false; // prepare() builds the texture
+	h->hw_fetch = hardware != 0;
+	return MILB_OK;
+}
+
 int milb_reg_prepare(milb_reg_t *h, const float *pre_tmx, float *sd_t, void *stream)
 {
 	if (!h || !h->have_images) return MILB_ERR_ARG;
@@ -222,6 +274,7 @@ int milb_reg_prepare(milb_reg_t *h, const float *pre_tmx, float *sd_t, void *str
 	double sq[2] = {0, 0};
 	MILB_CUDA_TRY(cudaMemcpyAsync(sq, h->d_red, 2 * sizeof(double), cudaMemcpyDeviceToHost, st));
 	MILB_CUDA_TRY(cudaStreamSynchronize(st));
+	if (h->hw_fetch) MILB_TRY(reg_bind_source_texture(h, st)); // cudacopydevicetoarray + BindTexture, src/api_subfunc.cu:2869-2873
 	h->sd_t = (float)sqrt(sq[1]); // valueStatic, src/api_subfunc.cu:2863
 	if (sd_t) *sd_t = h->sd_t;
 	if ((float)sqrt(sq[0]) == 0 || h->sd_t == 0) return MILB_ERR_EMPTY; // :2852-2855, :2864-2867
@@ -232,7 +285,8 @@ int milb_reg_prepare(milb_reg_t *h, const float *pre_tmx, float *sd_t, void *str
 template <int K>
 static void launch_zncc(milb_reg *h, const AffBatch &b, cudaStream_t st)
 {
-	k_zncc<K><<<h->grid, 256, 0, st>>>(h->tgt_dm, h->src_dm, h->sx, h->sy, h->sz, b, h->d_partial);
+	if (h->hw_fetch) k_zncc<K, true><<<h->grid, 256, 0, st>>>(h->tgt_dm, h->src_dm, h->src_tex, h->sx, h->sy, h->sz, b, h->d_partial);
+	else k_zncc<K, false><<<h->grid, 256, 0, st>>>(h->tgt_dm, h->src_dm, 0, h->sx, h->sy, h->sz, b, h->d_partial);
 	k_zncc_final<<<1, 256, 0, st>>>(h->d_partial, h->grid, K, h->d_out);
 	milb_count_launches(2);
 }

@@ -128,12 +128,16 @@ class Decon:
 class Reg:
     """Mean-removed target/source pair for ZNCC cost evaluations (milb_reg_t)."""
 
-    def __init__(self, shape):
+    def __init__(self, shape, fetch=None):
+        """fetch: None = library default (hardware texture unit), "hw" or "sw" (software restatement, bit-identical
+        to the CPU oracle)."""
         self.lib = _lib.load()
         self.shape = tuple(int(s) for s in shape)
         self._h = C.c_void_p()
         _check(self.lib.milb_reg_create(C.byref(self._h), _size(self.shape)), "milb_reg_create")
         self.sd_t = None
+        if fetch is not None:
+            _check(self.lib.milb_reg_set_fetch(self._h, 1 if fetch == "hw" else 0), "milb_reg_set_fetch")
 
     def close(self):
         if self._h:

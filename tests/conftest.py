@@ -11,6 +11,7 @@ if ROOT not in sys.path:
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run with -m gpu on the B200 box)")
+    config.addinivalue_line("markers", "hw_fetch: run with the product's default ZNCC source fetch (hardware texture unit)")
 
 
 def _have_gpu():
@@ -37,4 +38,20 @@ def _oracle_built():
     need = [os.path.join(ROOT, "oracle", "liboracle_reg.so")]
     if not all(os.path.exists(p) for p in need) or os.path.isdir("/root/reference"):
         subprocess.run(["make", "-C", os.path.join(ROOT, "oracle")], check=False, capture_output=True)
+    yield
+
+
+# The registration cost kernel samples the source with the hardware texture unit by default (the reference's own
+# mechanism: each sample is the float the reference's tex3D returns).  The CPU oracle restates that fetch in software;
+# its bit-identical CUDA twin is selected with MILB_ZNCC_FETCH=sw.  Tests that compare Powell trajectories / sums
+# with the ORACLE bit for bit run the twin; tests marked hw_fetch and tests/test_gpu_reference_pinned.py (product vs
+# the reference itself) run the default.
+_ORACLE_TWIN_MODULES = ("test_gpu_reg", "test_gpu_prealign", "test_gpu_apps", "test_golden_vectors")
+
+
+@pytest.fixture(autouse=True)
+def _zncc_fetch_mode(request, monkeypatch):
+    mod = request.module.__name__.split(".")[-1]
+    if mod in _ORACLE_TWIN_MODULES and "hw_fetch" not in request.keywords:
+        monkeypatch.setenv("MILB_ZNCC_FETCH", "sw")
     yield

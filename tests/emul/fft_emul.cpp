@@ -6,20 +6,16 @@
 
 extern "C" {
 
-// schedule of the fused plane stage: out[ticket] = {valid, phase, plane, tile, dep kind, dep plane}
-int emul_plane_tickets(int planes, int group, int tpp, int ring, int *out, int cap)
+// scheduling rules of the fused plane stage: out[b] = {phase, rank, nrole} per CTA
+void emul_plane_roles(int grid, int nA, int nB, int *out)
 {
-	const int total = plane_total_tickets(planes, group, tpp);
-	if (total > cap) return -total;
-	for (int t = 0; t < total; t++) {
-		PlaneWork w;
-		const bool ok = plane_ticket(t, planes, group, tpp, w);
-		int dp = -1;
-		const int k = ok ? plane_dependency(w, ring, &dp) : 0;
-		int *o = out + 6 * t;
-		o[0] = ok; o[1] = w.phase; o[2] = w.plane; o[3] = w.tile; o[4] = k; o[5] = dp;
-	}
-	return total;
+	for (int b = 0; b < grid; b++) plane_role(b, grid, nA, nB, out + 3 * b, out + 3 * b + 1, out + 3 * b + 2);
+}
+// dependency of a tile of `phase` on `plane`: returns the kind (0 none, 1 phase A, 2 phase B), *dep_plane the plane
+int emul_plane_dependency(int phase, int plane, int ring, int *dep_plane)
+{
+	PlaneWork w = {phase, plane, 0};
+	return plane_dependency(w, ring, dep_plane);
 }
 
 int emul_plan(int n, int *radix, int *pos)

@@ -101,21 +101,36 @@ def _pair(shape=(40, 56, 72), seed=3):
 
 
 def test_affine_warp_three_way():
-    """atrans3dgpu: the reference samples with the hardware texture unit, oracle and product with the
-    software restatement (<= 2 ulp of the filtered value apart)."""
-    from microimagelib_b200 import libapi
+    """atrans3dgpu: the reference samples with the hardware texture unit.  (1) The hardware fetch at the PRODUCT's
+    coordinates reproduces the reference's output bit for bit (the coordinate expression is pinned to the reference
+    build's SASS).  (2) The product's warp is the software restatement of the filter, bit-identical to the oracle.
+    (3) Software restatement vs hardware: a few ulp on almost every sample; on a few 1e-4 of the samples the 8-bit
+    weights differ by one step (bounded at 1e-3 of the largest value)."""
+    import ctypes as C
+    from microimagelib_b200 import _lib, libapi
     from oracle import reg_oracle as ro
+    lib = _lib.load()
+    F = C.POINTER(C.c_float)
+    lib.milb_debug_tex3d_warp.argtypes = [F, F, C.POINTER(C.c_uint), F]
     tgt, src, m = _pair()
     big = synth.affine_matrix(rot_z_deg=35.0, scale=(0.7, 1.3, 1.0), shift=(4, -3, 2))
-    for mat, oshape in ((m, None), (IDENT, None), (big, (30, 70, 50))):
+    for mat, oshape in ((m, None), (IDENT, None), (big, None), (big, (30, 70, 50))):
         ref, st = ref_gpu.api().atrans3dgpu(src, mat, out_shape=oshape)
         got, st2 = libapi.atrans3dgpu(src, mat, out_shape=oshape)
         orc = ro.affine_warp(src, mat, out_shape=oshape)
         assert st == 0 and st2 == 0
         assert np.array_equal(got, orc)
+        if oshape is None:
+            hw = np.zeros_like(src)
+            size = (C.c_uint * 3)(src.shape[2], src.shape[1], src.shape[0])
+            mm = np.ascontiguousarray(mat, np.float32)
+            assert lib.milb_debug_tex3d_warp(hw.ctypes.data_as(F), src.ctypes.data_as(F), size, mm.ctypes.data_as(F)) == 0
+            assert np.array_equal(hw, ref)
         scale = float(np.abs(src).max())
-        assert float(np.abs(ref - orc).max()) <= 4e-6 * scale       # a few ulp of the largest filtered value
-        assert np.array_equal(ref == 0, orc == 0) or float(np.mean((ref == 0) != (orc == 0))) < 1e-4   # same validity mask
+        d = np.abs(ref - orc)
+        assert np.array_equal(ref == 0, orc == 0)                      # same validity mask
+        assert float(d.max()) <= 1e-3 * scale
+        assert float(np.mean(d > 4e-6 * scale)) <= 1e-3
 
 
 def test_affine_warp_16bit_nearest_three_way():
@@ -131,8 +146,12 @@ def test_affine_warp_16bit_nearest_three_way():
 
 @pytest.mark.parametrize("method", [1, 2, 3, 4, 5, 6, 7])
 def test_reg3d_three_way(method):
-    """Whole reg3d (ZNCC cost + Powell): initial / final ZNCC within 1e-5 and the matrix within 1e-3
-    voxel-equivalent displacement of the reference's."""
+    """Whole reg3d (ZNCC cost + Powell) for every affMethod.
+    product (default: hardware fetch) vs reference: the SAME trajectory -- identical evaluation count, initial / final
+    ZNCC within 1e-5, matrix within 1e-3 voxel-equivalent displacement (measured: bit-identical).
+    oracle (software restatement of the fetch) vs reference: every single cost evaluation agrees to ~1e-7, so the
+    initial ZNCC is within 1e-5; Powell then amplifies one-ulp cost differences into different line-search brackets, so
+    the end points are only equally good optima: final ZNCC within 2e-3, matrices within one voxel."""
     from microimagelib_b200 import libapi
     from oracle import reg_oracle as ro
     tgt, src, m_true = _pair()
@@ -140,13 +159,13 @@ def test_reg3d_three_way(method):
     _, tmx_g, st_g, rec_g = libapi.reg3d(tgt, src, regChoice=2, regMethod=method, FTOL=1e-4, itLimit=3000)
     orc = ro.reg3d_affine(tgt, src, method, ftol=1e-4, it_limit=3000)
     assert st_r == 0 and st_g == 0
-    # the cost at the starting point: one corrfunc evaluation (src/api_subfunc.cu:954-988) each
-    assert abs(float(orc["records"][1]) - float(rec_r[1])) <= 1e-5
     assert abs(float(rec_g[1]) - float(rec_r[1])) <= 1e-5
-    assert abs(float(orc["records"][3]) - float(rec_r[3])) <= 1e-4
-    assert abs(float(rec_g[3]) - float(rec_r[3])) <= 1e-4
-    assert corner_disp(orc["tmx"], tmx_r, tgt.shape) <= 1e-3 or abs(float(orc["records"][3]) - float(rec_r[3])) <= 1e-5
-    assert corner_disp(tmx_g, tmx_r, tgt.shape) <= 1e-3 or abs(float(rec_g[3]) - float(rec_r[3])) <= 1e-5
+    assert abs(float(rec_g[3]) - float(rec_r[3])) <= 1e-5
+    assert int(rec_g[5]) == int(rec_r[5])
+    assert corner_disp(tmx_g, tmx_r, tgt.shape) <= 1e-3
+    assert abs(float(orc["records"][1]) - float(rec_r[1])) <= 1e-5
+    assert abs(float(orc["records"][3]) - float(rec_r[3])) <= 2e-3
+    assert corner_disp(orc["tmx"], tmx_r, tgt.shape) <= 1.0
 
 
 def test_zncc_at_given_matrices_three_way():

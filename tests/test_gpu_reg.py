@@ -146,6 +146,50 @@ def test_registration_matches_oracle(method):
         assert float(rec[3]) > 0.9
 
 
+@pytest.mark.hw_fetch
+def test_hardware_fetch_cost_within_tolerance_of_the_oracle():
+    """Default product path: the source is sampled by the texture unit.  Sums within 1e-6 relative of the
+    software restatement (<= 2 ulp per sample), costs within the north-star 1e-5."""
+    from microimagelib_b200 import device
+    from oracle import reg_oracle as ro
+    tgt, src, m = _pair()
+    src_dm, _ = ro.demean(src)
+    tgt_dm, sd_ref = ro.demean(tgt)
+    rng = np.random.default_rng(2)
+    mats = np.concatenate([_matrices(rng, 6), IDENT[None], m[None]])
+    out = {}
+    for mode in ("hw", "sw"):
+        r = device.Reg(tgt.shape, fetch=mode)
+        r.set_images(tgt, src)
+        r.prepare()
+        out[mode] = (r.cost_sums(mats), r.cost(mats))
+        single = np.array([r.cost(mats[k:k + 1])[0] for k in range(len(mats))], np.float32)
+        assert np.array_equal(single, out[mode][1])      # K-batched == single launches in either mode
+        r.close()
+    (ss_h, st_h), c_h = out["hw"]
+    (ss_s, st_s), c_s = out["sw"]
+    for k in range(len(mats)):
+        ss_ref, st_ref = ro.zncc_sums(tgt_dm, src_dm, mats[k])
+        assert abs(ss_s[k] - ss_ref) <= 1e-11 * abs(ss_ref)
+        assert abs(ss_h[k] - ss_ref) <= 1e-6 * abs(ss_ref)
+        assert abs(st_h[k] - st_ref) <= 1e-6 * max(abs(st_ref), abs(ss_ref) ** 0.5 * float(sd_ref))
+        assert abs(float(c_h[k]) - ro.cost_from_sums(ss_ref, st_ref, sd_ref)) <= 1e-5
+
+
+@pytest.mark.hw_fetch
+@pytest.mark.parametrize("method", [6, 7])
+def test_registration_hardware_fetch_vs_oracle(method):
+    from microimagelib_b200 import libapi
+    from oracle import reg_oracle as ro
+    tgt, src, m_true = _pair()
+    reg, tmx, st, rec = libapi.reg3d(tgt, src, regChoice=2, regMethod=method, FTOL=1e-4, itLimit=3000)
+    ref = ro.reg3d_affine(tgt, src, method, ftol=1e-4, it_limit=3000)
+    assert st == 0
+    assert abs(float(rec[1]) - float(ref["records"][1])) <= 1e-5
+    assert float(rec[3]) > 0.9 and abs(float(rec[3]) - float(ref["records"][3])) <= 2e-3
+    assert corner_disp(tmx, synth.invert_affine(m_true), tgt.shape) < 1.0
+
+
 def test_registration_with_input_matrix_and_choice0():
     from microimagelib_b200 import libapi
     from oracle import reg_oracle as ro

@@ -1,7 +1,8 @@
-"""Host check of the fused plane stage's work list (csrc/plane_sched.h, compiled with g++ into the
-emulation library): every (phase, plane, tile) appears exactly once, every ticket's producers come
-earlier in the list (so the static round-robin deal cannot deadlock), and a ring slot is only
-rewritten after its previous plane has been consumed."""
+"""Host replay of the fused plane stage's pipeline (csrc/plane_sched.h, compiled with g++ into the
+emulation library): the CTA roles cover every (phase, plane, tile) exactly once, and a discrete
+replay of the kernel's rules -- a CTA takes its role's tiles in order, a tile starts only when its
+dependency counter is complete, completion is signalled one tile late -- always runs to the end
+(no deadlock) and never lets two planes share a ring slot."""
 import ctypes as C
 import os
 import subprocess
@@ -22,42 +23,74 @@ def lib():
     return C.CDLL(SO)
 
 
-@pytest.mark.parametrize("planes,group,tpp,ring", [(129, 4, 32, 16), (257, 4, 32, 16), (65, 16, 8, 64), (33, 64, 2, 128), (513, 1, 128, 2),
-                                                    (129, 5, 32, 10), (3, 4, 32, 16), (1, 1, 1, 2)])
-def test_schedule_is_complete_and_ordered(lib, planes, group, tpp, ring):
-    cap = (planes // group + 4) * 3 * group * tpp
-    out = np.zeros((cap, 6), np.int32)
-    total = lib.emul_plane_tickets(planes, group, tpp, ring, out.ctypes.data_as(C.POINTER(C.c_int)), cap)
-    assert 0 < total <= cap
-    out = out[:total]
-    seen = {}
-    last_of = {}           # (phase, plane) -> ticket of its last tile
-    for t, (ok, ph, pl, ti, kind, dp) in enumerate(out.tolist()):
-        if not ok:
-            continue
-        assert 0 <= ph < 3 and 0 <= pl < planes and 0 <= ti < tpp
-        assert (ph, pl, ti) not in seen
-        seen[(ph, pl, ti)] = t
-        last_of[(ph, pl)] = t
-    assert len(seen) == 3 * planes * tpp
-    for (ph, pl, ti), t in seen.items():
-        ok, _, _, _, kind, dp = out[t].tolist()
-        if ph == 0:
-            assert (kind, dp) == ((2, pl - ring) if pl >= ring else (0, pl - ring))
-        else:
-            assert (kind, dp) == (ph, pl)
-        if kind:
-            prod = (kind - 1, dp)                    # phase A (0) or phase B (1) of plane dp
-            assert last_of[prod] < t, "a ticket must come after every ticket it waits for"
-    # ring: between A(p) and the end of B(p) no other plane may be written into slot p mod ring
-    for p in range(planes):
-        a0 = min(seen[(0, p, i)] for i in range(tpp))
-        b1 = last_of[(1, p)]
-        for q in range(p % ring, planes, ring):
-            if q == p:
+CASES = [  # planes, tiles per plane, ring, grid, nA, nB
+    (129, 32, 16, 148, 42, 68), (257, 32, 16, 148, 42, 68), (65, 8, 4, 148, 40, 70), (33, 4, 2, 296, 90, 130),
+    (513, 128, 8, 148, 42, 68), (5, 32, 16, 148, 50, 50), (1, 2, 2, 3, 1, 1), (129, 32, 2, 7, 2, 3),
+]
+
+
+@pytest.mark.parametrize("planes,tpp,ring,grid,nA,nB", CASES)
+def test_roles_cover_everything_and_the_pipeline_drains(lib, planes, tpp, ring, grid, nA, nB):
+    roles = np.zeros((grid, 3), np.int32)
+    lib.emul_plane_roles(grid, nA, nB, roles.ctypes.data_as(C.POINTER(C.c_int)))
+    ntiles = planes * tpp
+    seen = set()
+    queues = []                      # per CTA: (phase, [tile indices j])
+    for b in range(grid):
+        ph, rank, nrole = roles[b].tolist()
+        assert 0 <= ph < 3 and 0 <= rank < nrole
+        js = list(range(rank, ntiles, nrole))
+        for j in js:
+            assert (ph, j) not in seen
+            seen.add((ph, j))
+        queues.append((ph, js))
+    assert len(seen) == 3 * ntiles
+
+    def dep(ph, plane):
+        dp = C.c_int(0)
+        k = lib.emul_plane_dependency(ph, plane, ring, C.byref(dp))
+        return k, dp.value
+
+    done = {0: [0] * planes, 1: [0] * planes}       # signalled tiles per plane of phase A / B
+    pos = [0] * grid                                 # next tile of each CTA
+    pending = [None] * grid                          # (phase, plane) finished but not yet signalled
+    slot_owner = {}                                  # ring slot -> plane currently written / not yet consumed
+    remaining = 3 * ntiles
+    rounds = 0
+    while remaining:
+        progressed = False
+        for b in range(grid):
+            ph, js = queues[b]
+            if pos[b] >= len(js):
+                if pending[b]:
+                    done[pending[b][0]][pending[b][1]] += 1
+                    pending[b] = None
+                    progressed = True
                 continue
-            qa = [seen[(0, q, i)] for i in range(tpp)]
-            assert max(qa) < a0 or min(qa) > a0, "two planes interleave in one ring slot"
-            if q > p:
-                # q's phase A waits for B(q - ring) ... B(p) transitively: its dependency chain reaches p
-                assert (q - p) % ring == 0
+            plane = js[pos[b]] // tpp
+            kind, dp = dep(ph, plane)
+            ok = kind == 0 or done[kind - 1][dp] == tpp
+            if not ok:
+                if pending[b]:                       # a waiting CTA sends its pending signal first
+                    done[pending[b][0]][pending[b][1]] += 1
+                    pending[b] = None
+                    progressed = True
+                continue
+            if ph == 0:                              # phase A writes ring slot plane % ring
+                s = plane % ring
+                if s in slot_owner and slot_owner[s] != plane:
+                    assert done[1][slot_owner[s]] == tpp, "ring slot rewritten before it was consumed"
+                slot_owner[s] = plane
+            if pending[b]:                           # the previous tile is signalled during this one
+                done[pending[b][0]][pending[b][1]] += 1
+            pending[b] = (ph, plane) if ph < 2 else None
+            pos[b] += 1
+            remaining -= 1
+            progressed = True
+        rounds += 1
+        assert progressed, "pipeline deadlocked"
+        assert rounds < 20 * (ntiles + grid)
+    for b in range(grid):
+        if pending[b]:
+            done[pending[b][0]][pending[b][1]] += 1
+    assert all(v == tpp for v in done[0]) and all(v == tpp for v in done[1])
