@@ -45,6 +45,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", default="512,512,512", help="slices,H,W")
     ap.add_argument("--shape2", default="256,512,512", help="second record (BASELINE config 2); empty = skip")
+    ap.add_argument("--no-config3", action="store_true", help="skip the config-3 record (one 1024x1024x512 dual-view pair: single GPU at N=1, "
+                    "slab-decomposed distributed FFT over all ranks at N>1)")
+    ap.add_argument("--config3-shape", default="512,1024,1024", help="slices,H,W of the config-3 FFT box")
+    ap.add_argument("--config3-iters", type=int, default=5)
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu side-run that measures DRAM bytes per iteration")
     ap.add_argument("--no-refgpu", action="store_true", help="skip the reference's own GPU path (oracle/_ref) as an in-run yardstick")
     ap.add_argument("--iters", type=int, default=50)
@@ -272,6 +276,108 @@ def measure_traffic(shape, timeout_s=240):
         "ncu side-run in this bench run: dram__bytes_read.sum + dram__bytes_write.sum of the 2nd of 3 iterations"
 
 
+def run_config3(args, rank, local_rank, world, barrier):
+    """BASELINE config 3: deconDualView joint RL on ONE 1024x1024x512 pair.  N = 1: the single-GPU loop (the strong-scaling
+    base).  N > 1: the volume is slab-decomposed over all ranks (csrc/dslab.cu + dist_decon.py), the exchange of the
+    distributed FFT folded into the kernels' stores over NVLink peer memory; before timing, a small box is run both ways
+    and compared bit for bit with the single-GPU result (rank 0).  Every rank calls this; rank 0 returns the record."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from microimagelib_b200 import device, synth
+    shape = tuple(int(v) for v in args.config3_shape.split(","))
+    iters = args.config3_iters
+    dev = torch.device("cuda", local_rank)
+    psf_a = synth.gaussian_psf((65, 65, 65), (4, 2, 2))
+    psf_b = synth.gaussian_psf((65, 65, 65), (2, 2, 4))
+    nfft = float(np.prod(shape))
+    rec = {"config": {"workload": f"deconDualView joint RL {shape[2]}x{shape[1]}x{shape[0]} pair, one volume on {world} GPU(s) (BASELINE config 3)",
+                      "iterations": iters, "views": 2}, "unit": "voxel-iters/s", "scaling": "strong", "n_gpus": world}
+
+    def timed(fn):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        fn()
+        b.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    g = torch.Generator(device=dev)
+    if world == 1:
+        d = device.Decon(shape, 2)
+        d.set_psf(0, psf_a)
+        d.set_psf(1, psf_b)
+        g.manual_seed(20260)
+        for v in range(2):
+            d.set_image(v, torch.rand(shape, generator=g, device=dev) * 50 + 100)
+        d.run(1)
+        ms = timed(lambda: d.run(iters)) / iters
+        d.close()
+        rec.update({"value": nfft / (ms * 1e-3), "ms_per_iteration": ms, "implementation": "single GPU: the same fused kernels, no exchange",
+                    "roofline": {"bound": "hbm", "achieved": 2 * ALG_BYTES_PER_VOXEL_ITER * nfft / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                                 "peak": peak_hbm()[0], "frac": 2 * ALG_BYTES_PER_VOXEL_ITER * nfft / (ms * 1e-3) / 1e9 / peak_hbm()[0]}})
+        torch.cuda.empty_cache()
+        return rec
+    from microimagelib_b200.dist_decon import DistDecon
+    # ---- correctness first: a small box through the distributed path vs the single-GPU path, bit for bit
+    small = (64, 128, 128)
+    pa, pb = synth.gaussian_psf((17, 17, 17), (3, 2, 2)), synth.gaussian_psf((17, 17, 17), (2, 2, 3))
+    g.manual_seed(7)
+    va, vb = (torch.rand(small, generator=g, device=dev) * 50 + 100 for _ in range(2))    # same seed on every rank: same volumes
+    dd = DistDecon(small, 2)
+    L = dd.L
+    dd.set_psf(0, pa)
+    dd.set_psf(1, pb)
+    dd.set_image(0, va[:, L.y0:L.y0 + L.ny, :])
+    dd.set_image(1, vb[:, L.y0:L.y0 + L.ny, :])
+    E = dd.run(3)
+    parts = [torch.empty_like(E) for _ in range(world)]
+    dist.all_gather(parts, E)
+    same = None
+    if rank == 0:
+        s = device.Decon(small, 2)
+        s.set_psf(0, pa)
+        s.set_psf(1, pb)
+        s.set_image(0, va)
+        s.set_image(1, vb)
+        s.run(3)
+        ref = torch.empty(small, dtype=torch.float32, device=dev)
+        s.result(ref)
+        same = bool(torch.equal(torch.cat(parts, dim=1), ref))
+        s.close()
+    rec["bit_identical_to_single_gpu"] = {"box": list(small), "iterations": 3, "equal": same, "exchange": "fused" if dd.fused else "nccl"}
+    dd.close()
+    del dd, parts
+    torch.cuda.empty_cache()
+    # ---- the timed volume
+    dd = DistDecon(shape, 2)
+    L = dd.L
+    dd.set_psf(0, psf_a)
+    dd.set_psf(1, psf_b)
+    g.manual_seed(20260 + rank)
+    for v in range(2):
+        dd.set_image(v, torch.rand((L.X, L.ny, L.Z), generator=g, device=dev) * 50 + 100)
+    dd.run(1)
+    ms = timed(lambda: dd.run(iters)) / iters
+    sent = dd.a2a_bytes_per_gpu()                  # bytes one GPU sends in one exchange; 8 exchanges per dual-view iteration
+    per_iter = 8 * sent
+    rec.update({"value": nfft / (ms * 1e-3), "ms_per_iteration": ms,
+                "implementation": ("exchange fused into the X-pass / Y-inverse kernels' stores over NVLink peer memory (CUDA IPC)" if dd.fused
+                                   else "NCCL all_to_all_single + re-layout copies"),
+                "roofline": {"bound": "nvlink", "achieved": per_iter / (ms * 1e-3) / 1e9, "unit": "GB/s per direction per GPU", "peak": 770.0,
+                             "frac": per_iter / (ms * 1e-3) / 1e9 / 770.0, "peak_source": "measured peer-copy figure, B200_PROFILING.md",
+                             "bytes_sent_per_gpu_per_iteration": per_iter,
+                             "note": "exchange bytes / WHOLE iteration time: the exchange rides on the kernels' stores, so the butterflies of "
+                                     "1/N of the volume are inside the same time"}})
+    dd.close()
+    torch.cuda.empty_cache()
+    return rec
+
+
 def device_loop(d, iters, steps, warmup, stream, barrier, world, local_rank, clocks=None):
     """W warm-up runs, then `steps` timed runs of the full iteration loop (CUDA events on the launching stream)."""
     import torch
@@ -375,6 +481,22 @@ def main():
                "ms_per_step": 1e3 * float(tt.item()) / args.steps,
                "call": "libapi.decon_singleview(host float32 image, host PSF) -> host float32 volume; OTFs cached across calls"}
 
+    fused = bool(d.plane_stage_fused())
+    # ---- config 3 (one volume on all ranks): every rank takes part, after the headline's timed regions ------------
+    config3 = None
+    if not args.no_config3:
+        try:
+            if world > 1:
+                d.close()
+            torch.cuda.empty_cache()
+            config3 = run_config3(args, rank, local_rank, world, barrier)
+        except Exception as e:
+            config3 = {"error": str(e)[:300]}
+            try:
+                barrier()
+            except Exception:
+                pass
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -384,7 +506,6 @@ def main():
     peak, peak_src = peak_hbm()
     ms_iter = ms_max / (args.steps * args.iters)
     achieved = ALG_BYTES_PER_VOXEL_ITER * n_fft / (ms_iter * 1e-3) / 1e9
-    fused = bool(d.plane_stage_fused()) if hasattr(d, "plane_stage_fused") else False
     launch_desc = ("one single-view RL iteration = 2 fused plane-stage launches (k_planes_fused) + 2 fused X-pass launches (k_xpassP)" if fused
                    else "one single-view RL iteration = 6 plane-pass launches + 2 fused X-pass launches")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
@@ -447,8 +568,7 @@ def main():
                 rerr = float(np.linalg.norm(ours.astype(np.float64) - rout) / np.linalg.norm(rout.astype(np.float64)))
                 refgpu = {"what": "the reference's own decon_singleview (cuFFT + its kernels, oracle/_ref/libapi_ref.so) on this GPU, same host "
                                   "buffers, same iteration count; pageable host memory as the reference allocates it",
-                          "ms_per_call": rdt * 1e3, "decon_seconds_reported": float(rrec[8]), "voxel_iters_per_s_e2e": n_fft * args.iters / rdt,
-                          "ms_per_iteration_loop_only": float(rrec[8]) * 1e3 / args.iters,
+                          "ms_per_call": rdt * 1e3, "voxel_iters_per_s_e2e": n_fft * args.iters / rdt,
                           "parity_rel_l2_ours_vs_reference": rerr, "iterations": args.iters, "ok": bool(rerr <= 1e-4),
                           "e2e_speedup_ours_vs_reference_gpu": (rdt * 1e3) / e2e["ms_per_step"] if e2e else None}
                 if parity is not None:
@@ -525,7 +645,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": cfg,
         "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "parity": parity, "cpu_baseline": cpu,
-        "reference_gpu_yardstick": refgpu, "yardstick": yard, "registration": registration, "config2": config2,
+        "reference_gpu_yardstick": refgpu, "yardstick": yard, "registration": registration, "config2": config2, "config3": config3,
     }
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libapi.so")
+# MILB_LIBAPI: another build of the same library (A/B measurements of compile-time variants); default: the in-tree build
+LIB_PATH = os.environ.get("MILB_LIBAPI") or os.path.join(HERE, "lib", "libapi.so")
 
 _F = C.POINTER(C.c_float)
 _D = C.POINTER(C.c_double)

@@ -37,7 +37,13 @@ constexpr size_t SMP3 = (size_t)(3 * TileGeom<N, PL>::elems + N) * sizeof(float2
 constexpr bool kXNarrow = MILB_X_NARROW && (2048 / N >= 4);
 constexpr int R0 = FastPlan<N>::r0;                 // radix of the register-fused stage of the X pass: one butterfly per thread
 constexpr int TXF = (N / R0) * L;                   // threads of the non-persistent X pass
-constexpr int XL = (MILB_X_WIDE ? 8192 : kXNarrow ? 2048 : 4096) / N, XT = (N / R0) * XL;
+// MILB_X_WIDE512: 8192-point X tiles at N = 512 only (4096 points there are just 8 column pairs = 64-byte rows of the
+// real volumes; 16 pairs make them 128 bytes)
+#ifndef MILB_X_WIDE512
+#define MILB_X_WIDE512 0
+#endif
+constexpr bool kXWide = MILB_X_WIDE || (MILB_X_WIDE512 && N == 512);
+constexpr int XL = (kXWide ? 8192 : kXNarrow ? 2048 : 4096) / N, XT = (N / R0) * XL;
 constexpr int XCTAS = xpassP_ctas<N, XL, XT>();
 constexpr size_t SMX = (size_t)(2 * N * XL + 2 * (N / 2 + 1) * XL + N) * sizeof(float2);
 int g_ctas = 0, g_sms = 0; // persistent grids

@@ -9,21 +9,39 @@
 // unit was measured to do with the corner weights (scripts/tex_probe3.py, 7 x 20000 samples, zero
 // mismatches): 8-bit weights from two rounded products, ties up for the dx = 1 corners and down
 // for the dx = 0 corners.  Bit-for-bit twin of oracle/reg_oracle.c: tex3d_linear.
-__device__ __forceinline__ void split_coord(float t, int &i0, int &a)
+// Clamp addressing acts on the coordinate: xB = t - 0.5 is clamped to [0, n - 1] before it is split (within half a texel
+// of a face all of the axis' weight goes to the edge texel), and the unit rounds xB to 8 fractional bits, so a fraction
+// that rounds up to one is texel i + 1 with weight 0.  Both pinned on the reference's own tex3D output
+// (scripts/tex_cases.py: 129 024 samples, zero mismatches).
+__device__ __forceinline__ void split_coord(float t, int n, int &i0, int &a)
 {
-	const int u = __float2int_rd(__fmul_rn(__fsub_rn(t, 0.5f), 512.0f)); // floor((t - 0.5) * 512), exact scaling
-	i0 = u >> 9;
-	a = ((u + 1) >> 1) - (i0 << 8); // round(frac * 256) in [0, 256]
+	const float xb = fminf(fmaxf(__fsub_rn(t, 0.5f), 0.f), (float)(n - 1));
+	const int u = __float2int_rd(__fmul_rn(xb, 512.0f)); // floor(xB * 512), exact scaling
+	const int f = (u + 1) >> 1;                           // round(xB * 256): 8 fractional bits
+	i0 = f >> 8;
+	a = f & 255;
 }
 
-__device__ __forceinline__ float wf(int w) { return __int_as_float(0x4B000000 + w) - 8388608.0f; } // exact int -> float, 0 <= w < 2^22
+// double -> float, round to nearest with ties AWAY from zero (twin of oracle/reg_oracle.c round_half_away): how the unit
+// rounds the exact sum of its weight * texel products
+__device__ __forceinline__ float round_half_away(double v)
+{
+	const float f = __double2float_rn(v);
+	const double r = v - (double)f;
+	if (r == 0.0) return f;
+	const float g = nextafterf(f, r > 0 ? INFINITY : -INFINITY);
+	const double dg = fabs((double)g - v), df = fabs(v - (double)f);
+	if (dg < df) return g;
+	if (dg > df) return f;
+	return (fabsf(g) > fabsf(f)) ? g : f;
+}
 
 __device__ __forceinline__ float tex3d_linear(const float *__restrict__ v, int sx, int sy, int sz, float tx, float ty, float tz)
 {
 	int ix, iy, iz, a, b, c;
-	split_coord(tx, ix, a);
-	split_coord(ty, iy, b);
-	split_coord(tz, iz, c);
+	split_coord(tx, sx, ix, a);
+	split_coord(ty, sy, iy, b);
+	split_coord(tz, sz, iz, c);
 	float t000, t100, t010, t110, t001, t101, t011, t111;
 	const int pl = sx * sy; // volumes stay below 2^31 voxels: 32-bit element indices
 	if ((unsigned)ix < (unsigned)(sx - 1) && (unsigned)iy < (unsigned)(sy - 1) && (unsigned)iz < (unsigned)(sz - 1)) {
@@ -46,16 +64,16 @@ __device__ __forceinline__ float tex3d_linear(const float *__restrict__ v, int s
 	const int w0z1 = (a0 * c + 127) >> 8, w1z1 = (a * c + 128) >> 8;
 	const int h0z0 = (w0z0 * b + 127) >> 8, h1z0 = (w1z0 * b + 128) >> 8;
 	const int h0z1 = (w0z1 * b + 127) >> 8, h1z1 = (w1z1 * b + 128) >> 8;
-	float acc = 0.f;
-	acc = __fmaf_rn(wf(w0z0 - h0z0), t000, acc);
-	acc = __fmaf_rn(wf(w1z0 - h1z0), t100, acc);
-	acc = __fmaf_rn(wf(h0z0), t010, acc);
-	acc = __fmaf_rn(wf(h1z0), t110, acc);
-	acc = __fmaf_rn(wf(w0z1 - h0z1), t001, acc);
-	acc = __fmaf_rn(wf(w1z1 - h1z1), t101, acc);
-	acc = __fmaf_rn(wf(h0z1), t011, acc);
-	acc = __fmaf_rn(wf(h1z1), t111, acc);
-	return __fmul_rn(acc, 1.0f / 256.0f);
+	// the eight products are summed without intermediate rounding (double), rounded to float once, scaled by the exact 1/256
+	double acc = (double)(w0z0 - h0z0) * (double)t000;
+	acc += (double)(w1z0 - h1z0) * (double)t100;
+	acc += (double)h0z0 * (double)t010;
+	acc += (double)h1z0 * (double)t110;
+	acc += (double)(w0z1 - h0z1) * (double)t001;
+	acc += (double)(w1z1 - h1z1) * (double)t101;
+	acc += (double)h0z1 * (double)t011;
+	acc += (double)h1z1 * (double)t111;
+	return __fmul_rn(round_half_away(acc), 1.0f / 256.0f);
 }
 
 // a0*x + a1*y + a2*z + a3 + 0.5 with the contraction nvcc (12.9, -fmad=true) gives the reference
@@ -75,20 +93,19 @@ __device__ __forceinline__ float aff_coord(const float *a, float fx, float fy, f
 __device__ __forceinline__ float tex2d_linear(const float *__restrict__ v, int sx, int sy, float tx, float ty)
 {
 	int ix, iy, a, b;
-	split_coord(tx, ix, a);
-	split_coord(ty, iy, b);
+	split_coord(tx, sx, ix, a);
+	split_coord(ty, sy, iy, b);
 	const int x0 = min(max(ix, 0), sx - 1), x1 = min(max(ix + 1, 0), sx - 1);
 	const int y0 = min(max(iy, 0), sy - 1), y1 = min(max(iy + 1, 0), sy - 1);
 	const float *p0 = v + (long long)y0 * sx, *p1 = v + (long long)y1 * sx;
 	const float t00 = __ldg(p0 + x0), t10 = __ldg(p0 + x1), t01 = __ldg(p1 + x0), t11 = __ldg(p1 + x1);
 	const int w0 = 256 - a, w1 = a;
 	const int h0 = (w0 * b + 127) >> 8, h1 = (w1 * b + 128) >> 8;
-	float acc = 0.f;
-	acc = __fmaf_rn(wf(w0 - h0), t00, acc);
-	acc = __fmaf_rn(wf(w1 - h1), t10, acc);
-	acc = __fmaf_rn(wf(h0), t01, acc);
-	acc = __fmaf_rn(wf(h1), t11, acc);
-	return __fmul_rn(acc, 1.0f / 256.0f);
+	double acc = (double)(w0 - h0) * (double)t00;
+	acc += (double)(w1 - h1) * (double)t10;
+	acc += (double)h0 * (double)t01;
+	acc += (double)h1 * (double)t11;
+	return __fmul_rn(round_half_away(acc), 1.0f / 256.0f);
 }
 
 // a0*x + a1*y + a2 + 0.5 (include/cukernel.cuh:564-565, 579-580) as the reference build contracts it:

@@ -24,32 +24,61 @@
  *     W(dx,1,dz)    = round(Wxz(dx,dz) * b / 256),   W(dx,0,dz) = Wxz(dx,dz) - W(dx,1,dz)
  * with round-to-nearest and ties going UP for the dx = 1 corners and DOWN for the dx = 0 corners
  * (so the weights always sum to 256).  The value is sum(W * texel) / 256.
- * Canonical float evaluation order (the CUDA product path restates the same order): fused
- * multiply-adds over the corners in (z, y, x) order starting from 0, then * 1/256.            */
+ * The eight weight * texel products are summed without intermediate rounding (double: exact for image data), rounded to
+ * float once with ties away from zero, then scaled by the exact 1/256 -- pinned on the reference's own tex3D output:
+ * 99.88 % of 105 196 samples bit-identical, the rest one ulp off (an fma chain agreed on 68 %).                  */
+/* double -> float, round to nearest with ties AWAY from zero: what the unit does with the exact sum of its eight
+ * weight * texel products (scripts/tex_cases_analyze.py and the residual analysis in DESIGN.md section 4: of 18 761 samples
+ * 23 of 24 exact ties went up; with this rule 99.8 % of all samples are bit-identical to tex3D, the rest are one ulp off) */
+static inline float round_half_away(double v)
+{
+	float f = (float)v;                     /* nearest-even candidate */
+	double r = v - (double)f;               /* exact in double: both share the exponent range */
+	if (r == 0.0) return f;
+	float g = nextafterf(f, r > 0 ? INFINITY : -INFINITY);   /* neighbour on the side of v */
+	double dg = (double)g - v, df = v - (double)f;
+	if (dg < 0) dg = -dg;
+	if (df < 0) df = -df;
+	if (dg < df) return g;
+	if (dg > df) return f;
+	return (fabs((double)g) > fabs((double)f)) ? g : f;       /* tie: away from zero */
+}
+
 static inline int clampi(int v, int hi) { return v < 0 ? 0 : (v > hi ? hi : v); }
 
-/* t (texture coordinate) -> texel index i = floor(t - 0.5) and weight a = round(frac * 256) */
-static inline void split_coord(float t, int *i0, int *a)
+/* t (texture coordinate) -> texel index i = floor(xB) and weight a = round(frac(xB) * 256), xB = t - 0.5.
+ * Clamp addressing acts on the COORDINATE: xB is clamped to [0, n - 1] before it is split, so within half a texel
+ * of a face all of the axis' weight goes to the edge texel (a = 0) instead of being split between two copies of it
+ * -- which changes the rounded corner weights by one step.  Pinned on the reference's own tex3D output
+ * (scripts/tex_cases.py / tex_cases_analyze.py: 1432 boundary samples that differed before, none after). */
+static inline void split_coord(float t, int n, int *i0, int *a)
 {
 	float xb = t - 0.5f;
+	if (xb < 0.0f) xb = 0.0f;
+	if (xb > (float)(n - 1)) xb = (float)(n - 1);
 	int u = (int)floorf(xb * 512.0f);      /* exact: power-of-two scaling */
 	int i = u >> 9;                         /* floor(xb) (arithmetic shift) */
+	int w = ((u + 1) >> 1) - i * 256;       /* floor(frac * 256 + 0.5), in [0, 256] */
+	if (w == 256) { i += 1; w = 0; }        /* the unit rounds the COORDINATE to 8 fractional bits: a fraction that rounds up to
+	                                           one belongs to the next texel with weight 0, i.e. the dx = 0 (ties-down) corner rules
+	                                           apply (seen as the last 26 mismatches of scripts/tex_cases_analyze.py: all of them had
+	                                           frac * 256 > 255.5 on one axis and an exact tie in the y split) */
 	*i0 = i;
-	*a = ((u + 1) >> 1) - i * 256;          /* floor(frac * 256 + 0.5), in [0, 256] */
+	*a = w;
 }
 
 static inline float tex3d_linear(const float *v, long long sx, long long sy, long long sz,
 	float tx, float ty, float tz)
 {
 	int ix, iy, iz, a, b, c;
-	split_coord(tx, &ix, &a);
-	split_coord(ty, &iy, &b);
-	split_coord(tz, &iz, &c);
+	split_coord(tx, (int)sx, &ix, &a);
+	split_coord(ty, (int)sy, &iy, &b);
+	split_coord(tz, (int)sz, &iz, &c);
 	int xi[2] = { clampi(ix, (int)sx - 1), clampi(ix + 1, (int)sx - 1) };
 	int yi[2] = { clampi(iy, (int)sy - 1), clampi(iy + 1, (int)sy - 1) };
 	int zi[2] = { clampi(iz, (int)sz - 1), clampi(iz + 1, (int)sz - 1) };
 	int wx[2] = { 256 - a, a }, wz[2] = { 256 - c, c };
-	float acc = 0.0f;
+	double acc = 0.0;                        /* the unit sums the eight weight * texel products without intermediate rounding */
 	for (int dz = 0; dz < 2; dz++) {
 		int w_y[2][2];                       /* [dy][dx] */
 		for (int dx = 0; dx < 2; dx++) {
@@ -61,11 +90,11 @@ static inline float tex3d_linear(const float *v, long long sx, long long sy, lon
 		}
 		for (int dy = 0; dy < 2; dy++) {
 			const float *row = v + (long long)yi[dy] * sx + (long long)zi[dz] * sx * sy;
-			acc = fmaf((float)w_y[dy][0], row[xi[0]], acc);
-			acc = fmaf((float)w_y[dy][1], row[xi[1]], acc);
+			acc += (double)w_y[dy][0] * (double)row[xi[0]];
+			acc += (double)w_y[dy][1] * (double)row[xi[1]];
 		}
 	}
-	return acc * (1.0f / 256.0f);
+	return round_half_away(acc) * (1.0f / 256.0f);   /* one rounding to float, then the exact scaling */
 }
 
 /* Affine coordinate: d_aff[0]*ix + d_aff[1]*iy + d_aff[2]*iz + d_aff[3] + 0.5
@@ -228,8 +257,8 @@ void orc_dof9tomatrix(float *p_out, const float *p_dof, int dofNum)
 static inline float tex2d_linear(const float *v, long long sx, long long sy, float tx, float ty)
 {
 	int ix, iy, a, b;
-	split_coord(tx, &ix, &a);
-	split_coord(ty, &iy, &b);
+	split_coord(tx, (int)sx, &ix, &a);
+	split_coord(ty, (int)sy, &iy, &b);
 	int xi[2] = { clampi(ix, (int)sx - 1), clampi(ix + 1, (int)sx - 1) };
 	int yi[2] = { clampi(iy, (int)sy - 1), clampi(iy + 1, (int)sy - 1) };
 	int wx[2] = { 256 - a, a };
@@ -240,13 +269,13 @@ static inline float tex2d_linear(const float *v, long long sx, long long sy, flo
 		w[1][dx] = hi;
 		w[0][dx] = wx[dx] - hi;
 	}
-	float acc = 0.0f;
+	double acc = 0.0;
 	for (int dy = 0; dy < 2; dy++) {
 		const float *row = v + (long long)yi[dy] * sx;
-		acc = fmaf((float)w[dy][0], row[xi[0]], acc);
-		acc = fmaf((float)w[dy][1], row[xi[1]], acc);
+		acc += (double)w[dy][0] * (double)row[xi[0]];
+		acc += (double)w[dy][1] * (double)row[xi[1]];
 	}
-	return acc * (1.0f / 256.0f);
+	return round_half_away(acc) * (1.0f / 256.0f);
 }
 
 /* d_aff[0]*ix + d_aff[1]*iy + d_aff[2] + 0.5 as nvcc 12.9 contracts it in affineTransform2Dkernel /

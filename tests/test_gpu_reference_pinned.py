@@ -104,8 +104,8 @@ def test_affine_warp_three_way():
     """atrans3dgpu: the reference samples with the hardware texture unit.  (1) The hardware fetch at the PRODUCT's
     coordinates reproduces the reference's output bit for bit (the coordinate expression is pinned to the reference
     build's SASS).  (2) The product's warp is the software restatement of the filter, bit-identical to the oracle.
-    (3) Software restatement vs hardware: a few ulp on almost every sample; on a few 1e-4 of the samples the 8-bit
-    weights differ by one step (bounded at 1e-3 of the largest value)."""
+    (3) Software restatement vs hardware: the integer weights agree on every sample (also in the clamp region next to
+    the faces); only the float accumulation order differs, by a few ulp."""
     import ctypes as C
     from microimagelib_b200 import _lib, libapi
     from oracle import reg_oracle as ro
@@ -129,8 +129,7 @@ def test_affine_warp_three_way():
         scale = float(np.abs(src).max())
         d = np.abs(ref - orc)
         assert np.array_equal(ref == 0, orc == 0)                      # same validity mask
-        assert float(d.max()) <= 1e-3 * scale
-        assert float(np.mean(d > 4e-6 * scale)) <= 1e-3
+        assert float(d.max()) <= 4e-6 * scale                          # a few ulp of the largest filtered value
 
 
 def test_affine_warp_16bit_nearest_three_way():
