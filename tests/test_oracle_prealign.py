@@ -20,7 +20,14 @@ def test_tex2d_texel_centres_and_midpoints():
     c = np.stack([xs.ravel() + 0.5, ys.ravel() + 0.5], 1).astype(np.float32)
     assert np.array_equal(ro.tex2d_samples(img, c), img.ravel())          # texel centres are exact
     mid = ro.tex2d_samples(img, [[3.0, 4.5]])[0]                           # halfway between x = 2 and x = 3 on row 4
-    assert mid == np.float32((128 * img[4, 2] + 128 * img[4, 3]) / 256)
+    # integer weights 128 + 128, exact sum, ONE rounding to float with ties away from zero (what the texture unit does), exact 1/256
+    s = 128 * np.float64(img[4, 2]) + 128 * np.float64(img[4, 3])              # exact in double
+    f = np.float32(s)
+    if np.float64(f) != s:
+        g = np.nextafter(f, np.float32(np.inf) if s > np.float64(f) else np.float32(-np.inf))
+        if abs(np.float64(g) - s) == abs(np.float64(f) - s) and abs(g) > abs(f):
+            f = g                                                               # an exact tie: away from zero
+    assert mid == np.float32(f / np.float32(256))
     edge = ro.tex2d_samples(img, [[0.1, 0.2], [10.9, 8.9]])               # clamp addressing outside the first / last centre
     assert edge[0] == img[0, 0] and edge[1] == img[8, 10]
 
