@@ -37,6 +37,39 @@ template <class T> struct PinnedAllocator {
 	template <class U> bool operator!=(const PinnedAllocator<U> &) const { return false; }
 };
 using HostVec = std::vector<float, PinnedAllocator<float>>;
+using HostVec16 = std::vector<unsigned short, PinnedAllocator<unsigned short>>;
+
+// A volume in device memory (milb_dev_alloc): the libapi.h entry points of this backend accept device pointers for their
+// image arguments, so a time point can stay on the GPU between the calls of the fusion pipeline.
+template <class T> struct DevBuf {
+	T *p = nullptr;
+	size_t n = 0;
+	DevBuf() = default;
+	DevBuf(const DevBuf &) = delete;
+	DevBuf &operator=(const DevBuf &) = delete;
+	~DevBuf() { release(); }
+	void release()
+	{
+		if (p) milb_dev_free(p);
+		p = nullptr;
+		n = 0;
+	}
+	T *resize(size_t count)
+	{
+		if (count > n) {
+			release();
+			void *q = nullptr;
+			if (milb_dev_alloc(&q, (unsigned long long)(count * sizeof(T))) != 0) {
+				fprintf(stderr, "*** device memory allocation of %zu bytes failed\n", count * sizeof(T));
+				exit(1);
+			}
+			p = (T *)q;
+			n = count;
+		}
+		return p;
+	}
+	void swap(DevBuf &o) { std::swap(p, o.p); std::swap(n, o.n); }
+};
 
 struct Args {
 	int argc;

@@ -55,6 +55,30 @@ inline void fusion_preprocess(const FusionGeometry &g, HostVec &raw1, HostVec &r
 	}
 }
 
+// The same steps on volumes that live in device memory (this backend's libapi.h functions take device pointers): raw1 / raw2
+// are the float stacks as read, img1 / img2 scratch of the output sizes, rot scratch of view B's input size.  Returns where
+// the pre-processed views are (a view that needs no resampling is used in place, not copied).
+inline void fusion_preprocess_dev(const FusionGeometry &g, float *raw1, float *raw2, float *img1, float *img2, float *rot, int deviceNum,
+	float **out1, float **out2)
+{
+	if (!memcmp(g.in1, g.s1, sizeof g.s1)) *out1 = raw1;
+	else {
+		(void)imresize3d(img1, raw1, g.s1[0], g.s1[1], g.s1[2], g.in1[0], g.in1[1], g.in1[2], deviceNum);
+		*out1 = img1;
+	}
+	unsigned int rs[3] = {g.in2[0], g.in2[1], g.in2[2]};
+	float *src = raw2;
+	if (g.opChoice) {
+		(void)imoperation3D(rot, rs, raw2, (unsigned int *)g.in2, g.opChoice, deviceNum);
+		src = rot;
+	}
+	if (!memcmp(rs, g.s2, sizeof rs)) *out2 = src;
+	else {
+		(void)imresize3d(img2, src, g.s2[0], g.s2[1], g.s2[2], rs[0], rs[1], rs[2], deviceNum);
+		*out2 = img2;
+	}
+}
+
 struct RegSettings {
 	int regChoice = 2, affMethod = 6, itLimit = 3000, deviceNum = 0, gpuMemMode = -1;
 	float ftol = 0.0001f;
@@ -65,9 +89,10 @@ struct RegSettings {
 // (src/spim_fusion_batch.cpp:559,722-746): other pre-alignment scheme, then the initial matrix.
 // `recheck` re-evaluates checkmatrix after the second attempt (the reference does so only in its
 // regMode-2 branch, :764).
-inline void register_with_ladder(HostVec &reg, float *tmx, HostVec &img1, HostVec &img2, const FusionGeometry &g,
+inline void register_with_ladder(float *reg_p, float *tmx, float *img1_p, float *img2_p, const FusionGeometry &g,
 	const RegSettings &rs, bool flagTmx, const float *tmxInitial, bool recheck, float *rec)
 {
+	struct P { float *p; float *data() const { return p; } } reg{reg_p}, img1{img1_p}, img2{img2_p}; // host or device pointers
 	const float costBar = 0.1f;
 	(void)reg3d(reg.data(), tmx, img1.data(), img2.data(), (unsigned int *)g.s1, (unsigned int *)g.s2, rs.regChoice, rs.affMethod, flagTmx, rs.ftol,
 		rs.itLimit, rs.deviceNum, rs.gpuMemMode, rs.verbose, rec);

@@ -21,25 +21,42 @@ inline bool pipeline_enabled()
 class ReadAhead {
 public:
 	~ReadAhead() { join(); }
-	void start(const std::string &p1, const std::string &p2, size_t n1, size_t n2)
+	// raw16: keep 16-bit stacks as they are on disk (the device-resident pipeline converts them to float on the GPU)
+	void start(const std::string &p1, const std::string &p2, size_t n1, size_t n2, bool raw16 = false)
 	{
 		join();
 		if (!pipeline_enabled() || !fexists((char *)p1.c_str()) || !fexists((char *)p2.c_str())) return;
 		k1_ = p1; k2_ = p2;
-		b1_.resize(n1); b2_.resize(n2);
+		raw16_ = raw16;
+		if (raw16) { u1_.resize(n1); u2_.resize(n2); }
+		else { b1_.resize(n1); b2_.resize(n2); }
 		busy_ = true;
 		th_ = std::thread([this] { // the two views are decoded side by side
-			std::thread second([this] { readtifstack(b2_.data(), (char *)k2_.c_str(), s2_); });
-			readtifstack(b1_.data(), (char *)k1_.c_str(), s1_);
+			std::thread second([this] {
+				if (raw16_) readtifstack_16to16(u2_.data(), (char *)k2_.c_str(), s2_);
+				else readtifstack(b2_.data(), (char *)k2_.c_str(), s2_);
+			});
+			if (raw16_) readtifstack_16to16(u1_.data(), (char *)k1_.c_str(), s1_);
+			else readtifstack(b1_.data(), (char *)k1_.c_str(), s1_);
 			second.join();
 		});
+	}
+	// 16-bit variant of take()
+	bool take16(const std::string &p1, const std::string &p2, HostVec16 &raw1, HostVec16 &raw2, unsigned int *s1, unsigned int *s2)
+	{
+		if (!busy_) return false;
+		join();
+		if (p1 != k1_ || p2 != k2_ || !raw16_) return false;
+		raw1.swap(u1_); raw2.swap(u2_);
+		memcpy(s1, s1_, sizeof s1_); memcpy(s2, s2_, sizeof s2_);
+		return true;
 	}
 	// true: raw1/raw2 and the size triples now hold the prefetched stacks
 	bool take(const std::string &p1, const std::string &p2, HostVec &raw1, HostVec &raw2, unsigned int *s1, unsigned int *s2)
 	{
 		if (!busy_) return false;
 		join();
-		if (p1 != k1_ || p2 != k2_) return false;
+		if (p1 != k1_ || p2 != k2_ || raw16_) return false;
 		raw1.swap(b1_); raw2.swap(b2_);
 		memcpy(s1, s1_, sizeof s1_); memcpy(s2, s2_, sizeof s2_);
 		return true;
@@ -55,6 +72,8 @@ private:
 	bool busy_ = false;
 	std::string k1_, k2_;
 	HostVec b1_, b2_;
+	HostVec16 u1_, u2_;
+	bool raw16_ = false;
 	unsigned int s1_[3] = {0, 0, 0}, s2_[3] = {0, 0, 0};
 };
 
@@ -104,6 +123,28 @@ public:
 		q_.push_back(std::move(j));
 		cv_work_.notify_one();
 	}
+	// a 16-bit stack that is already converted (on the GPU): the buffer is taken over like in write_swap and written as is
+	void write_u16_swap(const std::string &path, HostVec16 &buf, const unsigned int *size)
+	{
+		if (th_.empty()) {
+			unsigned int s[3] = {size[0], size[1], size[2]};
+			writetifstack_16to16((char *)path.c_str(), buf.data(), s);
+			return;
+		}
+		Job j;
+		j.path = path; j.bits = 16;
+		memcpy(j.size, size, sizeof j.size);
+		{
+			std::unique_lock<std::mutex> lk(mu_);
+			if (!spare16_.empty()) { j.big16.swap(spare16_.back()); spare16_.pop_back(); }
+		}
+		if (j.big16.size() != buf.size()) j.big16.resize(buf.size());
+		j.big16.swap(buf);
+		std::unique_lock<std::mutex> lk(mu_);
+		cv_space_.wait(lk, [this] { return q_.size() < 6; });
+		q_.push_back(std::move(j));
+		cv_work_.notify_one();
+	}
 	// waits until everything submitted so far is on disk (end of the batch)
 	void drain()
 	{
@@ -122,6 +163,7 @@ private:
 		std::string path;
 		std::vector<float> data; // copied payload (small outputs) ...
 		HostVec big;             // ... or a buffer taken over from the caller (write_swap)
+		HostVec16 big16;         // ... or an already converted 16-bit stack (write_u16_swap)
 		unsigned int size[3];
 		unsigned short bits;
 	};
@@ -137,6 +179,12 @@ private:
 				q_.pop_front();
 				cv_space_.notify_one();
 			}
+			if (!j.big16.empty()) {
+				writetifstack_16to16((char *)j.path.c_str(), j.big16.data(), j.size);
+				std::unique_lock<std::mutex> lk(mu_);
+				spare16_.push_back(std::move(j.big16));
+				continue;
+			}
 			writetifstack((char *)j.path.c_str(), j.big.empty() ? j.data.data() : j.big.data(), j.size, j.bits);
 			if (!j.big.empty()) {
 				std::unique_lock<std::mutex> lk(mu_);
@@ -149,5 +197,6 @@ private:
 	std::condition_variable cv_work_, cv_space_;
 	std::deque<Job> q_;
 	std::vector<HostVec> spare_; // written-out big buffers waiting to be reused
+	std::vector<HostVec16> spare16_;
 	bool stop_ = false;
 };

@@ -33,7 +33,7 @@ static void usage(const char *app, bool full)
 		"32: <int>     Bit depth of the outputs (16 or 32)", "33: <int>     Query GPUs first (0/1)", "34: <int>     GPU device",
 		"35/36: <file> (optional) backward projectors 1 / 2"};
 	for (const char *l : lines) printf("\t%s\n", l);
-	printf("\nEnvironment: MILB_SHARD=<rank>/<world> processes every world-th time point on GPU <arg 34> + rank * MILB_SHARD_DEVICE_STRIDE (default 1);\n             MILB_PIPELINE=0 disables the read-ahead / write-behind I/O threads.\n");
+	printf("\nEnvironment: MILB_SHARD=<rank>/<world> processes every world-th time point on GPU <arg 34> + rank * MILB_SHARD_DEVICE_STRIDE (default 1);\n             MILB_PIPELINE=0 disables the read-ahead / write-behind I/O threads;\n             MILB_DEVICE_RESIDENT=0 moves every stage's volumes through host memory like the reference.\n");
 }
 
 static std::string join(const std::string &a, const std::string &b) { return a + b; }
@@ -142,7 +142,20 @@ int main(int argc, char **argv)
 
 	const size_t sx = g.s1[0], sy = g.s1[1], sz = g.s1[2];
 	const long long projectNum = 36;
-	HostVec raw1(voxels(g.in1)), raw2(voxels(g.in2)), img1, img2, reg(voxels(g.s1)), decon(voxels(g.s1));
+	// Device-resident time point (default; MILB_DEVICE_RESIDENT=0 restores the host round trips between the stages): the two
+	// stacks go to the GPU once (as 16-bit when the files are 16-bit), every stage -- 16-bit -> float, rotation, resampling,
+	// registration or matrix application, joint deconvolution, projections, float -> 16-bit -- runs on device buffers that
+	// live for the whole batch, and only the result stack and the projections come back.  The stages are the same libapi.h
+	// calls as in the host path (this backend's entry points accept device pointers); outputs are byte-identical.
+	const bool resident = [] { const char *e = getenv("MILB_DEVICE_RESIDENT"); return !(e && e[0] == '0'); }();
+	const bool raw16 = resident && bitsImg == 16;
+	if (resident && milb_set_device(rs.deviceNum) != 0) { fprintf(stderr, "*** cannot select GPU %d\n", rs.deviceNum); return 1; }
+	DevBuf<float> dRaw1, dRaw2, dImg1, dImg2, dRot, dReg, dDecon;
+	DevBuf<unsigned short> dU1, dU2;
+	HostVec16 raw1u, raw2u, out16;
+	HostVec hostTmp;
+	HostVec raw1, raw2, img1, img2, reg, decon;
+	if (!resident) { raw1.resize(voxels(g.in1)); raw2.resize(voxels(g.in2)); reg.resize(voxels(g.s1)); decon.resize(voxels(g.s1)); }
 	std::vector<float> mp2d, mp3d;
 	if (saveXProj || saveYProj || saveZProj) mp2d.resize(sx * sy + sy * sz + sz * sx);
 	float regRec[11] = {0}, deconRec[10] = {0};
@@ -162,7 +175,13 @@ int main(int argc, char **argv)
 		const std::string f1 = dir1 + base1 + n + ".tif", f2 = dir2 + base2 + n + ".tif";
 		printf("... Preprocessing ...\n");
 		unsigned int tmp2[3];
-		if (!ahead.take(f1, f2, raw1, raw2, tmp, tmp2)) {
+		if (raw16) {
+			if (!ahead.take16(f1, f2, raw1u, raw2u, tmp, tmp2)) {
+				raw1u.resize(voxels(g.in1)); raw2u.resize(voxels(g.in2));
+				readtifstack_16to16(raw1u.data(), (char *)f1.c_str(), tmp);
+				readtifstack_16to16(raw2u.data(), (char *)f2.c_str(), tmp2);
+			}
+		} else if (!ahead.take(f1, f2, raw1, raw2, tmp, tmp2)) {
 			raw1.resize(voxels(g.in1)); raw2.resize(voxels(g.in2));
 			readtifstack(raw1.data(), (char *)f1.c_str(), tmp);
 			readtifstack(raw2.data(), (char *)f2.c_str(), tmp2);
@@ -174,24 +193,48 @@ int main(int argc, char **argv)
 			const int nextNum = (regMode == 1) ? numStart - 1 + numStep * (1 + shardRank) : num + step;
 			if (nextNum <= numEnd && nextNum != num) {
 				const std::string nn = std::to_string(nextNum);
-				ahead.start(dir1 + base1 + nn + ".tif", dir2 + base2 + nn + ".tif", voxels(g.in1), voxels(g.in2));
+				ahead.start(dir1 + base1 + nn + ".tif", dir2 + base2 + nn + ".tif", voxels(g.in1), voxels(g.in2), raw16);
 			}
 		}
 		const double tRead = tPoint.s();
-		fusion_preprocess(g, raw1, raw2, img1, img2, rs.deviceNum);
+		float *pImg1 = nullptr, *pImg2 = nullptr, *pReg = nullptr, *pDecon = nullptr; // host or device volumes of this time point
+		if (resident) {
+			const size_t n1 = voxels(g.in1), n2 = voxels(g.in2);
+			dRaw1.resize(n1); dRaw2.resize(n2);
+			if (raw16) { // 16-bit over PCIe, (float)uint16 on the GPU (readtifstack's conversion, src/apifunc.cpp:160-170)
+				dU1.resize(n1 > voxels(g.s1) ? n1 : voxels(g.s1)); dU2.resize(n2);
+				if (milb_memcpy(dU1.p, raw1u.data(), n1 * 2) || milb_memcpy(dU2.p, raw2u.data(), n2 * 2) ||
+					milb_convert_u16_to_f32(dRaw1.p, dU1.p, (long long)n1, nullptr) || milb_convert_u16_to_f32(dRaw2.p, dU2.p, (long long)n2, nullptr)) {
+					fprintf(stderr, "*** upload of the input stacks failed\n");
+					return 1;
+				}
+			} else if (milb_memcpy(dRaw1.p, raw1.data(), n1 * 4) || milb_memcpy(dRaw2.p, raw2.data(), n2 * 4)) {
+				fprintf(stderr, "*** upload of the input stacks failed\n");
+				return 1;
+			}
+			dImg1.resize(voxels(g.s1)); dImg2.resize(voxels(g.s2));
+			if (g.opChoice) dRot.resize(n2);
+			fusion_preprocess_dev(g, dRaw1.p, dRaw2.p, dImg1.p, dImg2.p, dRot.p, rs.deviceNum, &pImg1, &pImg2);
+			pReg = dReg.resize(voxels(g.s1));
+			pDecon = dDecon.resize(voxels(g.s1));
+		} else {
+			fusion_preprocess(g, raw1, raw2, img1, img2, rs.deviceNum);
+			reg.resize(voxels(g.s1)); // every reg3d path writes the whole volume
+			decon.resize(voxels(g.s1));
+			pImg1 = img1.data(); pImg2 = img2.data(); pReg = reg.data(); pDecon = decon.data();
+		}
 		printf("\tTime cost for  reading: %2.3f s, preprocessing: %2.3f s\n", tRead, tPoint.s() - tRead);
 
 		printf("...Registration...\n");
 		WallTimer tReg;
-		reg.resize(voxels(g.s1)); // every reg3d path writes the whole volume
 		if (flagTmx) memcpy(affInitial, tmx, sizeof tmx);
 		switch (regMode) {
 		case 0:
-			(void)reg3d(reg.data(), tmx, img1.data(), img2.data(), g.s1, g.s2, rs.regChoice, rs.affMethod, flagTmx, rs.ftol, rs.itLimit, rs.deviceNum,
+			(void)reg3d(pReg, tmx, pImg1, pImg2, g.s1, g.s2, rs.regChoice, rs.affMethod, flagTmx, rs.ftol, rs.itLimit, rs.deviceNum,
 				rs.gpuMemMode, rs.verbose, regRec);
 			break;
 		case 1:
-			register_with_ladder(reg, tmx, img1, img2, g, rs, flagTmx, affInitial, false, regRec);
+			register_with_ladder(pReg, tmx, pImg1, pImg2, g, rs, flagTmx, affInitial, false, regRec);
 			// the remaining time points only apply this matrix; the reference restarts its loop with
 			// "imgNum = imgNumStart - 1; continue" (src/spim_fusion_batch.cpp:748-751), i.e. at
 			// imgNumStart - 1 + interval
@@ -201,19 +244,19 @@ int main(int argc, char **argv)
 			continue;
 		case 2:
 			if (num == numStart) {
-				register_with_ladder(reg, tmx, img1, img2, g, rs, flagTmx, affInitial, true, regRec);
+				register_with_ladder(pReg, tmx, pImg1, pImg2, g, rs, flagTmx, affInitial, true, regRec);
 				memcpy(affWeighted, tmx, sizeof tmx);
 			} else {
 				flagTmx = true;
 				rs.regChoice = 2;
 				memcpy(tmx, affWeighted, sizeof tmx);
-				(void)reg3d(reg.data(), tmx, img1.data(), img2.data(), g.s1, g.s2, rs.regChoice, rs.affMethod, flagTmx, rs.ftol, rs.itLimit, rs.deviceNum,
+				(void)reg3d(pReg, tmx, pImg1, pImg2, g.s1, g.s2, rs.regChoice, rs.affMethod, flagTmx, rs.ftol, rs.itLimit, rs.deviceNum,
 					rs.gpuMemMode, rs.verbose, regRec);
 				if (!checkmatrix(tmx, sx, sy, sz) || regRec[3] < 0.1f) {
 					printf("\n\t... Attempt failed: transformation matrix problematic or cost function value %f < threshold %2.2f\n", regRec[3], 0.1f);
 					printf("\n\t... Use previous transformation matrix!!!\n");
 					memcpy(tmx, affPrevious, sizeof tmx);
-					(void)reg3d(reg.data(), tmx, img1.data(), img2.data(), g.s1, g.s2, 0, rs.affMethod, true, rs.ftol, rs.itLimit, rs.deviceNum, rs.gpuMemMode,
+					(void)reg3d(pReg, tmx, pImg1, pImg2, g.s1, g.s2, 0, rs.affMethod, true, rs.ftol, rs.itLimit, rs.deviceNum, rs.gpuMemMode,
 						rs.verbose, regRec);
 				}
 				for (int j = 0; j < 12; j++) affWeighted[j] = (float)(0.8 * affWeighted[j] + 0.2 * tmx[j]); // blend for the next time point
@@ -222,14 +265,22 @@ int main(int argc, char **argv)
 			break;
 		case 3:
 			if (flagTmx) memcpy(tmx, affInitial, sizeof tmx);
-			register_with_ladder(reg, tmx, img1, img2, g, rs, flagTmx, affInitial, false, regRec);
+			register_with_ladder(pReg, tmx, pImg1, pImg2, g, rs, flagTmx, affInitial, false, regRec);
 			break;
 		default:
 			break;
 		}
 		write_tmx((tmxDir + "Matrix_" + n + ".tmx").c_str(), tmx); // the matrix is always saved
-		if (saveReg1) behind.write(regDir1 + base1 + "reg_" + n + ".tif", img1.data(), g.s1, (unsigned short)bitsImg);
-		if (saveReg2) behind.write(regDir2 + base2 + "reg_" + n + ".tif", reg.data(), g.s1, (unsigned short)bitsImg);
+		for (int which = 0; which < 2; which++) { // optional registered inputs (the writer copies what it is given)
+			if (!(which ? saveReg2 : saveReg1)) continue;
+			const float *src = which ? pReg : pImg1;
+			if (resident) {
+				hostTmp.resize(voxels(g.s1));
+				if (milb_memcpy(hostTmp.data(), src, voxels(g.s1) * 4)) { fprintf(stderr, "*** download failed\n"); return 1; }
+				src = hostTmp.data();
+			}
+			behind.write((which ? regDir2 + base2 : regDir1 + base1) + "reg_" + n + ".tif", src, g.s1, (unsigned short)bitsImg);
+		}
 		printf("\tTime cost for  registration: %2.3f s\n", tReg.s());
 		{
 			char buf[256];
@@ -239,8 +290,7 @@ int main(int argc, char **argv)
 
 		printf("... Deconvolution ...\n");
 		WallTimer tDec;
-		decon.resize(voxels(g.s1));
-		(void)decon_dualview(decon.data(), img1.data(), reg.data(), g.s1, psf1.data(), psf2.data(), psfSize, false, iters, rs.deviceNum, rs.gpuMemMode, rs.verbose,
+		(void)decon_dualview(pDecon, pImg1, pReg, g.s1, psf1.data(), psf2.data(), psfSize, false, iters, rs.deviceNum, rs.gpuMemMode, rs.verbose,
 			deconRec, unmatched, bp1.data(), bp2.data());
 		const int modeActual = (int)deconRec[0];
 		printf("\tTime cost for  deconvolution: %2.3f s\n", tDec.s());
@@ -253,7 +303,7 @@ int main(int argc, char **argv)
 
 		if (saveXProj || saveYProj || saveZProj) { // packed [Z-proj | X-proj | Y-proj], src/apifunc.cpp:485-505
 			unsigned int sizeMP[6], s2d[3] = {0, 0, 1};
-			(void)mp2dgpu(mp2d.data(), sizeMP, decon.data(), g.s1, saveZProj, saveXProj, saveYProj);
+			(void)mp2dgpu(mp2d.data(), sizeMP, pDecon, g.s1, saveZProj, saveXProj, saveYProj);
 			if (saveZProj) { s2d[0] = sizeMP[0]; s2d[1] = sizeMP[1]; behind.write(mpXY + "MP_XY_" + n + ".tif", mp2d.data(), s2d, bits); }
 			if (saveXProj) { s2d[0] = sizeMP[2]; s2d[1] = sizeMP[3]; behind.write(mpYZ + "MP_YZ_" + n + ".tif", mp2d.data() + sx * sy, s2d, bits); }
 			if (saveYProj) { s2d[0] = sizeMP[4]; s2d[1] = sizeMP[5]; behind.write(mpZX + "MP_ZX_" + n + ".tif", mp2d.data() + sx * sy + sy * sz, s2d, bits); }
@@ -265,13 +315,28 @@ int main(int argc, char **argv)
 				const double a2 = (axis == 1) ? (double)sy * sy : (double)sx * sx;
 				const long long R = (long long)round(sqrt(a2 + (double)sz * sz));
 				mp3d.assign((size_t)((axis == 1 ? sx : sy) * R * projectNum), 0.f);
-				(void)mip3dgpu(mp3d.data(), s3d, decon.data(), g.s1, axis, projectNum);
+				(void)mip3dgpu(mp3d.data(), s3d, pDecon, g.s1, axis, projectNum);
 				const std::string f = (axis == 1) ? mp3X + "MP_3D_Xaxis_" + n + ".tif" : mp3Y + "MP_3D_Yaxis_" + n + ".tif";
 				behind.write(f, mp3d.data(), s3d, bits);
 			}
 		}
 		// the deconvolved volume goes to the writer last, so that its buffer can be handed over instead of copied
-		behind.write_swap(deconDir + "Decon_" + n + ".tif", decon, g.s1, bits);
+		if (resident && bits == 16) { // (unsigned short)float on the GPU (writetifstack's conversion, src/apifunc.cpp:255), 16-bit over PCIe
+			const size_t nv = voxels(g.s1);
+			dU1.resize(nv);
+			out16.resize(nv);
+			if (milb_convert_f32_to_u16(dU1.p, pDecon, (long long)nv, nullptr) || milb_memcpy(out16.data(), dU1.p, nv * 2)) {
+				fprintf(stderr, "*** download of the result failed\n");
+				return 1;
+			}
+			behind.write_u16_swap(deconDir + "Decon_" + n + ".tif", out16, g.s1);
+		} else {
+			if (resident) {
+				decon.resize(voxels(g.s1));
+				if (milb_memcpy(decon.data(), pDecon, voxels(g.s1) * 4)) { fprintf(stderr, "*** download of the result failed\n"); return 1; }
+			}
+			behind.write_swap(deconDir + "Decon_" + n + ".tif", decon, g.s1, bits);
+		}
 		printf("\tTime cost for  projections and output hand-off: %2.3f s\n", tPoint.s() - tAfterDecon);
 		printf("...Time cost for current image is %2.3f s\n", tPoint.s());
 	}

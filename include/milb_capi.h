@@ -106,6 +106,9 @@ int milb_dslab_psf_box(milb_dslab_t *h, float *out_slab, const float *d_psf, con
 /* mode 0: out = max(a, 0.01); mode 1: out = (a + b) * 0.5  (src/api_subfunc.cu:3380, 3616-3617) */
 int milb_dslab_elementwise(float *out, const float *a, const float *b, long long n, int mode, void *stream);
 
+/* 1 if milb_dslab_set_peers will accept this box on `world` ranks (the fused exchange's constraints depend on the build's
+ * X-pass tile width; callers fall back to the all-to-all path on 0) */
+int milb_dslab_can_fuse(const milb_dslab_t *h, int world);
 /* Exchange folded into the kernels (no all-to-all): with the peers' plane and slab buffers mapped
  * into this process (milb_ipc_*), the X pass stores every spectrum row straight into the plane
  * buffer of the rank that owns it and the last plane pass stores every output row straight into the
@@ -124,6 +127,10 @@ int milb_host_alloc(void **out, unsigned long long bytes);
 int milb_host_free(void *p);
 int milb_dev_alloc(void **out, unsigned long long bytes);
 int milb_dev_free(void *p);
+/* selects the GPU the calling thread's later milb_dev_alloc / milb_memcpy / conversion calls act on */
+int milb_set_device(int device);
+/* synchronous copy between any two of host / device memory (direction inferred) */
+int milb_memcpy(void *dst, const void *src, unsigned long long bytes);
 int milb_ipc_export(void *p, unsigned char *handle64);
 int milb_ipc_open(const unsigned char *handle64, void **out);
 int milb_ipc_close(void *p);
@@ -207,6 +214,12 @@ void milb_dof9tomatrix(float *p_out, const float *p_dof, int dofNum);
 typedef float (*milb_costfn)(const float *x, void *user);
 int milb_powell(float *p, float *xi, int n, float ftol, int *iter, float *fret, milb_costfn func,
 	void *user, const int *totalIt, int itLimit);
+
+/* 16-bit <-> float conversions of the TIFF path on the device (readtifstack's (float)uint16, src/apifunc.cpp:160-170;
+ * writetifstack's (unsigned short)float C truncation without clamp, :255), so that a time point crosses PCIe as 16-bit
+ * stacks.  Device pointers; n elements. */
+int milb_convert_u16_to_f32(float *d_out, const unsigned short *d_in, long long n, void *stream);
+int milb_convert_f32_to_u16(unsigned short *d_out, const float *d_in, long long n, void *stream);
 
 #ifdef __cplusplus
 }

@@ -74,13 +74,18 @@ CAPI_PROTOS = {
     "milb_dslab_planes": (C.c_int, [_VP, _VP, _VP, _VP, C.c_float, _VP]),
     "milb_dslab_psf_box": (C.c_int, [_VP, _VP, _VP, _U, C.c_int, _VP]),
     "milb_dslab_elementwise": (C.c_int, [_VP, _VP, _VP, _LL, C.c_int, _VP]),
+    "milb_dslab_can_fuse": (C.c_int, [_VP, C.c_int]),
     "milb_dslab_set_peers": (C.c_int, [_VP, C.c_int, C.c_int, C.POINTER(_VP), C.POINTER(_VP), _I]),
     "milb_dslab_xpass_peer": (C.c_int, [_VP, C.c_int, _VP, _VP, _VP, _VP]),
     "milb_dslab_planes_peer": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
+    "milb_convert_u16_to_f32": (C.c_int, [_VP, _VP, _LL, _VP]),
+    "milb_convert_f32_to_u16": (C.c_int, [_VP, _VP, _LL, _VP]),
     "milb_host_alloc": (C.c_int, [C.POINTER(_VP), C.c_ulonglong]),
     "milb_host_free": (C.c_int, [_VP]),
     "milb_dev_alloc": (C.c_int, [C.POINTER(_VP), C.c_ulonglong]),
     "milb_dev_free": (C.c_int, [_VP]),
+    "milb_set_device": (C.c_int, [C.c_int]),
+    "milb_memcpy": (C.c_int, [_VP, _VP, C.c_ulonglong]),
     "milb_ipc_export": (C.c_int, [_VP, C.c_char_p]),
     "milb_ipc_open": (C.c_int, [C.c_char_p, C.POINTER(_VP)]),
     "milb_ipc_close": (C.c_int, [_VP]),

@@ -25,6 +25,7 @@ struct PlaneFuse {
 struct FastAxisOps {
 	int n = 0;                 // FFT length
 	int lanes = 0;             // pencils per CTA
+	int xlanes = 0;            // column pairs per tile of the persistent X pass (the widest tile an X-pass launch may use)
 	// one-time opt-in to > 48 KB dynamic shared memory
 	int (*setup)() = nullptr;
 	// mode: 0 fwd-real, 1 ratio, 2 update, 3 update-last (XF_* in fft_fast.cuh); M = columns of float2 pairs

@@ -230,7 +230,7 @@ void fwd_scaled(float2 *spec, const float2 *tw, int cols, int plane0, int nplane
 const FastAxisOps *MILB_CAT(milb_fast_ops_, MILB_FAST_N)()
 {
 	static FastAxisOps ops;
-	ops.n = N; ops.lanes = L; ops.setup = setup; ops.xpass = xpass; ops.passT = passT; ops.pass_inv = pass_inv;
+	ops.n = N; ops.lanes = L; ops.xlanes = XL > L ? XL : L; ops.setup = setup; ops.xpass = xpass; ops.passT = passT; ops.pass_inv = pass_inv;
 	ops.convT = convT; ops.fwd_scaled = fwd_scaled; ops.planes_fused = planes_fused; ops.xpass_peer = xpass_peer; ops.pass_inv_peer = pass_inv_peer; ops.grid_cap = &g_cap;
 	return &ops;
 }

@@ -143,12 +143,23 @@ extern "C" int milb_dslab_elementwise(float *out, const float *a, const float *b
 // into the plane buffer of the rank that owns it, and the last plane pass (Y inverse) stores each
 // output row straight into the slab buffer of the rank that owns it.  The caller provides the
 // peers' buffers (opened with milb_ipc_open) and a cross-rank barrier between the two phases.
+// 1 if the exchange can be folded into the kernels' stores for this box on `world` ranks: at most 8 ranks, power-of-two
+// slabs, and an X-pass tile (xlanes column pairs -- a property of the build) that stays inside one row of Z / 2 pairs
+extern "C" int milb_dslab_can_fuse(const milb_dslab_t *h, int world)
+{
+	if (!h || world < 1 || world > 8) return 0;
+	if (h->ny * world != h->Y || (h->ny & (h->ny - 1))) return 0;
+	const FastAxisOps *ox = milb_fast_ops(h->X);
+	if (!ox || (h->Z / 2) % ox->xlanes) return 0;
+	return 1;
+}
+
 extern "C" int milb_dslab_set_peers(milb_dslab_t *h, int world, int rank, void *const *planes_ptrs, void *const *slab_ptrs,
 	const int *plane_counts)
 {
 	if (!h || world < 1 || world > 8 || rank < 0 || rank >= world || !planes_ptrs || !slab_ptrs || !plane_counts) return MILB_ERR_ARG;
 	if (h->ny * world != h->Y || (h->ny & (h->ny - 1)) || h->y0 != rank * h->ny) return MILB_ERR_ARG;
-	if ((h->Z / 2) % milb_fast_ops(h->X)->lanes) return MILB_ERR_SIZE; // an X-pass tile must stay inside one row
+	if (!milb_dslab_can_fuse(h, world)) return MILB_ERR_SIZE;
 	PeerMap pm;
 	memset(&pm, 0, sizeof pm);
 	pm.world = world; pm.me = rank; pm.ny = h->ny; pm.Y = h->Y; pm.Z = h->Z;
@@ -283,6 +294,18 @@ extern "C" int milb_dev_alloc(void **out, unsigned long long bytes)
 extern "C" int milb_dev_free(void *p)
 {
 	if (p) MILB_CUDA_TRY(cudaFree(p));
+	return MILB_OK;
+}
+extern "C" int milb_set_device(int device)
+{
+	MILB_CUDA_TRY(cudaSetDevice(device));
+	return MILB_OK;
+}
+// copy between any two of host / device memory (direction inferred from the pointers), synchronous
+extern "C" int milb_memcpy(void *dst, const void *src, unsigned long long bytes)
+{
+	if (!dst || !src) return MILB_ERR_ARG;
+	MILB_CUDA_TRY(cudaMemcpy(dst, src, bytes, cudaMemcpyDefault));
 	return MILB_OK;
 }
 extern "C" int milb_ipc_export(void *p, unsigned char *handle64)

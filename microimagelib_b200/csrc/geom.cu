@@ -8,6 +8,7 @@
 #include "common.h"
 #include "geom.h"
 #include "launch_count.h"
+#include "tex_sw.cuh"
 
 static int ggrid(long long n) { long long b = cdiv_ll(n, 256); return (int)(b > 148 * 16 ? 148 * 16 : (b < 1 ? 1 : b)); }
 
@@ -160,6 +161,92 @@ int milb_warp_u16_dev(unsigned short *d_out, const unsigned short *d_src, int sx
 	AffOne a;
 	memcpy(a.m, tmx, sizeof a.m);
 	k_warp_u16_point<<<ggrid((long long)sx * sy * sz), 256, 0, st>>>(d_out, d_src, sx, sy, sz, sx2, sy2, sz2, a);
+	milb_count_launches(1);
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+// ---- rotating maximum-intensity projections, fused (mip3dgpu / mp3dgpu, src/apifunc.cpp:507-644) ---------------------------
+// The reference warps the volume into a rotated box (so0, so1, so2) for each of the projectNum angles, then takes the
+// maximum along z of that box, then copies the projection to the host: 36 x (write + re-read of the rotated volume) and
+// 36 synchronous copies.  Here one launch produces all projections: a thread owns one output pixel (x, y) of one
+// projection and marches z through the rotated box, sampling the source exactly as the warp kernel would
+// (affinetransformkernel: same coordinate expression, same 0 <= t < size mask, same trilinear fetch) and keeping the
+// running maximum, which starts at 0 like the reference's accumulator (include/cukernel.cuh:401).  The rotated volume
+// never exists; the values compared are bit for bit the ones the two-step path would have written and read back.
+struct AffMany {
+	float m[64][12];
+};
+__global__ void __launch_bounds__(256) k_rot_mip(float *__restrict__ out, const float *__restrict__ src, int so0, int so1, int so2, int sx, int sy, int sz,
+	AffMany aff, int first)
+{
+	const int p = blockIdx.y;
+	const float *a = aff.m[p];
+	const long long npix = (long long)so0 * so1;
+	const float fsx = (float)sx, fsy = (float)sy, fsz = (float)sz;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < npix; i += (long long)gridDim.x * blockDim.x) {
+		const int x = (int)(i % so0), y = (int)(i / so0);
+		const float fx = (float)x, fy = (float)y;
+		float best = 0.f;
+		for (int z = 0; z < so2; z++) {
+			const float fz = (float)z;
+			const float tx = aff_coord(a + 0, fx, fy, fz), ty = aff_coord(a + 4, fx, fy, fz), tz = aff_coord(a + 8, fx, fy, fz);
+			if (tx >= 0 && tx < fsx && ty >= 0 && ty < fsy && tz >= 0 && tz < fsz) {
+				const float v = tex3d_linear(src, sx, sy, sz, tx, ty, tz);
+				best = (best > v) ? best : v;
+			}
+		}
+		out[(long long)(first + p) * npix + i] = best;
+	}
+}
+
+// d_out: nproj projections of so0 x so1 pixels; matrices: nproj x 12 (target voxel of the rotated box -> source voxel)
+int milb_rot_mip_dev(float *d_out, const float *d_src, const unsigned int *sizeRot, const unsigned int *sizeSrc, const float *matrices, int nproj,
+	cudaStream_t st)
+{
+	if (!d_out || !d_src || !sizeRot || !sizeSrc || !matrices || nproj < 1) return MILB_ERR_ARG;
+	const long long npix = (long long)sizeRot[0] * sizeRot[1];
+	long long bx = cdiv_ll(npix, 256);
+	if (bx > 148 * 4) bx = 148 * 4;
+	for (int first = 0; first < nproj; first += 64) {
+		const int cnt = nproj - first < 64 ? nproj - first : 64;
+		AffMany am;
+		memcpy(am.m, matrices + 12ll * first, sizeof(float) * 12 * cnt);
+		k_rot_mip<<<dim3((unsigned)bx, cnt), 256, 0, st>>>(d_out, d_src, sizeRot[0], sizeRot[1], sizeRot[2], sizeSrc[0], sizeSrc[1], sizeSrc[2], am,
+			first);
+		milb_count_launches(1);
+	}
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+// ---- 16-bit <-> float on the device (readtifstack / writetifstack conversions, src/apifunc.cpp:160-170, 255) --------------
+__global__ void k_u16_to_f32(float *__restrict__ out, const unsigned short *__restrict__ in, long long n)
+{
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) out[i] = (float)in[i];
+}
+// (unsigned short)f as the reference's host code performs it on x86-64: truncation toward zero through a 32-bit integer, low
+// 16 bits kept, no clamp; values outside the int range (and NaN) give the "integer indefinite" 0x80000000, i.e. 0
+__global__ void k_f32_to_u16(unsigned short *__restrict__ out, const float *__restrict__ in, long long n)
+{
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		const float f = in[i];
+		const int v = (f > -2147483904.0f && f < 2147483648.0f) ? __float2int_rz(f) : (int)0x80000000;
+		out[i] = (unsigned short)((unsigned)v & 0xFFFFu);
+	}
+}
+extern "C" int milb_convert_u16_to_f32(float *d_out, const unsigned short *d_in, long long n, void *stream)
+{
+	if (!d_out || !d_in || n < 0) return MILB_ERR_ARG;
+	k_u16_to_f32<<<ggrid(n), 256, 0, (cudaStream_t)stream>>>(d_out, d_in, n);
+	milb_count_launches(1);
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+extern "C" int milb_convert_f32_to_u16(unsigned short *d_out, const float *d_in, long long n, void *stream)
+{
+	if (!d_out || !d_in || n < 0) return MILB_ERR_ARG;
+	k_f32_to_u16<<<ggrid(n), 256, 0, (cudaStream_t)stream>>>(d_out, d_in, n);
 	milb_count_launches(1);
 	MILB_CUDA_TRY(cudaGetLastError());
 	return MILB_OK;

@@ -44,6 +44,82 @@ void cuda_fatal(cudaError_t e, const char *what)
 	exit(1);
 }
 
+// ---- image arguments: host pointers (the reference's convention) or, as an extension of this backend, device pointers ----
+// Every volume argument of the libapi.h entry points may live in device memory of the selected GPU (allocated with
+// milb_dev_alloc / cudaMalloc): inputs are then used in place and outputs written in place, with no PCIe transfer.  The
+// command-line batch app keeps a whole time point on the device this way (apps/spim_fusion_batch.cpp) while still calling
+// the same imresize3d / imoperation3D / reg3d / decon_dualview / mp2dgpu / mip3dgpu functions a host-buffer caller uses.
+bool on_device(const void *p)
+{
+	if (!p) return false;
+	cudaPointerAttributes a;
+	if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+	return a.type == cudaMemoryTypeDevice;
+}
+
+// Temporary device buffers come from the stream-ordered pool of the current device with its release threshold lifted, so
+// that the per-call malloc / free pairs of this layer (the reference's structure) cost microseconds after the first call.
+void *tmp_alloc(size_t bytes, const char *what = "****Memory allocating fails... GPU out of memory !!!!*****")
+{
+	static std::mutex mu;
+	static bool tuned[64] = {false};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		if (dev >= 0 && dev < 64 && !tuned[dev]) {
+			cudaMemPool_t pool;
+			if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+				unsigned long long keep = ~0ull;
+				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+			}
+			tuned[dev] = true;
+		}
+	}
+	void *p = nullptr;
+	cuda_fatal(cudaMallocAsync(&p, bytes ? bytes : 1, 0), what);
+	return p;
+}
+void tmp_free(void *p)
+{
+	if (p) cudaFreeAsync(p, 0);
+}
+
+// device view of an input volume: the caller's own memory when that is device memory, else an uploaded copy
+template <class T> struct DevIn {
+	const T *d = nullptr;
+	T *owned = nullptr;
+	DevIn(const T *p, size_t n)
+	{
+		if (on_device(p)) d = p;
+		else {
+			owned = (T *)tmp_alloc(n * sizeof(T));
+			cuda_fatal(cudaMemcpyAsync(owned, p, n * sizeof(T), cudaMemcpyHostToDevice, 0), "H2D");
+			d = owned;
+		}
+	}
+	~DevIn() { tmp_free(owned); }
+	DevIn(const DevIn &) = delete;
+};
+// device buffer for an output volume: the caller's own memory when that is device memory, else a buffer that commit() downloads
+template <class T> struct DevOut {
+	T *d = nullptr, *user = nullptr;
+	size_t n = 0;
+	bool direct = false;
+	DevOut(T *p, size_t count) : user(p), n(count)
+	{
+		direct = on_device(p);
+		d = direct ? p : (T *)tmp_alloc(n * sizeof(T));
+	}
+	void commit()
+	{
+		if (!direct) cuda_fatal(cudaMemcpyAsync(user, d, n * sizeof(T), cudaMemcpyDeviceToHost, 0), "D2H");
+		cuda_fatal(cudaStreamSynchronize(0), "synchronize");
+	}
+	~DevOut() { if (!direct) tmp_free(d); }
+	DevOut(const DevOut &) = delete;
+};
+
 float free_mb()
 {
 	size_t fr = 0, tot = 0;
@@ -165,10 +241,11 @@ int decon_common(int nviews, float *h_decon, float *const h_img[2], unsigned int
 	}
 	deconRecords[2] = (hit && same_handle) ? deconRecords[1] : free_mb();
 	printf("...GPU free memory(after mallocing) is %.0f MBites\n", deconRecords[2]);
-	for (int v = 0; v < nviews; v++) fatal_if(milb_decon_set_image(c.h, v, h_img[v], 0, nullptr), "****Image preparation failed !!!!*****");
+	for (int v = 0; v < nviews; v++)
+		fatal_if(milb_decon_set_image(c.h, v, h_img[v], on_device(h_img[v]) ? 1 : 0, nullptr), "****Image preparation failed !!!!*****");
 	const double t2 = now_s();
 	fatal_if(milb_decon_run(c.h, itNumForDecon, flagConstInitial ? 1 : 0, nullptr), "decon iterration error");
-	fatal_if(milb_decon_get_result(c.h, h_decon, 0, nullptr), "decon result transfer");
+	fatal_if(milb_decon_get_result(c.h, h_decon, on_device(h_decon) ? 1 : 0, nullptr), "decon result transfer");
 	const double t3 = now_s();
 	deconRecords[4] = (hit && same_handle) ? deconRecords[1] : free_mb();
 	printf("...GPU free memory (after processing) is %.0f MBites\n", deconRecords[4]);
@@ -294,18 +371,16 @@ int reg3d(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int 
 		return -1;
 	}
 	// modes 1 and 2 run the same device-resident path
-	float *d_t = nullptr, *d_s = nullptr, *d_tmp = nullptr, *d_reg = nullptr;
-	cuda_fatal(cudaMalloc(&d_t, sizeof(float) * n1), "****Memory allocating fails... GPU out of memory !!!!*****");
-	cuda_fatal(cudaMalloc(&d_s, sizeof(float) * n1), "****Memory allocating fails... GPU out of memory !!!!*****");
-	cuda_fatal(cudaMalloc(&d_reg, sizeof(float) * n1), "****Memory allocating fails... GPU out of memory !!!!*****");
+	DevIn<float> in_t(h_img1, (size_t)n1), in_s(h_img2, (size_t)n2);
+	DevOut<float> out_reg(h_reg, (size_t)n1);
+	const float *d_t = in_t.d, *d_s = in_s.d;
+	float *d_reg = out_reg.d, *d_tmp = nullptr;
 	const bool same = imSize1[0] == imSize2[0] && imSize1[1] == imSize2[1] && imSize1[2] == imSize2[2];
-	if (same) cuda_fatal(cudaMemcpy(d_s, h_img2, sizeof(float) * n2, cudaMemcpyHostToDevice), "H2D");
-	else { // centre crop / zero pad the source to the target size, src/api_reg.cpp:401-406
-		cuda_fatal(cudaMalloc(&d_tmp, sizeof(float) * n2), "cudaMalloc");
-		cuda_fatal(cudaMemcpy(d_tmp, h_img2, sizeof(float) * n2, cudaMemcpyHostToDevice), "H2D");
-		fatal_if(milb_alignsize_dev(d_s, d_tmp, imSize1[0], imSize1[1], imSize1[2], imSize2[0], imSize2[1], imSize2[2], nullptr), "alignsize");
+	if (!same) { // centre crop / zero pad the source to the target size, src/api_reg.cpp:401-406
+		d_tmp = (float *)tmp_alloc(sizeof(float) * n1);
+		fatal_if(milb_alignsize_dev(d_tmp, in_s.d, imSize1[0], imSize1[1], imSize1[2], imSize2[0], imSize2[1], imSize2[2], nullptr), "alignsize");
+		d_s = d_tmp;
 	}
-	cuda_fatal(cudaMemcpy(d_t, h_img1, sizeof(float) * n1, cudaMemcpyHostToDevice), "H2D");
 	records[9] = free_mb();
 	if (regChoice == 0) affMethod = 0;
 	if (regChoice == 1 || regChoice == 3) {
@@ -318,9 +393,8 @@ int reg3d(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int 
 		if (regChoice == 1) {
 			const long long neg[3] = {-shiftXYZ[0], -shiftXYZ[1], -shiftXYZ[2]};
 			fatal_if(milb_imshift(d_reg, d_s, imSize1, neg, nullptr), "imshift");
-			cuda_fatal(cudaMemcpy(h_reg, d_reg, sizeof(float) * n1, cudaMemcpyDeviceToHost), "D2H");
-			cudaFree(d_t); cudaFree(d_s); cudaFree(d_reg);
-			if (d_tmp) cudaFree(d_tmp);
+			out_reg.commit();
+			tmp_free(d_tmp);
 			records[10] = free_mb();
 			records[7] = (float)(now_s() - t_start);
 			if (verbose) printf("\t... registration done !!! \n");
@@ -333,9 +407,7 @@ int reg3d(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int 
 		printf("\t... 2D MIP registration ... \n");
 		const float shiftRegion = 0.3f, totalStep = 30.f;
 		const long long n2d = std::max((long long)imSize1[0] * imSize1[1], (long long)imSize1[2] * imSize1[0]);
-		float *d_m1 = nullptr, *d_m2 = nullptr;
-		cuda_fatal(cudaMalloc(&d_m1, sizeof(float) * n2d), "cudaMalloc");
-		cuda_fatal(cudaMalloc(&d_m2, sizeof(float) * n2d), "cudaMalloc");
+		float *d_m1 = (float *)tmp_alloc(sizeof(float) * n2d), *d_m2 = (float *)tmp_alloc(sizeof(float) * n2d);
 		float tmx1[6] = {1, 0, 0, 0, 1, 0}, rec2d[9];
 		fatal_if(milb_mip_dev(d_m1, d_t, imSize1[0], imSize1[1], imSize1[2], 1, nullptr), "mip");
 		fatal_if(milb_mip_dev(d_m2, d_s, imSize1[0], imSize1[1], imSize1[2], 1, nullptr), "mip");
@@ -348,7 +420,8 @@ int reg3d(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int 
 			const unsigned int szx[2] = {imSize1[2], imSize1[0]};
 			rc2 = milb_reg2d_shiftalign(nullptr, tmx2, d_m1, szx, d_m2, szx, 1, 0, shiftRegion, totalStep, 1, rec2d, nullptr);
 		}
-		cudaFree(d_m1); cudaFree(d_m2);
+		cuda_fatal(cudaStreamSynchronize(0), "synchronize");
+		tmp_free(d_m1); tmp_free(d_m2);
 		if (rc2 == MILB_ERR_EMPTY) {
 			fprintf(stderr, "*** SD of image 1 is zero, empty image input **** \n");
 			exit(1);
@@ -368,9 +441,8 @@ int reg3d(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int 
 		exit(1);
 	}
 	fatal_if(rc == MILB_ERR_ARG ? MILB_OK : rc, "registration failed");
-	cuda_fatal(cudaMemcpy(h_reg, d_reg, sizeof(float) * n1, cudaMemcpyDeviceToHost), "D2H");
-	cudaFree(d_t); cudaFree(d_s); cudaFree(d_reg);
-	if (d_tmp) cudaFree(d_tmp);
+	out_reg.commit();
+	tmp_free(d_tmp);
 	records[10] = free_mb();
 	records[7] = (float)(now_s() - t_start);
 	if (verbose) printf("\t... registration done !!! \n");
@@ -431,18 +503,14 @@ int reg2d(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int 
 				return 1;
 			}
 			const long long n = (long long)s1[0] * s1[1];
-			float *d_t = nullptr, *d_s = nullptr;
-			cuda_fatal(cudaMalloc(&d_t, sizeof(float) * n), "cudaMalloc");
-			cuda_fatal(cudaMalloc(&d_s, sizeof(float) * n), "cudaMalloc");
-			cuda_fatal(cudaMemcpy(d_t, h_img1, sizeof(float) * n, cudaMemcpyHostToDevice), "H2D");
-			cuda_fatal(cudaMemcpy(d_s, h_img2, sizeof(float) * n, cudaMemcpyHostToDevice), "H2D");
+			DevIn<float> in_t(h_img1, (size_t)n), in_s(h_img2, (size_t)n);
+			DevOut<float> out_reg(h_reg, (size_t)n);
 			const unsigned int s3[3] = {s1[0], s1[1], 1};
 			long long sh[3] = {0, 0, 0};
-			rc = milb_phasor(sh, d_t, d_s, s3, nullptr);
+			rc = milb_phasor(sh, in_t.d, in_s.d, s3, nullptr);
 			const long long neg[3] = {-sh[0], -sh[1], 0};
-			if (rc == MILB_OK) rc = milb_imshift(d_t, d_s, s3, neg, nullptr);
-			if (rc == MILB_OK) cuda_fatal(cudaMemcpy(h_reg, d_t, sizeof(float) * n, cudaMemcpyDeviceToHost), "D2H");
-			cudaFree(d_t); cudaFree(d_s);
+			if (rc == MILB_OK) rc = milb_imshift(out_reg.d, in_s.d, s3, neg, nullptr);
+			if (rc == MILB_OK) out_reg.commit();
 			iTmx[0] = 1; iTmx[1] = 0; iTmx[2] = (float)sh[0];
 			iTmx[3] = 0; iTmx[4] = 1; iTmx[5] = (float)sh[1];
 			break;
@@ -469,7 +537,11 @@ int reg2d(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int 
 int atrans3dgpu(float *h_reg, float *iTmx, float *h_img2, unsigned int *imSize1, unsigned int *imSize2, int deviceNum)
 {
 	cuda_fatal(cudaSetDevice(deviceNum), "cudaSetDevice");
-	fatal_if(milb_affine_warp(h_reg, imSize1, h_img2, imSize2, iTmx, 0, nullptr), "affine transformation");
+	const size_t n1 = (size_t)imSize1[0] * imSize1[1] * imSize1[2], n2 = (size_t)imSize2[0] * imSize2[1] * imSize2[2];
+	DevIn<float> in(h_img2, n2);
+	DevOut<float> out(h_reg, n1);
+	fatal_if(milb_affine_warp(out.d, imSize1, in.d, imSize2, iTmx, 1, nullptr), "affine transformation");
+	out.commit();
 	return 0;
 }
 
@@ -477,13 +549,10 @@ int atrans3dgpu_16bit(unsigned short *h_reg, float *iTmx, unsigned short *h_img2
 {
 	cuda_fatal(cudaSetDevice(deviceNum), "cudaSetDevice");
 	const long long n1 = (long long)imSize1[0] * imSize1[1] * imSize1[2], n2 = (long long)imSize2[0] * imSize2[1] * imSize2[2];
-	unsigned short *d_o = nullptr, *d_i = nullptr;
-	cuda_fatal(cudaMalloc(&d_o, n1 * 2), "cudaMalloc");
-	cuda_fatal(cudaMalloc(&d_i, n2 * 2), "cudaMalloc");
-	cuda_fatal(cudaMemcpy(d_i, h_img2, n2 * 2, cudaMemcpyHostToDevice), "H2D");
-	fatal_if(milb_warp_u16_dev(d_o, d_i, imSize1[0], imSize1[1], imSize1[2], imSize2[0], imSize2[1], imSize2[2], iTmx, nullptr), "warp16");
-	cuda_fatal(cudaMemcpy(h_reg, d_o, n1 * 2, cudaMemcpyDeviceToHost), "D2H");
-	cudaFree(d_o); cudaFree(d_i);
+	DevIn<unsigned short> in(h_img2, (size_t)n2);
+	DevOut<unsigned short> out(h_reg, (size_t)n1);
+	fatal_if(milb_warp_u16_dev(out.d, in.d, imSize1[0], imSize1[1], imSize1[2], imSize2[0], imSize2[1], imSize2[2], iTmx, nullptr), "warp16");
+	out.commit();
 	return 0;
 }
 
@@ -497,15 +566,12 @@ int alignsize3d(float *h_odata, float *h_idata, long long int sx, long long int 
 		printf("\n****Wrong gpuMemMode setup, processing stopped !!! ****\n");
 		return 1;
 	}
-	float *d_o = nullptr, *d_i = nullptr;
-	cuda_fatal(cudaMalloc(&d_o, sizeof(float) * sx * sy * sz), "cudaMalloc");
-	cuda_fatal(cudaMalloc(&d_i, sizeof(float) * sx2 * sy2 * sz2), "cudaMalloc");
-	cuda_fatal(cudaMemcpy(d_i, h_idata, sizeof(float) * sx2 * sy2 * sz2, cudaMemcpyHostToDevice), "H2D");
+	DevIn<float> in(h_idata, (size_t)(sx2 * sy2 * sz2));
+	DevOut<float> out(h_odata, (size_t)(sx * sy * sz));
 	// the reference passes (sx,sy,sz) with sx the SLOWEST axis of its kernel; the per-axis rule is
 	// symmetric, so in x-fastest terms this is the same call with the axes reversed
-	fatal_if(milb_alignsize_dev(d_o, d_i, (int)sz, (int)sy, (int)sx, (int)sz2, (int)sy2, (int)sx2, nullptr), "alignsize");
-	cuda_fatal(cudaMemcpy(h_odata, d_o, sizeof(float) * sx * sy * sz, cudaMemcpyDeviceToHost), "D2H");
-	cudaFree(d_o); cudaFree(d_i);
+	fatal_if(milb_alignsize_dev(out.d, in.d, (int)sz, (int)sy, (int)sx, (int)sz2, (int)sy2, (int)sx2, nullptr), "alignsize");
+	out.commit();
 	return 0;
 }
 
@@ -531,13 +597,12 @@ int imoperation3D(float *h_odata, unsigned int *sizeOut, float *h_idata, unsigne
 		return 1;
 	}
 	const long long n = (long long)sizeIn[0] * sizeIn[1] * sizeIn[2];
-	float *d_o = nullptr, *d_i = nullptr;
-	cuda_fatal(cudaMalloc(&d_o, sizeof(float) * n), "cudaMalloc");
-	cuda_fatal(cudaMalloc(&d_i, sizeof(float) * n), "cudaMalloc");
-	cuda_fatal(cudaMemcpy(d_i, h_idata, sizeof(float) * n, cudaMemcpyHostToDevice), "H2D");
-	fatal_if(milb_rot_y_dev(d_o, d_i, sizeIn[0], sizeIn[1], sizeIn[2], opChoice == 1 ? 1 : -1, nullptr), "rotation");
-	cuda_fatal(cudaMemcpy(h_odata, d_o, sizeof(float) * n, cudaMemcpyDeviceToHost), "D2H");
-	cudaFree(d_o); cudaFree(d_i);
+	{
+		DevIn<float> in(h_idata, (size_t)n);
+		DevOut<float> out(h_odata, (size_t)n);
+		fatal_if(milb_rot_y_dev(out.d, in.d, sizeIn[0], sizeIn[1], sizeIn[2], opChoice == 1 ? 1 : -1, nullptr), "rotation");
+		out.commit();
+	}
 	const unsigned int a = sizeIn[0], b = sizeIn[1], c = sizeIn[2];
 	sizeOut[0] = c; sizeOut[1] = b; sizeOut[2] = a;
 	return 0;
@@ -551,17 +616,16 @@ int mp2dgpu(float *h_MP, unsigned int *sizeMP, float *h_img, unsigned int *sizeI
 	(void)flagYProj; // sic: the reference gates the Y projection by flagZProj (src/apifunc.cpp:498)
 	const int sx = sizeImg[0], sy = sizeImg[1], sz = sizeImg[2];
 	const long long n = (long long)sx * sy * sz, nmp = (long long)sx * sy + (long long)sy * sz + (long long)sz * sx;
-	float *d_img = nullptr, *d_mp = nullptr;
-	cuda_fatal(cudaMalloc(&d_img, sizeof(float) * n), "cudaMalloc");
-	cuda_fatal(cudaMalloc(&d_mp, sizeof(float) * nmp), "cudaMalloc");
-	cuda_fatal(cudaMemset(d_mp, 0, sizeof(float) * nmp), "memset");
-	cuda_fatal(cudaMemcpy(d_img, h_img, sizeof(float) * n, cudaMemcpyHostToDevice), "H2D");
+	DevIn<float> in(h_img, (size_t)n);
+	DevOut<float> out(h_MP, (size_t)nmp);
+	const float *d_img = in.d;
+	float *d_mp = out.d;
+	cuda_fatal(cudaMemsetAsync(d_mp, 0, sizeof(float) * nmp, 0), "memset");
 	if (flagZProj) fatal_if(milb_mip_dev(d_mp, d_img, sx, sy, sz, 1, nullptr), "mip");
 	if (flagXProj) fatal_if(milb_mip_dev(d_mp + (long long)sx * sy, d_img, sx, sy, sz, 3, nullptr), "mip");
 	if (flagZProj) fatal_if(milb_mip_dev(d_mp + (long long)sx * sy + (long long)sy * sz, d_img, sx, sy, sz, 2, nullptr), "mip");
 	sizeMP[0] = sx; sizeMP[1] = sy; sizeMP[2] = sy; sizeMP[3] = sz; sizeMP[4] = sz; sizeMP[5] = sx;
-	cuda_fatal(cudaMemcpy(h_MP, d_mp, sizeof(float) * nmp, cudaMemcpyDeviceToHost), "D2H");
-	cudaFree(d_img); cudaFree(d_mp);
+	out.commit();
 	return 0;
 }
 
@@ -594,7 +658,9 @@ static void rot2matrix(float *p_out, float theta, long long sx, long long sy, lo
 	milb_matrixmultiply(p_out, t, t3);
 }
 
-static int mip3d_axis(float *h_MP, float *d_img, const unsigned int *sizeImg, int rAxis, long long projectNum, float projectStep,
+// one rotation axis: all projectNum projections in ONE launch (geom.cu k_rot_mip: the rotated volume is never written) and one
+// copy of the whole stack.  h_MP may be a host or a device pointer.
+static int mip3d_axis(float *h_MP, const float *d_img, const unsigned int *sizeImg, int rAxis, long long projectNum, float projectStep,
 	unsigned int *sizeOut /* 3 */)
 {
 	const long long sx = sizeImg[0], sy = sizeImg[1], sz = sizeImg[2];
@@ -602,19 +668,12 @@ static int mip3d_axis(float *h_MP, float *d_img, const unsigned int *sizeImg, in
 	if (rAxis == 1) { sr = sx; R = (long long)round(sqrt((double)(sy * sy + sz * sz))); }
 	else { sr = sy; R = (long long)round(sqrt((double)(sx * sx + sz * sz))); }
 	const unsigned int so[3] = {(unsigned)(rAxis == 1 ? sr : R), (unsigned)(rAxis == 1 ? R : sr), (unsigned)R};
-	const long long nrot = sr * R * R, nproj = sr * R;
-	float *d_rot = nullptr, *d_proj = nullptr;
-	cuda_fatal(cudaMalloc(&d_rot, sizeof(float) * nrot), "cudaMalloc");
-	cuda_fatal(cudaMalloc(&d_proj, sizeof(float) * nproj), "cudaMalloc");
-	for (long long i = 0; i < projectNum; i++) {
-		const float ang = projectStep * i;
-		float aff[12];
-		rot2matrix(aff, ang, sx, sy, sz, rAxis);
-		fatal_if(milb_affine_warp(d_rot, so, d_img, sizeImg, aff, 1, nullptr), "mip3d warp");
-		fatal_if(milb_mip_dev(d_proj, d_rot, so[0], so[1], so[2], 1, nullptr), "mip3d projection");
-		cuda_fatal(cudaMemcpy(h_MP + nproj * i, d_proj, sizeof(float) * nproj, cudaMemcpyDeviceToHost), "D2H");
-	}
-	cudaFree(d_rot); cudaFree(d_proj);
+	const long long nproj = sr * R;
+	std::vector<float> aff((size_t)12 * projectNum);
+	for (long long i = 0; i < projectNum; i++) rot2matrix(aff.data() + 12 * i, projectStep * i, sx, sy, sz, rAxis);
+	DevOut<float> out(h_MP, (size_t)(nproj * projectNum));
+	fatal_if(milb_rot_mip_dev(out.d, d_img, so, sizeImg, aff.data(), (int)projectNum, nullptr), "mip3d projections");
+	out.commit();
 	sizeOut[0] = so[0]; sizeOut[1] = so[1]; sizeOut[2] = (unsigned)projectNum;
 	return 0;
 }
@@ -624,12 +683,9 @@ int mip3dgpu(float *h_MP, unsigned int *sizeMP, float *h_img, unsigned int *size
 	// src/apifunc.cpp:576-644
 	if (rAxis != 1 && rAxis != 2) return -1;
 	const long long n = (long long)sizeImg[0] * sizeImg[1] * sizeImg[2];
-	float *d_img = nullptr;
-	cuda_fatal(cudaMalloc(&d_img, sizeof(float) * n), "cudaMalloc");
-	cuda_fatal(cudaMemcpy(d_img, h_img, sizeof(float) * n, cudaMemcpyHostToDevice), "H2D");
+	DevIn<float> in(h_img, (size_t)n);
 	const float projectStep = (float)(3.14159 * 2 / (float)projectNum);
-	mip3d_axis(h_MP, d_img, sizeImg, rAxis, projectNum, projectStep, sizeMP);
-	cudaFree(d_img);
+	mip3d_axis(h_MP, in.d, sizeImg, rAxis, projectNum, projectStep, sizeMP);
 	return 0;
 }
 
@@ -639,17 +695,14 @@ int mp3dgpu(float *h_MP, unsigned int *sizeMP, float *h_img, unsigned int *sizeI
 	if (!flagXaxis && !flagYaxis) return -1;
 	const long long sx = sizeImg[0], sy = sizeImg[1], sz = sizeImg[2];
 	const long long n = sx * sy * sz;
-	float *d_img = nullptr;
-	cuda_fatal(cudaMalloc(&d_img, sizeof(float) * n), "cudaMalloc");
-	cuda_fatal(cudaMemcpy(d_img, h_img, sizeof(float) * n, cudaMemcpyHostToDevice), "H2D");
+	DevIn<float> in(h_img, (size_t)n);
 	const float projectStep = (float)(3.14159 * 2 / projectNum);
-	if (flagXaxis) mip3d_axis(h_MP, d_img, sizeImg, 1, projectNum, projectStep, sizeMP);
+	if (flagXaxis) mip3d_axis(h_MP, in.d, sizeImg, 1, projectNum, projectStep, sizeMP);
 	if (flagYaxis) {
 		const long long Ry = (long long)round(sqrt((double)(sy * sy + sz * sz)));
 		const long long ystart = sx * Ry * projectNum; // offset is applied even when the X stack is absent (:548)
-		mip3d_axis(h_MP + ystart, d_img, sizeImg, 2, projectNum, projectStep, sizeMP + 3);
+		mip3d_axis(h_MP + ystart, in.d, sizeImg, 2, projectNum, projectStep, sizeMP + 3);
 	}
-	cudaFree(d_img);
 	return 0;
 }
 

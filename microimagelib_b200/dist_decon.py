@@ -135,13 +135,13 @@ class DistDecon:
         L = self.L
         self.nviews = nviews
         self.fused = (os.environ.get("MILB_DIST_FUSED", "1") != "0") if fused is None else bool(fused)
-        # the fused exchange needs <= 8 ranks, power-of-two slabs, and X-pass tiles (4096 / X column pairs)
-        # that do not straddle rows of Z / 2 pairs; anything else takes the all-to-all path
-        if self.fused and (self.world > 8 or (L.ny & (L.ny - 1)) or min(L.counts) < 1 or (L.Z // 2) % max(4096 // L.X, 1)):
-            self.fused = False
         self._h = C.c_void_p()
         size = (C.c_uint * 3)(L.Z, L.Y, L.X)
         _check(self.lib.milb_dslab_create(C.byref(self._h), size, L.y0, L.ny, L.np), "milb_dslab_create")
+        # the fused exchange needs <= 8 ranks, power-of-two slabs and X-pass tiles that stay inside one row (the library knows its
+        # tile width); every rank must own at least one plane; anything else takes the all-to-all path
+        if self.fused and (min(L.counts) < 1 or not self.lib.milb_dslab_can_fuse(self._h, self.world)):
+            self.fused = False
         f32 = dict(dtype=torch.float32, device=self.dev)
         self.A = [torch.empty((L.X, L.ny, L.Z), **f32) for _ in range(nviews)]
         self.E = torch.empty((L.X, L.ny, L.Z), **f32)

@@ -103,16 +103,20 @@ def test_spim_fusion_batch_pipeline_and_sharding(tmp_path):
         libapi.writetifstack(in1 / f"A_{t}.tif", a, 16)
         libapi.writetifstack(in2 / f"B_{t}.tif", b, 16)
     runs = {}
-    for tag, env in (("seq", {"MILB_PIPELINE": "0"}), ("pipe", {"MILB_PIPELINE": "1"})):
+    # seq: host round trips between the stages and no I/O threads (the reference's structure); pipe: I/O threads;
+    # resident (the default): the time point stays on the GPU between the stages, 16-bit <-> float on the GPU
+    for tag, env in (("seq", {"MILB_PIPELINE": "0", "MILB_DEVICE_RESIDENT": "0"}), ("pipe", {"MILB_PIPELINE": "1", "MILB_DEVICE_RESIDENT": "0"}),
+                     ("resident", {"MILB_PIPELINE": "1"}), ("resident_seq", {"MILB_PIPELINE": "0"})):
         out = tmp_path / tag
         r = subprocess.run(_batch_cmd(out, in1, in2, tmp_path / "pa.tif", tmp_path / "pb.tif", 0, 2, 3), capture_output=True, text=True,
                            env={**os.environ, **env}, timeout=600)
         assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
         runs[tag] = _tree(out)
     assert len(runs["seq"]) >= 3 * (1 + 1 + 1 + 3)            # per time point: Decon, RegB, matrix, three 2-D MIPs
-    assert runs["seq"].keys() == runs["pipe"].keys()
-    for k in runs["seq"]:
-        assert runs["seq"][k] == runs["pipe"][k], k
+    for tag in ("pipe", "resident", "resident_seq"):
+        assert runs["seq"].keys() == runs[tag].keys()
+        for k in runs["seq"]:
+            assert runs["seq"][k] == runs[tag][k], (tag, k)
     # two shards (both on GPU 0 here: MILB_SHARD_DEVICE_STRIDE=0) write the same files as the single process
     out = tmp_path / "shards"
     procs = [subprocess.Popen(_batch_cmd(out, in1, in2, tmp_path / "pa.tif", tmp_path / "pb.tif", 0, 2, 3), stdout=subprocess.PIPE,

@@ -124,3 +124,74 @@ def test_atrans_16bit_is_point_sampled():
     ok = (tx >= 0) & (tx < 10) & (ty >= 0) & (ty < 8) & (tz >= 0) & (tz < 6)
     want = np.where(ok, v[np.clip(np.floor(tz).astype(int), 0, 5), np.clip(np.floor(ty).astype(int), 0, 7), np.clip(np.floor(tx).astype(int), 0, 9)], 0)
     assert st == 0 and np.array_equal(got, want.astype(np.uint16))
+
+
+def test_libapi_accepts_device_pointers():
+    """Extension of this backend: every volume argument of the libapi.h entry points may be a device pointer (used in place,
+    written in place).  Same results as with host buffers, bit for bit."""
+    import ctypes as C
+    import torch
+    from microimagelib_b200 import _lib, libapi, synth
+    lib = _lib.load()
+    F, U = C.POINTER(C.c_float), C.POINTER(C.c_uint)
+    rng = np.random.default_rng(3)
+    vol = (rng.random((20, 28, 36)) * 4000).astype(np.float32)
+    d_vol = torch.from_numpy(vol).cuda()
+
+    def fp(t):
+        return C.cast(t.data_ptr(), F)
+
+    size = (C.c_uint * 3)(36, 28, 20)
+    # rotation
+    want, _ = libapi.imoperation3D(vol, 1)
+    d_out = torch.empty(vol.size, dtype=torch.float32, device="cuda")
+    so = (C.c_uint * 3)()
+    assert lib.imoperation3D(fp(d_out), so, fp(d_vol), size, 1, 0) == 0
+    assert np.array_equal(d_out.cpu().numpy().reshape(so[2], so[1], so[0]), want)
+    # resampling (the warp)
+    want, _ = libapi.imresize3d(vol, (30, 28, 36))
+    d_out = torch.empty((30, 28, 36), dtype=torch.float32, device="cuda")
+    assert lib.imresize3d(fp(d_out), fp(d_vol), 36, 28, 30, 36, 28, 20, 0) == 0
+    assert np.array_equal(d_out.cpu().numpy(), want)
+    # 2-D projections: device volume in, host projections out
+    zp, xp, yp, _ = libapi.mp2dgpu(vol)
+    buf = np.zeros(36 * 28 + 28 * 20 + 20 * 36, np.float32)
+    smp = (C.c_uint * 6)()
+    assert lib.mp2dgpu(buf.ctypes.data_as(F), smp, fp(d_vol), size, True, True, True) == 0
+    assert np.array_equal(buf[:36 * 28].reshape(28, 36), zp) and np.array_equal(buf[36 * 28:36 * 28 + 28 * 20].reshape(20, 28), xp)
+    # rotating projections: device volume in, device stack out
+    want, _ = libapi.mip3dgpu(vol, 2, 5)
+    d_mp = torch.zeros(want.shape, dtype=torch.float32, device="cuda")
+    s3 = (C.c_uint * 3)()
+    assert lib.mip3dgpu(fp(d_mp), s3, fp(d_vol), size, 2, 5) == 0
+    assert np.array_equal(d_mp.cpu().numpy(), want)
+    # deconvolution and registration
+    psf = synth.gaussian_psf((9, 9, 9), (2, 2, 2))
+    img = synth.bead_image((16, 32, 32), psf, density=1 / 256.0, seed=9)
+    want, st, _ = libapi.decon_singleview(img, psf, 4)
+    d_img, d_dec = torch.from_numpy(img).cuda(), torch.empty(img.shape, dtype=torch.float32, device="cuda")
+    rec = np.zeros(10, np.float32)
+    isz, psz = (C.c_uint * 3)(32, 32, 16), (C.c_uint * 3)(9, 9, 9)
+    assert lib.decon_singleview(fp(d_dec), fp(d_img), isz, psf.ctypes.data_as(F), psz, False, 4, 0, 1, False, rec.ctypes.data_as(F), False,
+                                psf.ctypes.data_as(F)) == 0
+    assert np.array_equal(d_dec.cpu().numpy(), want)
+    m = synth.affine_matrix(rot_z_deg=1.0, scale=(1.01, 0.99, 1.0), shift=(0.5, -0.5, 0.25), center=(16, 16, 8))
+    src = synth.warp_exact(img, m)
+    reg_w, tmx_w, st, rec_w = libapi.reg3d(img, src, regChoice=2, regMethod=2, FTOL=1e-3, itLimit=300)
+    d_src, d_reg = torch.from_numpy(src).cuda(), torch.empty(img.shape, dtype=torch.float32, device="cuda")
+    tmx = np.array([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], np.float32)
+    rrec = np.zeros(11, np.float32)
+    assert lib.reg3d(fp(d_reg), tmx.ctypes.data_as(F), fp(d_img), fp(d_src), isz, isz, 2, 2, False, 1e-3, 300, 0, 1, False, rrec.ctypes.data_as(F)) == 0
+    assert np.array_equal(tmx, tmx_w) and np.array_equal(d_reg.cpu().numpy(), reg_w)
+    # 16-bit <-> float conversions: (float)uint16 and the x86 (unsigned short)(int)float truncation, no clamp
+    f = np.array([0.0, 0.99, 1.0, 65535.7, 65536.0, 70000.5, -1.0, -0.5, 3e9, -3e9, 123.999], np.float32)
+    d_f = torch.from_numpy(f).cuda()
+    d_u = torch.zeros(f.size, dtype=torch.int16, device="cuda")
+    assert lib.milb_convert_f32_to_u16(d_u.data_ptr(), d_f.data_ptr(), f.size, None) == 0
+    torch.cuda.synchronize()
+    want16 = np.array([0, 0, 1, 65535, 0, 70000 - 65536, 65535, 0, 0, 0, 123], np.uint16)
+    assert np.array_equal(d_u.cpu().numpy().view(np.uint16), want16)
+    d_back = torch.zeros(f.size, dtype=torch.float32, device="cuda")
+    assert lib.milb_convert_u16_to_f32(d_back.data_ptr(), d_u.data_ptr(), f.size, None) == 0
+    torch.cuda.synchronize()
+    assert np.array_equal(d_back.cpu().numpy(), want16.astype(np.float32))
