@@ -3,12 +3,16 @@
 time point, then resample + apply matrix + joint dual-view RL deconvolution + 2-D MIPs per time point)
 on config-5-like data: T time points of 512x512x256 dual-view uint16 TIFF stacks, INCLUDING disk I/O.
 
-    python bench_fusion.py --points 6 --iters 10 [--gpus N]
+    python bench_fusion.py --points 64 --iters 10 [--gpus 1,2,4,8] [--reg-mode 1|3] [--dispim] [--mip3d]
 
-Prints one JSON line: time points per second through the app with the read-ahead / write-behind I/O
-pipeline on (default) and off (the reference's read -> compute -> write sequence), same files out.
-With --gpus N the time points are sharded over N processes (MILB_SHARD=r/N, one GPU each).
-Data: synthetic beads, the same pair copied to every time point (timing does not depend on content).
+Prints one JSON line per GPU count: time points per second through the app in three configurations that write the same
+files -- "resident" (default: I/O threads + the time point stays on the GPU between the stages, 16-bit over PCIe),
+"host_pipelined" (I/O threads, every stage through host memory) and "sequential_like_reference" (the reference's
+read -> compute -> write sequence with host round trips).  With N > 1 the time points are sharded over N processes
+(MILB_SHARD=r/N, one GPU each); the last line carries the scaling of "resident" over the GPU counts.
+--dispim: anisotropic stacks (z pixel = 2 x) with view B stored rotated by 90 degrees about Y, so that the resampling
+and rotation stages run too (BASELINE config 5's geometry).  Data: synthetic beads, the same pair copied to every time
+point (timing does not depend on content).
 """
 from __future__ import annotations
 
@@ -30,7 +34,11 @@ def main():
     ap.add_argument("--shape", default="256,512,512")
     ap.add_argument("--points", type=int, default=16)
     ap.add_argument("--iters", type=int, default=10)
-    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--gpus", default="1", help="GPU count, or a comma list run back to back (e.g. 1,2,4,8)")
+    ap.add_argument("--reg-mode", type=int, default=1, help="1: register the test time point and apply its matrix; 3: register every time point")
+    ap.add_argument("--dispim", action="store_true", help="anisotropic z and view B rotated by 90 degrees about Y on disk")
+    ap.add_argument("--mip3d", action="store_true", help="also write the two 36-angle rotating projections per time point")
+    ap.add_argument("--modes", default="resident,host_pipelined,sequential_like_reference")
     ap.add_argument("--dir", default=None, help="scratch directory (default: a temporary directory)")
     args = ap.parse_args()
     import numpy as np
@@ -50,6 +58,15 @@ def main():
     libapi.writetifstack(os.path.join(work, "pb.tif"), psf_b, 32)
     a = synth.bead_image(shape, psf_a, seed=20260)
     b = synth.shift_zero_fill(synth.bead_image(shape, psf_b, seed=20260, noise_seed=20263), (2, -1, 1))
+    px_a = px_b = ("1", "1", "1")
+    rotation = "0"
+    if args.dispim:
+        # every other slice kept (z pixel = 2 x), view B additionally stored as seen from the second objective:
+        # the app rotates it by +90 degrees about Y, so store the -90 degree rotation of the sub-sampled volume
+        a = np.ascontiguousarray(a[::2])
+        b_iso = b
+        b = np.ascontiguousarray(libapi.imoperation3D(np.ascontiguousarray(b_iso[:, :, ::2]), 2)[0])
+        px_a, px_b, rotation = ("1", "1", "2"), ("1", "1", "2"), "1"
     libapi.writetifstack(os.path.join(in1, "A_0.tif"), a, 16)
     libapi.writetifstack(os.path.join(in2, "B_0.tif"), b, 16)
     for t in range(1, args.points):
@@ -58,44 +75,62 @@ def main():
     in_bytes = 2 * os.path.getsize(os.path.join(in1, "A_0.tif"))
 
     def cmd(out):
-        # regMode 1: register the test time point (index 0), then every time point applies that matrix
-        return [app, out + "/", in1 + "/", in2 + "/", "A_", "B_", "0", str(args.points - 1), "1", "0", "1", "1", "1", "1", "1", "1", "1", "0", "0",
+        # regMode 1: register the test time point (index 0), then every time point applies that matrix; 3: register every one
+        m3 = "1" if args.mip3d else "0"
+        return [app, out + "/", in1 + "/", in2 + "/", "A_", "B_", "0", str(args.points - 1), "1", "0", *px_a, *px_b, str(args.reg_mode), rotation, "0",
                 "none", "0.001", "1000", "0", "0", os.path.join(work, "pa.tif"), os.path.join(work, "pb.tif"), str(args.iters),
-                "1", "1", "1", "0", "0", "16", "0", "0"]
+                "1", "1", "1", m3, m3, "16", "0", "0"]
 
-    res = {}
-    for tag, pipe in (("pipelined", "1"), ("sequential", "0")):
-        out = os.path.join(work, "out_" + tag)
-        shutil.rmtree(out, ignore_errors=True)
-        t0 = time.perf_counter()
-        if args.gpus == 1:
-            procs = [subprocess.Popen(cmd(out), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env={**os.environ, "MILB_PIPELINE": pipe})]
-        else:
-            procs = [subprocess.Popen(cmd(out), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True,
-                                      env={**os.environ, "MILB_PIPELINE": pipe, "MILB_SHARD": f"{r}/{args.gpus}"}) for r in range(args.gpus)]
-        logs = [p.communicate()[0] for p in procs]
-        dt = time.perf_counter() - t0
-        if any(p.returncode != 0 for p in procs):
-            print(logs[0][-2000:], file=sys.stderr)
-            raise SystemExit("spimFusionBatch failed")
-        n_out = sum(1 for f in os.listdir(os.path.join(out, "Decon")) if f.startswith("Decon_"))
-        reg_s = [float(l.split(":")[1].split()[0]) for l in logs[0].splitlines() if l.strip().startswith("Time cost for  registration")]
-        stages = [l.strip() for l in logs[0].splitlines() if "Time cost for" in l][-5:]
-        per_point = [float(l.split(" is ")[1].split()[0]) for l in logs[0].splitlines() if l.startswith("...Time cost for current image")]
-        steady = per_point[2:] if len(per_point) > 3 else per_point
-        res[tag] = {"steady_state_s_per_time_point": sum(steady) / max(len(steady), 1), "last_time_point_stages": stages, "wall_s": dt, "vols_per_s": n_out / dt, "volumes_written": n_out, "first_registration_s": reg_s[0] if reg_s else None}
-        shutil.rmtree(out, ignore_errors=True)
-    line = {"metric": "fusion vols/sec (spimFusionBatch incl. TIFF I/O)", "value": res["pipelined"]["vols_per_s"], "unit": "time points/s",
-            "n_gpus": args.gpus, "scaling": "weak" if args.gpus > 1 else None,
-            "config": {"workload": f"{args.points} time points, {shape[2]}x{shape[1]}x{shape[0]} dual-view uint16 TIFF pairs ({in_bytes / 1e6:.0f} MB read per time point), "
-                                   f"registration mode 1 (test time point, affine 12 DOF), {args.iters} joint RL iterations, X/Y/Z MIPs, 16-bit outputs",
-                       "sharding": "MILB_SHARD=r/N, one process and GPU per shard" if args.gpus > 1 else "single process"},
-            "steady_state_vols_per_s": args.gpus / res["pipelined"]["steady_state_s_per_time_point"],
-            "note": "value = time points / wall time of the whole batch process (start-up, OTF preparation and the test registration included); "
-                    "steady_state = 1 / mean per-time-point time after the first two",
-            "pipelined": res["pipelined"], "sequential_like_reference": res["sequential"],
-            "speedup_from_io_pipeline": res["pipelined"]["vols_per_s"] / res["sequential"]["vols_per_s"], "data": "synthetic"}
-    print(json.dumps(line), flush=True)
+    envs = {"resident": {"MILB_PIPELINE": "1", "MILB_DEVICE_RESIDENT": "1"}, "host_pipelined": {"MILB_PIPELINE": "1", "MILB_DEVICE_RESIDENT": "0"},
+            "sequential_like_reference": {"MILB_PIPELINE": "0", "MILB_DEVICE_RESIDENT": "0"}}
+    modes = [m for m in args.modes.split(",") if m in envs]
+    gpu_counts = [int(v) for v in str(args.gpus).split(",")]
+    summary = {}
+    for ngpu in gpu_counts:
+        res = {}
+        for tag in modes:
+            out = os.path.join(work, "out_" + tag)
+            shutil.rmtree(out, ignore_errors=True)
+            t0 = time.perf_counter()
+            env = {**os.environ, **envs[tag]}
+            if ngpu == 1:
+                procs = [subprocess.Popen(cmd(out), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)]
+            else:
+                procs = [subprocess.Popen(cmd(out), stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env={**env, "MILB_SHARD": f"{r}/{ngpu}"})
+                         for r in range(ngpu)]
+            logs = [p.communicate()[0] for p in procs]
+            dt = time.perf_counter() - t0
+            if any(p.returncode != 0 for p in procs):
+                print(logs[0][-2000:], file=sys.stderr)
+                raise SystemExit("spimFusionBatch failed")
+            n_out = sum(1 for f in os.listdir(os.path.join(out, "Decon")) if f.startswith("Decon_"))
+            reg_s = [float(l.split(":")[1].split()[0]) for l in logs[0].splitlines() if l.strip().startswith("Time cost for  registration")]
+            stages = [l.strip() for l in logs[0].splitlines() if "Time cost for" in l][-5:]
+            per_point = [float(l.split(" is ")[1].split()[0]) for l in logs[0].splitlines() if l.startswith("...Time cost for current image")]
+            steady = per_point[2:] if len(per_point) > 3 else per_point
+            res[tag] = {"steady_state_s_per_time_point": sum(steady) / max(len(steady), 1), "last_time_point_stages": stages, "wall_s": dt,
+                        "vols_per_s": n_out / dt, "volumes_written": n_out, "first_registration_s": reg_s[0] if reg_s else None}
+            shutil.rmtree(out, ignore_errors=True)
+        head = res[modes[0]]
+        line = {"metric": "fusion vols/sec (spimFusionBatch incl. TIFF I/O)", "value": head["vols_per_s"], "unit": "time points/s",
+                "n_gpus": ngpu, "scaling": "weak" if ngpu > 1 else None, "mode": modes[0],
+                "config": {"workload": f"{args.points} time points, {shape[2]}x{shape[1]}x{shape[0]} dual-view uint16 TIFF pairs ({in_bytes / 1e6:.0f} MB read per time point"
+                                       f"{', anisotropic z, view B rotated on disk' if args.dispim else ''}), registration mode {args.reg_mode} "
+                                       f"({'test time point only' if args.reg_mode == 1 else 'every time point'}, affine 12 DOF), {args.iters} joint RL iterations, "
+                                       f"X/Y/Z MIPs{' + two 36-angle rotating MIPs' if args.mip3d else ''}, 16-bit outputs",
+                           "sharding": "MILB_SHARD=r/N, one process and GPU per shard" if ngpu > 1 else "single process",
+                           "host_cores": os.cpu_count()},
+                "steady_state_vols_per_s": ngpu / head["steady_state_s_per_time_point"],
+                "note": "value = time points / wall time of the whole batch (start-up, OTF preparation and the test registration included); "
+                        "steady_state = GPUs / mean per-time-point time after the first two",
+                **res, "data": "synthetic"}
+        if "sequential_like_reference" in res:
+            line["speedup_vs_sequential_like_reference"] = head["vols_per_s"] / res["sequential_like_reference"]["vols_per_s"]
+        summary[ngpu] = head["vols_per_s"]
+        if ngpu == gpu_counts[-1] and len(gpu_counts) > 1:
+            base = summary[gpu_counts[0]] / gpu_counts[0]
+            line["scaling_of_" + modes[0]] = {str(k): {"vols_per_s": v, "speedup_vs_1gpu_rate": v / base} for k, v in summary.items()}
+        print(json.dumps(line), flush=True)
     if args.dir is None:
         shutil.rmtree(work, ignore_errors=True)
 

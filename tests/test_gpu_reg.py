@@ -142,7 +142,7 @@ def test_registration_matches_oracle(method):
     assert np.array_equal(reg, ref["reg"]) or corner_disp(tmx, ref["tmx"], tgt.shape) > 0
     # and it found the transform we applied (method 2 is rigid only: looser)
     if method != 2:
-        assert corner_disp(tmx, synth.invert_affine(m_true), tgt.shape) < 1.0   # src(x) = tgt(M x) => recovers M^-1
+        assert corner_disp(tmx, synth.invert_affine(m_true), tgt.shape) < 1.5   # src(x) = tgt(M x) => recovers M^-1 (the reference's own run: 1.07 for method 6)
         assert float(rec[3]) > 0.9
 
 
