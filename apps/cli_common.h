@@ -150,3 +150,16 @@ inline const char *gpu_mode_text(int gm)
 }
 
 inline size_t voxels(const unsigned int *s) { return (size_t)s[0] * s[1] * s[2]; }
+
+// readtifstack / readtifstack_16to16 into a buffer of `cap` voxels: the stack's size is looked up first and nothing is read
+// if it does not fit (the caller's size comparison then reports the mismatch instead of the read overrunning the buffer)
+inline void read_stack_checked(float *dst, const std::string &path, size_t cap, unsigned int *size)
+{
+	(void)gettifinfo((char *)path.c_str(), size);
+	if (voxels(size) <= cap) readtifstack(dst, (char *)path.c_str(), size);
+}
+inline void read_stack_checked(unsigned short *dst, const std::string &path, size_t cap, unsigned int *size)
+{
+	(void)gettifinfo((char *)path.c_str(), size);
+	if (voxels(size) <= cap) readtifstack_16to16(dst, (char *)path.c_str(), size);
+}

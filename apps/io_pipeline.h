@@ -33,11 +33,11 @@ public:
 		busy_ = true;
 		th_ = std::thread([this] { // the two views are decoded side by side
 			std::thread second([this] {
-				if (raw16_) readtifstack_16to16(u2_.data(), (char *)k2_.c_str(), s2_);
-				else readtifstack(b2_.data(), (char *)k2_.c_str(), s2_);
+				if (raw16_) read_stack_checked(u2_.data(), k2_, u2_.size(), s2_);
+				else read_stack_checked(b2_.data(), k2_, b2_.size(), s2_);
 			});
-			if (raw16_) readtifstack_16to16(u1_.data(), (char *)k1_.c_str(), s1_);
-			else readtifstack(b1_.data(), (char *)k1_.c_str(), s1_);
+			if (raw16_) read_stack_checked(u1_.data(), k1_, u1_.size(), s1_);
+			else read_stack_checked(b1_.data(), k1_, b1_.size(), s1_);
 			second.join();
 		});
 	}

@@ -178,13 +178,13 @@ int main(int argc, char **argv)
 		if (raw16) {
 			if (!ahead.take16(f1, f2, raw1u, raw2u, tmp, tmp2)) {
 				raw1u.resize(voxels(g.in1)); raw2u.resize(voxels(g.in2));
-				readtifstack_16to16(raw1u.data(), (char *)f1.c_str(), tmp);
-				readtifstack_16to16(raw2u.data(), (char *)f2.c_str(), tmp2);
+				read_stack_checked(raw1u.data(), f1, raw1u.size(), tmp);
+				read_stack_checked(raw2u.data(), f2, raw2u.size(), tmp2);
 			}
 		} else if (!ahead.take(f1, f2, raw1, raw2, tmp, tmp2)) {
 			raw1.resize(voxels(g.in1)); raw2.resize(voxels(g.in2));
-			readtifstack(raw1.data(), (char *)f1.c_str(), tmp);
-			readtifstack(raw2.data(), (char *)f2.c_str(), tmp2);
+			read_stack_checked(raw1.data(), f1, raw1.size(), tmp);
+			read_stack_checked(raw2.data(), f2, raw2.size(), tmp2);
 		}
 		if (memcmp(tmp, g.in1, sizeof tmp)) { printf("\t Input image 1 size does not match !!!\n"); return 1; }
 		if (memcmp(tmp2, g.in2, sizeof tmp2)) { printf("\t Input image 2 size does not match !!!\n"); return 1; }

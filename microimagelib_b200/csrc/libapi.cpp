@@ -440,7 +440,7 @@ int reg3d(float *h_reg, float *iTmx, float *h_img1, float *h_img2, unsigned int 
 		fprintf(stderr, "*** SD of image is zero, empty image input or empty image after initial transformation **** \n");
 		exit(1);
 	}
-	fatal_if(rc == MILB_ERR_ARG ? MILB_OK : rc, "registration failed");
+	fatal_if(rc, "registration failed");
 	out_reg.commit();
 	tmp_free(d_tmp);
 	records[10] = free_mb();

@@ -177,10 +177,8 @@ extern "C" int milb_reg3d_affine(float *reg_out, float *iTmx, const float *targe
 	int affMethod, int flagTmx, float FTOL, int itLimit, int on_device, int verbose, float *records, void *stream)
 {
 	if (!reg_out || !iTmx || !target || !source || !size || !records) return MILB_ERR_ARG;
-	if (affMethod < 0 || affMethod > 7) {
-		printf("\n ****Wrong affine registration method is setup, no registraiton performed !!! **** \n");
-		return MILB_ERR_ARG;
-	}
+	// An affMethod outside 0..7 takes the reference's `default:` branch (src/api_subfunc.cu:2945-2978): a warning, no search, and
+	// the source is still warped by the starting matrix (identity, or iTmx when one was given) -- see the switch below.
 	const double t0 = now_s();
 	milb_reg_t *h = nullptr;
 	MILB_TRY(milb_reg_create(&h, size));
@@ -278,6 +276,9 @@ extern "C" int milb_reg3d_affine(float *reg_out, float *iTmx, const float *targe
 		milb_matrix2p(s.affCoef, p);
 		run(p, xi12, NDIM, 12, FTOL);
 		break;
+	default:
+		printf("\n ****Wrong affine registration method is setup, no registraiton performed !!! **** \n");
+		break; // s.affCoef holds the matrix of the one evaluation made so far: the starting matrix
 	}
 	float affFinal[12];
 	memcpy(affFinal, s.affCoef, sizeof affFinal);

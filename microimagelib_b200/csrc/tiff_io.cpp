@@ -30,6 +30,7 @@ struct Page {
 	uint32_t width = 0, height = 0, rows_per_strip = 0xffffffffu;
 	uint16_t bits = 1, compression = 1, sample_format = 1, samples = 1;
 	std::vector<uint32_t> offsets, counts;
+	bool tiled = false;            // TileWidth / TileLength / TileOffsets / TileByteCounts present
 };
 
 bool read_at(FILE *f, uint64_t off, void *dst, size_t n)
@@ -78,6 +79,7 @@ int64_t read_ifd(const Reader &r, uint32_t off, Page &pg)
 		case 278: if (entry_values(r, e, v) && !v.empty()) pg.rows_per_strip = v[0]; break;
 		case 279: entry_values(r, e, pg.counts); break;
 		case 339: if (entry_values(r, e, v) && !v.empty()) pg.sample_format = (uint16_t)v[0]; break;
+		case 322: case 323: case 324: case 325: pg.tiled = true; break;
 		default: break;
 		}
 	}
@@ -89,11 +91,18 @@ bool open_reader(const char *path, Reader &r, uint32_t &first_ifd)
 	r.f = fopen(path, "rb");
 	if (!r.f) return false;
 	unsigned char hdr[8];
-	if (fread(hdr, 1, 8, r.f) != 8) return false;
-	if (hdr[0] == 'I' && hdr[1] == 'I') r.big = false;
-	else if (hdr[0] == 'M' && hdr[1] == 'M') r.big = true;
-	else return false;
-	if (r.u16(hdr + 2) != 42) return false; // classic TIFF only
+	bool ok = fread(hdr, 1, 8, r.f) == 8;
+	if (ok) {
+		if (hdr[0] == 'I' && hdr[1] == 'I') r.big = false;
+		else if (hdr[0] == 'M' && hdr[1] == 'M') r.big = true;
+		else ok = false;
+	}
+	if (ok && r.u16(hdr + 2) != 42) ok = false; // classic TIFF only
+	if (!ok) {
+		fclose(r.f);
+		r.f = nullptr;
+		return false;
+	}
 	first_ifd = r.u32(hdr + 4);
 	return true;
 }
@@ -104,21 +113,31 @@ void die(const char *msg, const char *path)
 	exit(1);
 }
 
+const uint32_t kMaxPages = 1u << 20; // a directory chain longer than this is a cycle or garbage
+
 // Reads every page into dst (element size = bits/8), native byte order.  Returns pages read.
+// Every page must have the first page's width, height, bit depth and sample format and be stored in strips; at most
+// `max_pages` pages fit the caller's buffer (the callers size it from gettifinfo of the same file) -- anything else is
+// fatal BEFORE a byte is copied, like the reference's libtiff errors are.
 template <typename T>
-uint32_t read_pages(const char *path, T *dst, unsigned int *imsize, uint16_t want_bits)
+uint32_t read_pages(const char *path, T *dst, unsigned int *imsize, uint16_t want_bits, uint32_t max_pages)
 {
 	Reader r;
 	uint32_t off = 0;
 	if (!open_reader(path, r, off)) die("Failed to read image!!! Not a TIFF file", path);
 	uint32_t n = 0;
 	uint32_t W = 0, H = 0;
+	Page first;
 	while (off) {
 		Page pg;
 		const int64_t next = read_ifd(r, off, pg);
 		if (next < 0) die("Failed to read image!!! Corrupt TIFF directory", path);
-		if (n == 0) { W = pg.width; H = pg.height; }
+		if (n == 0) { W = pg.width; H = pg.height; first = pg; }
 		if (pg.compression != 1 || pg.samples != 1) die("Compressed or multi-sample TIFF is not supported", path);
+		if (pg.tiled) die("Tiled TIFF is not supported", path);
+		if (pg.width != W || pg.height != H || pg.bits != first.bits || pg.sample_format != first.sample_format)
+			die("Failed to read image!!! The pages of the stack differ in size or sample type", path);
+		if (n >= max_pages || n >= kMaxPages) die("Failed to read image!!! More pages than the stack was sized for", path);
 		if (pg.bits == want_bits && dst) {
 			const size_t row_bytes = (size_t)pg.width * sizeof(T);
 			unsigned char *out = (unsigned char *)(dst + (size_t)n * W * H);
@@ -229,6 +248,7 @@ unsigned short gettifinfo(char tifdir[], unsigned int *tifSize)
 		if (next < 0) die("Corrupt TIFF directory", tifdir);
 		if (n == 0) first = pg;
 		n++;
+		if (n > kMaxPages) die("Corrupt TIFF directory chain (cycle?)", tifdir);
 		off = (uint32_t)next;
 	}
 	fclose(r.f);
@@ -246,10 +266,10 @@ void readtifstack(float *h_Image, char *tifdir, unsigned int *imsize)
 	const unsigned short bits = gettifinfo(tifdir, sz);
 	if (bits == 16) {
 		std::vector<uint16_t> buf((size_t)sz[0] * sz[1] * sz[2]);
-		read_pages<uint16_t>(tifdir, buf.data(), imsize, 16);
+		read_pages<uint16_t>(tifdir, buf.data(), imsize, 16, sz[2]);
 		for (size_t i = 0; i < buf.size(); i++) h_Image[i] = (float)buf[i];
 	} else if (bits == 32) {
-		read_pages<float>(tifdir, h_Image, imsize, 32);
+		read_pages<float>(tifdir, h_Image, imsize, 32, sz[2]);
 	} else {
 		imsize[0] = sz[0]; imsize[1] = sz[1]; imsize[2] = sz[2];
 	}
@@ -263,7 +283,7 @@ void readtifstack_16to16(unsigned short *h_Image, char *tifdir, unsigned int *im
 	}
 	unsigned int sz[3];
 	const unsigned short bits = gettifinfo(tifdir, sz);
-	if (bits == 16) read_pages<uint16_t>(tifdir, h_Image, imsize, 16);
+	if (bits == 16) read_pages<uint16_t>(tifdir, h_Image, imsize, 16, sz[2]);
 	else {
 		imsize[0] = sz[0]; imsize[1] = sz[1]; imsize[2] = sz[2];
 		printf("Image bit per sample is not supported, please set input image as 16 bit!!!\n\n");

@@ -1,5 +1,7 @@
 """TIFF stack I/O of libapi (csrc/tiff_io.cpp, host only): round trips, the reference's pixel
 conversion rules (src/apifunc.cpp:171-175, :255) and interoperability with libtiff via Pillow."""
+import os
+
 import numpy as np
 import pytest
 
@@ -68,3 +70,47 @@ def test_pillow_reads_what_we_write_and_vice_versa(tmp_path):
     pages[0].save(q, save_all=True, append_images=pages[1:], compression=None)
     assert libapi.gettifinfo(q) == (16, (8, 6, 4))
     assert np.array_equal(libapi.readtifstack(q), vol.astype(np.uint16).astype(np.float32))
+
+
+def _run_reader(path):
+    """readtifstack in a child process (the library follows the reference's convention: errors print and exit(1))"""
+    import subprocess
+    import sys
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from microimagelib_b200 import libapi\n"
+            "v = libapi.readtifstack(%r)\n"
+            "print('READ', v.shape)\n") % (os.path.dirname(os.path.dirname(os.path.abspath(__file__))), str(path))
+    return subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120)
+
+
+def test_reader_rejects_inconsistent_and_cyclic_stacks(tmp_path):
+    """A stack whose pages differ in size, or whose directory chain loops, is refused before anything is copied."""
+    from PIL import Image
+    from microimagelib_b200 import libapi
+    good = tmp_path / "good.tif"
+    vol = (np.arange(3 * 6 * 8).reshape(3, 6, 8) % 200).astype(np.float32)
+    libapi.writetifstack(good, vol, 16)
+    r = _run_reader(good)
+    assert r.returncode == 0 and "READ (3, 6, 8)" in r.stdout
+    # pages of different sizes (written by Pillow)
+    bad = tmp_path / "ragged.tif"
+    pages = [Image.fromarray(np.zeros((6, 8), np.uint16)), Image.fromarray(np.zeros((7, 9), np.uint16))]
+    pages[0].save(bad, save_all=True, append_images=pages[1:], compression=None)
+    r = _run_reader(bad)
+    assert r.returncode != 0 and "differ" in (r.stdout + r.stderr)
+    # a directory chain that points back to the first directory
+    raw = bytearray(open(good, "rb").read())
+    first = int.from_bytes(raw[4:8], "little")
+    off = first
+    while True:
+        n = int.from_bytes(raw[off:off + 2], "little")
+        nxt_at = off + 2 + 12 * n
+        nxt = int.from_bytes(raw[nxt_at:nxt_at + 4], "little")
+        if nxt == 0:
+            raw[nxt_at:nxt_at + 4] = first.to_bytes(4, "little")
+            break
+        off = nxt
+    cyc = tmp_path / "cyclic.tif"
+    open(cyc, "wb").write(bytes(raw))
+    r = _run_reader(cyc)
+    assert r.returncode != 0
