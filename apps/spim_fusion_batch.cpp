@@ -163,6 +163,7 @@ int main(int argc, char **argv)
 	ReadAhead ahead;     // next time point's input stacks (io_pipeline.h)
 	WriteBehind behind;  // output stacks written while the next time point is processed
 
+	const double tSetup = whole.s();
 	for (int num = numStart; num <= numEnd; num += numStep) {
 		if (regMode == 0) rs.regChoice = 0;
 		else if (regMode == 1) num = numTest; // the test image provides the matrix for all others
@@ -340,7 +341,9 @@ int main(int argc, char **argv)
 		printf("\tTime cost for  projections and output hand-off: %2.3f s\n", tPoint.s() - tAfterDecon);
 		printf("...Time cost for current image is %2.3f s\n", tPoint.s());
 	}
+	const double tLoop = whole.s();
 	behind.drain();
+	printf("Time cost for set-up: %2.3f s, time points: %2.3f s, waiting for the writers: %2.3f s\n", tSetup, tLoop - tSetup, whole.s() - tLoop);
 	printf("Total time cost for whole processing is %2.3f s\n", whole.s());
 	return 0;
 }

@@ -20,7 +20,7 @@ BUILD = os.path.join(HERE, "build")
 LIBDIR = os.path.join(HERE, "lib")
 LIB = os.path.join(LIBDIR, "libapi.so")
 
-SOURCES = ["decon.cu", "decon_fast.cu", "decon_fast_n64.cu", "decon_fast_n128.cu", "decon_fast_n256.cu", "decon_fast_n512.cu", "decon_fast_n1024.cu", "dslab.cu", "reg.cu", "prealign.cu", "geom.cu", "yardstick.cu", "reg_driver.cpp", "powell.cpp", "libapi.cpp", "tiff_io.cpp"]
+SOURCES = ["decon.cu", "decon_fast.cu", "decon_fast_n64.cu", "decon_fast_n128.cu", "decon_fast_n256.cu", "decon_fast_n512.cu", "decon_fast_n1024.cu", "decon_fast_n192.cu", "decon_fast_n320.cu", "decon_fast_n384.cu", "decon_fast_n448.cu", "decon_fast_n576.cu", "decon_fast_n640.cu", "decon_fast_n768.cu", "dslab.cu", "reg.cu", "prealign.cu", "geom.cu", "yardstick.cu", "reg_driver.cpp", "powell.cpp", "libapi.cpp", "tiff_io.cpp"]
 
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]

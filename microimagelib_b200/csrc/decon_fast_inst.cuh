@@ -6,7 +6,9 @@
 namespace {
 constexpr int N = MILB_FAST_N;
 constexpr int T = 512;
-constexpr int L = 4096 / N;
+constexpr bool kPow2 = (N & (N - 1)) == 0;
+constexpr int pow2_floor(int v) { int p = 1; while (2 * p <= v) p *= 2; return p; }
+constexpr int L = pow2_floor(4096 / N); // pencils per 4096-point tile (a power of two also for the 64*k lengths)
 // plane passes: tile of PL pencils, PT threads.  The wide tile (8192 points, one CTA per SM) gives
 // 128-byte global rows at N = 512; measured 9 % faster per iteration than 4096-point tiles at
 // 2 CTAs/SM.  PL must not exceed the shortest possible row (64).
@@ -44,7 +46,7 @@ constexpr int TXF = (N / R0) * L;                   // threads of the non-persis
 #define MILB_X_WIDE512 1
 #endif
 constexpr bool kXWide = MILB_X_WIDE || (MILB_X_WIDE512 && N == 512);
-constexpr int XL = (kXWide ? 8192 : kXNarrow ? 2048 : 4096) / N, XT = (N / R0) * XL;
+constexpr int XL = pow2_floor((kXWide ? 8192 : kXNarrow ? 2048 : 4096) / N), XT = (N / R0) * XL;
 constexpr int XCTAS = xpassP_ctas<N, XL, XT>();
 constexpr size_t SMX = (size_t)(2 * N * XL + 2 * (N / 2 + 1) * XL + N) * sizeof(float2);
 int g_ctas = 0, g_sms = 0; // persistent grids
@@ -53,7 +55,7 @@ int g_cap = 0;              // override (FastAxisOps::grid_cap)
 inline int plane_grid(int tiles) { const int c = (g_cap > 0 && g_cap < g_ctas) ? g_cap : g_ctas; return tiles < c ? tiles : c; }
 
 // ---- tensor maps for the TMA tile loads (driver entry point fetched at run time: no -lcuda) ----------
-constexpr bool kTmaTiles = (PL > 8); // dense shared rows
+constexpr bool kTmaTiles = (PL > 8) && kPow2; // dense shared rows; the tile box is min(N, 256) rows and must divide N
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
 	const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn g_encode = nullptr;
@@ -86,19 +88,23 @@ int setup()
 	bad |= optin(k_xpassP<N, XL, XT, XF_RATIO>, SMX);
 	bad |= optin(k_xpassP<N, XL, XT, XF_UPDATE>, SMX);
 	bad |= optin(k_xpassP<N, XL, XT, XF_UPDATE_LAST>, SMX);
-	bad |= optin(k_xpassF<N, L, TXF, XF_FWD_REAL, true>, SM1);
-	bad |= optin(k_xpassP<N, XL, XT, XF_RATIO, true>, SMX);
-	bad |= optin(k_xpassP<N, XL, XT, XF_UPDATE, true>, SMX);
-	bad |= optin(k_ypassF<N, PL, PT, true, true>, SMP2);
+	if constexpr (kPow2) { // the distributed (peer-store) variants exist for the power-of-two lengths only
+		bad |= optin(k_xpassF<N, L, TXF, XF_FWD_REAL, true>, SM1);
+		bad |= optin(k_xpassP<N, XL, XT, XF_RATIO, true>, SMX);
+		bad |= optin(k_xpassP<N, XL, XT, XF_UPDATE, true>, SMX);
+		bad |= optin(k_ypassF<N, PL, PT, true, true>, SMP2);
+	}
 	bad |= optin(k_ypassT<N, PL, PT>, SMP3);
 	bad |= optin(k_ypassF<N, PL, PT, true>, SMP2);
 	bad |= optin(k_zconvT<N, PL, PT, true>, SMP3);
 	bad |= optin(k_zconvT<N, PL, PT, false>, SMP3);
-	bad |= optin(k_planes_fused<N, PL, PT>, SMP3);
 	g_fused_ctas = 0;
-	if (!bad) {
-		int per_sm = 0;
-		if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_planes_fused<N, PL, PT>, PT, SMP3) == cudaSuccess) g_fused_per_sm = per_sm;
+	if constexpr (kPow2) {
+		bad |= optin(k_planes_fused<N, PL, PT>, SMP3);
+		if (!bad) {
+			int per_sm = 0;
+			if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_planes_fused<N, PL, PT>, PT, SMP3) == cudaSuccess) g_fused_per_sm = per_sm;
+		}
 	}
 	if constexpr (kTmaTiles) {
 		bad |= optin(k_ypassF<N, PL, PT, true, false, true>, SMP2);
@@ -143,6 +149,7 @@ void xpass(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const floa
 // distributed variants: the output spectrum is stored into the owning ranks' buffers (peer memory)
 void xpass_peer(int mode, float2 *vol_io, const float2 *aux, const float4 *spec, const float2 *tw, long long M, const PeerMap *pm, cudaStream_t st)
 {
+	if constexpr (kPow2) {
 	float4 *sp = const_cast<float4 *>(spec);
 	if (mode == XF_FWD_REAL) {
 		k_xpassF<N, L, TXF, XF_FWD_REAL, true><<<(unsigned)(M / L), TXF, SM1, st>>>(vol_io, aux, sp, tw, M, *pm);
@@ -152,10 +159,12 @@ void xpass_peer(int mode, float2 *vol_io, const float2 *aux, const float4 *spec,
 	if (mode == XF_RATIO) k_xpassP<N, XL, XT, XF_RATIO, true><<<grid, XT, SMX, st>>>(vol_io, aux, sp, tw, M, ntiles, *pm);
 	else if (mode == XF_UPDATE) k_xpassP<N, XL, XT, XF_UPDATE, true><<<grid, XT, SMX, st>>>(vol_io, aux, sp, tw, M, ntiles, *pm);
 	else k_xpassP<N, XL, XT, XF_UPDATE_LAST><<<grid, XT, SMX, st>>>(vol_io, aux, sp, tw, M, ntiles); // no spectrum output
+	}
 }
 
 void pass_inv_peer(const float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, const PeerMap *pm, cudaStream_t st)
 {
+	if constexpr (kPow2) {
 	const int tiles = (cols / PL) * nplanes;
 	if constexpr (kTmaTiles) {
 		TileMap tm;
@@ -165,6 +174,7 @@ void pass_inv_peer(const float2 *spec, const float2 *tw, int cols, int plane0, i
 		}
 	}
 	k_ypassF<N, PL, PT, true, true><<<plane_grid(tiles), PT, SMP2, st>>>(const_cast<float2 *>(spec), tw, cols, plane0, nplanes, *pm);
+	}
 }
 
 void passT(const float2 *in, float2 *out, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
@@ -194,6 +204,8 @@ void convT(float2 *in, float2 *out, const float2 *otf, const float2 *tw, int col
 
 bool planes_fused(float2 *S, const float2 *otf, const float2 *tw, PlaneFuse *pf, cudaStream_t st)
 {
+	if constexpr (!kPow2) return false;
+	else {
 	if (g_fused_ctas < 3 || !pf || !pf->ring || !pf->counters) return false;
 	constexpr int TPP = N / PL;
 	const int cap = (g_cap > 0 && g_cap < g_fused_ctas) ? g_cap : g_fused_ctas;
@@ -216,6 +228,7 @@ bool planes_fused(float2 *S, const float2 *otf, const float2 *tw, PlaneFuse *pf,
 	sc.nB = nB;
 	k_planes_fused<N, PL, PT><<<grid, PT, SMP3, st>>>(S, pf->ring, otf, tw, sc);
 	return true;
+	}
 }
 
 void fwd_scaled(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, float scale, cudaStream_t st)
@@ -231,6 +244,7 @@ const FastAxisOps *MILB_CAT(milb_fast_ops_, MILB_FAST_N)()
 {
 	static FastAxisOps ops;
 	ops.n = N; ops.lanes = L; ops.xlanes = XL > L ? XL : L; ops.setup = setup; ops.xpass = xpass; ops.passT = passT; ops.pass_inv = pass_inv;
-	ops.convT = convT; ops.fwd_scaled = fwd_scaled; ops.planes_fused = planes_fused; ops.xpass_peer = xpass_peer; ops.pass_inv_peer = pass_inv_peer; ops.grid_cap = &g_cap;
+	ops.convT = convT; ops.fwd_scaled = fwd_scaled; ops.planes_fused = kPow2 ? planes_fused : nullptr;
+	ops.xpass_peer = kPow2 ? xpass_peer : nullptr; ops.pass_inv_peer = kPow2 ? pass_inv_peer : nullptr; ops.grid_cap = &g_cap;
 	return &ops;
 }

@@ -44,7 +44,7 @@ extern "C" int milb_dslab_create(milb_dslab_t **out, const unsigned int *fftSize
 	if (!out || !fftSize || ny <= 0 || y0 < 0 || planes_local < 0) return MILB_ERR_ARG;
 	const int Z = (int)fftSize[0], Y = (int)fftSize[1], X = (int)fftSize[2];
 	const FastAxisOps *fx = milb_fast_ops(X), *fy = milb_fast_ops(Y), *fz = milb_fast_ops(Z);
-	if (!fx || !fy || !fz) return MILB_ERR_SIZE; // the distributed path uses the power-of-two kernels only
+	if (!fx || !fy || !fz || !fx->xpass_peer || !fy->pass_inv_peer) return MILB_ERR_SIZE; // the distributed path uses the power-of-two kernels only
 	if (y0 + ny > Y || ((long long)ny * Z / 2) % 64 != 0 || planes_local > X / 2 + 1) return MILB_ERR_ARG;
 	if (fx->setup() || fy->setup() || fz->setup()) return MILB_ERR_CUDA;
 	milb_dslab *h = new milb_dslab();

@@ -159,6 +159,58 @@ template <bool INV> MILB_HD void bfly32(float2 *v)
 	}
 }
 
+// ---- odd radices in registers (closed forms, constants instead of table look-ups): the last stage of the compile-time
+// plans for the 64*k lengths snapTransformSize produces (192 = 8*8*3, 320 = 8*8*5, 448 = 8*8*7, ...) ----------------------
+template <bool INV> MILB_HD void bfly3(float2 *v)
+{
+	const float s = 0.86602540378443864676f; // sin(2 pi / 3)
+	const float2 t1 = cadd(v[1], v[2]);
+	const float2 t2 = csub(v[0], cscale(t1, 0.5f));
+	const float2 t3 = mul_mi<INV>(cscale(csub(v[1], v[2]), s));
+	v[0] = cadd(v[0], t1);
+	v[1] = cadd(t2, t3);
+	v[2] = csub(t2, t3);
+}
+
+template <bool INV> MILB_HD void bfly5(float2 *v)
+{
+	const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f; // cos(2 pi / 5), cos(4 pi / 5)
+	const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;  // sin(2 pi / 5), sin(4 pi / 5)
+	const float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]), t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+	const float2 a = v[0];
+	const float2 m1 = cadd(a, cadd(cscale(t1, c1), cscale(t2, c2)));
+	const float2 m2 = cadd(a, cadd(cscale(t1, c2), cscale(t2, c1)));
+	const float2 n1 = mul_mi<INV>(cadd(cscale(t3, s1), cscale(t4, s2)));
+	const float2 n2 = mul_mi<INV>(csub(cscale(t3, s2), cscale(t4, s1)));
+	v[0] = cadd(a, cadd(t1, t2));
+	v[1] = cadd(m1, n1);
+	v[4] = csub(m1, n1);
+	v[2] = cadd(m2, n2);
+	v[3] = csub(m2, n2);
+}
+
+template <bool INV> MILB_HD void bfly7(float2 *v)
+{
+	const float c1 = 0.62348980185873353053f, c2 = -0.22252093395631440429f, c3 = -0.90096886790241912624f; // cos(2 pi k / 7)
+	const float s1 = 0.78183148246802980871f, s2 = 0.97492791218182360702f, s3 = 0.43388373911755812048f;  // sin(2 pi k / 7)
+	const float2 t1 = cadd(v[1], v[6]), t2 = cadd(v[2], v[5]), t3 = cadd(v[3], v[4]);
+	const float2 u1 = csub(v[1], v[6]), u2 = csub(v[2], v[5]), u3 = csub(v[3], v[4]);
+	const float2 a = v[0];
+	const float2 m1 = cadd(a, cadd(cscale(t1, c1), cadd(cscale(t2, c2), cscale(t3, c3))));
+	const float2 m2 = cadd(a, cadd(cscale(t1, c2), cadd(cscale(t2, c3), cscale(t3, c1))));
+	const float2 m3 = cadd(a, cadd(cscale(t1, c3), cadd(cscale(t2, c1), cscale(t3, c2))));
+	const float2 n1 = mul_mi<INV>(cadd(cscale(u1, s1), cadd(cscale(u2, s2), cscale(u3, s3))));
+	const float2 n2 = mul_mi<INV>(csub(cscale(u1, s2), cadd(cscale(u2, s3), cscale(u3, s1))));
+	const float2 n3 = mul_mi<INV>(cadd(csub(cscale(u1, s3), cscale(u2, s1)), cscale(u3, s2)));
+	v[0] = cadd(a, cadd(t1, cadd(t2, t3)));
+	v[1] = cadd(m1, n1);
+	v[6] = csub(m1, n1);
+	v[2] = cadd(m2, n2);
+	v[5] = csub(m2, n2);
+	v[3] = cadd(m3, n3);
+	v[4] = csub(m3, n3);
+}
+
 // naive length-r DFT using the axis twiddle table (r divides n): w_r^t = tw[t * (n / r)]
 template <bool INV> MILB_HD void bfly_generic(float2 *v, int r, const float2 *tw, int n)
 {

@@ -1,4 +1,6 @@
-// Power-of-two fast path of the pencil FFT passes (N in {64,128,256,512,1024} per axis).
+// Compile-time fast path of the pencil FFT passes: N in {64,128,256,512,1024} per axis, plus the 64*k lengths
+// snapTransformSize really produces for non-power-of-two images {192,320,384,448,576,640,768} (an odd radix 3 / 5 / 7 as the
+// LAST stage, power-of-two radices before it).
 //
 // Same algorithm and the same position-order spectrum as the generic engine (fft_core.h), but
 // with compile-time lengths and radices (FastPlan<N>: 8x8, 8x16, 16x16, 16x32, 8x8x4x4): every
@@ -76,6 +78,16 @@ MILB_FAST_PLAN(1024, 3, 8, 16, 8, 1)
 MILB_FAST_PLAN(1024, 4, 8, 8, 4, 4)
 #endif
 
+// 64*k lengths (src/api_subfunc.cu:79-86: 300 -> 320, 400 -> 448, 600 -> 640, ...): the odd factor is the last stage, so the
+// register-fused first stage of the X pass and the twiddled stages stay power-of-two radices
+MILB_FAST_PLAN(192, 3, 8, 8, 3, 1)
+MILB_FAST_PLAN(320, 3, 8, 8, 5, 1)
+MILB_FAST_PLAN(384, 3, 8, 16, 3, 1)
+MILB_FAST_PLAN(448, 3, 8, 8, 7, 1)
+MILB_FAST_PLAN(576, 4, 8, 8, 3, 3)
+MILB_FAST_PLAN(640, 3, 8, 16, 5, 1)
+MILB_FAST_PLAN(768, 3, 16, 16, 3, 1)
+
 // position of frequency k after the forward stages (same rule as AxisPlanTables::pos)
 template <int N> __device__ __forceinline__ int fast_pos(int k)
 {
@@ -92,6 +104,9 @@ template <int N> __device__ __forceinline__ int fast_pos(int k)
 template <int R, bool INV> __device__ __forceinline__ void fbfly(float2 (&v)[R])
 {
 	if constexpr (R == 2) bfly2<INV>(v[0], v[1]);
+	else if constexpr (R == 3) bfly3<INV>(v);
+	else if constexpr (R == 5) bfly5<INV>(v);
+	else if constexpr (R == 7) bfly7<INV>(v);
 	else if constexpr (R == 4) bfly4<INV>(v[0], v[1], v[2], v[3]);
 	else if constexpr (R == 8) bfly8<INV>(v);
 	else if constexpr (R == 32) bfly32<INV>(v);

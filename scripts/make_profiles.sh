@@ -2,7 +2,8 @@
 # Round profile artefacts (run under gpurun, one GPU): ncu launch list of a short RL run and a full
 # capture of one RL iteration's kernels.  Raw reports land in gpurun_out/, summaries in profiles/.
 cd "$(dirname "$0")/.."
-TAG=${1:-r01}
+TAG=${1:-r02}
+export PROBE_SHAPE=${PROBE_SHAPE:-512,512,512}   # the metric's own configuration
 mkdir -p gpurun_out profiles
 export PROBE_ITERS=3
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python scripts/prof_run.py > gpurun_out/launches_$TAG.log 2>&1
@@ -23,5 +24,5 @@ r = device.Reg(shape); r.set_images(t, t); r.prepare()
 for _ in range(3): r.cost(m)
 torch.cuda.synchronize()
 PY
-ncu --set full --clock-control none --import-source on -k regex:k_zncc -s 2 -c 1 -o gpurun_out/prof_zncc_$TAG -f python /tmp/prof_reg.py > gpurun_out/prof_zncc_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'^k_zncc$' --kernel-name-base function -s 2 -c 1 -o gpurun_out/prof_zncc_$TAG -f python /tmp/prof_reg.py > gpurun_out/prof_zncc_$TAG.log 2>&1
 ls -la gpurun_out/*$TAG*

@@ -8,7 +8,8 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-tag = sys.argv[1] if len(sys.argv) > 1 else "r01"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r02"
+shape = os.environ.get("PROBE_SHAPE", "512,512,512")
 out = os.path.join(ROOT, "profiles")
 os.makedirs(out, exist_ok=True)
 go = os.path.join(ROOT, "gpurun_out")
@@ -27,7 +28,7 @@ for row in csv.DictReader(lines):
     a[1] += v
 tot = sum(a[1] for a in agg.values())
 with open(os.path.join(out, f"{tag}_launches.txt"), "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: 3 RL iterations at 512x512x256 incl. OTF preparation\n")
+    f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none: 3 RL iterations at {shape} (slices,H,W) incl. OTF preparation\n")
     f.write("# cold-cache, serialised per-launch times: compare SHARES, not absolutes (scripts/make_profiles.sh)\n")
     f.write(f"{'kernel':60s} {'n':>5s} {'total us':>10s} {'avg us':>9s} {'share':>7s}\n")
     for k, (n, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
@@ -73,7 +74,7 @@ for rep, label in ((f"prof_{tag}.ncu-rep", "rl_iteration"), (f"prof_zncc_{tag}.n
         traffic["kernels"] = [{"kernel": p[0][:40], "dram_bytes": p[1], "us_under_ncu": p[2]} for p in per[:8]]
     else:
         traffic["zncc_dram_bytes_per_evaluation"] = per[0][1]
-traffic["source"] = f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, {tag}; 512x512x256 single view"
+traffic["source"] = f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum, {tag}; {shape} (slices,H,W) single view; zncc at 512x512x256"
 json.dump(traffic, open(os.path.join(out, "traffic.json"), "w"), indent=1)
 print(open(os.path.join(out, f"{tag}_launches.txt")).read())
 print(json.dumps(traffic, indent=1)[:1500])

@@ -18,6 +18,17 @@ int emul_plane_dependency(int phase, int plane, int ring, int *dep_plane)
 	return plane_dependency(w, ring, dep_plane);
 }
 
+// the closed-form odd-radix register butterflies (bfly3 / bfly5 / bfly7): in-place DFT of r complex values
+int emul_bfly_odd(int r, float *data /* r complex */, int inverse)
+{
+	float2 *v = (float2 *)data;
+	if (r == 3) { if (inverse) bfly3<true>(v); else bfly3<false>(v); }
+	else if (r == 5) { if (inverse) bfly5<true>(v); else bfly5<false>(v); }
+	else if (r == 7) { if (inverse) bfly7<true>(v); else bfly7<false>(v); }
+	else return -1;
+	return 0;
+}
+
 int emul_plan(int n, int *radix, int *pos)
 {
 	AxisPlanTables t;

@@ -75,3 +75,15 @@ def test_register_butterflies_are_dfts(lib, r):
         assert lib.emul_bfly(r, d.ctypes.data_as(F), inverse) == 0
         ref = np.fft.ifft(x.astype(np.complex128)) * r if inverse else np.fft.fft(x.astype(np.complex128))
         assert np.linalg.norm(d - ref) / np.linalg.norm(ref) < 3e-7
+
+
+@pytest.mark.parametrize("r", [3, 5, 7])
+def test_odd_radix_register_butterflies(lib, r):
+    """bfly3 / bfly5 / bfly7 (closed forms with constants, the last stage of the 64*k fast plans) == numpy's DFT"""
+    rng = np.random.default_rng(r)
+    for inverse in (0, 1):
+        x = (rng.standard_normal(r) + 1j * rng.standard_normal(r)).astype(np.complex64)
+        d = x.copy()
+        assert lib.emul_bfly_odd(r, d.ctypes.data_as(F), inverse) == 0
+        ref = np.fft.ifft(x.astype(np.complex128)) * r if inverse else np.fft.fft(x.astype(np.complex128))
+        assert np.abs(d - ref).max() <= 1e-6 * np.abs(ref).max()

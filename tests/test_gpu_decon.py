@@ -135,10 +135,16 @@ def test_device_resident_handle_matches_host_api():
     d.close()
 
 
-@pytest.mark.parametrize("shape", [(64, 128, 256), (256, 64, 128), (128, 512, 64), (64, 64, 1024), (512, 64, 128), (1024, 64, 64), (128, 256, 512)])
+FAST_SHAPES = [(64, 128, 256), (256, 64, 128), (128, 512, 64), (64, 64, 1024), (512, 64, 128), (1024, 64, 64), (128, 256, 512),
+               # the 64*k lengths of the compile-time plans, each in every axis role (X pencils / Y planes / Z planes)
+               (192, 320, 64), (320, 64, 192), (64, 192, 320), (384, 448, 64), (448, 64, 384), (64, 384, 448),
+               (576, 64, 640), (64, 640, 576), (640, 576, 64), (768, 64, 192), (64, 768, 128), (128, 64, 768)]
+
+
+@pytest.mark.parametrize("shape", FAST_SHAPES)
 def test_fast_pow2_path_matches_generic_path(shape, monkeypatch):
-    """The power-of-two fast kernels (fft_fast.cuh) and the generic mixed-radix kernels
-    (fft_kernels.cuh) are independent implementations of the same loop."""
+    """The compile-time fast kernels (fft_fast.cuh: power-of-two lengths and the 64*k lengths 192 ... 768) and the
+    generic mixed-radix kernels (fft_kernels.cuh) are independent implementations of the same loop."""
     from microimagelib_b200 import device
     psf = synth.gaussian_psf((17, 17, 17), (2.5, 2.0, 1.5))
     img = synth.bead_image(shape, psf, density=1 / 4096.0)
@@ -157,6 +163,19 @@ def test_fast_pow2_path_matches_generic_path(shape, monkeypatch):
                 assert np.array_equal(d.result(), outs["fast"])
         d.close()
     assert rel_l2(outs["fast"], outs["generic"]) <= 2e-6
+
+
+def test_non_pow2_fast_box_against_the_oracle():
+    """A box as snapTransformSize really produces it (300 x 400 x 90 image -> 320 x 448 x 96... here 320 x 448 x 192): the
+    compile-time 64*k plans against the CPU oracle, padding and cropping included."""
+    from microimagelib_b200 import libapi
+    from oracle import decon_oracle as do
+    psf = synth.gaussian_psf((17, 17, 17), (2.0, 2.0, 2.5))
+    img = synth.bead_image((180, 400, 300), psf, density=1 / 4096.0)
+    assert do.fft_shape_for(img.shape) == (192, 448, 320)
+    got, st, _ = libapi.decon_singleview(img, psf, 5)
+    ref = do.decon_singleview(img, psf, 5)
+    assert st == 0 and rel_l2(got, ref) <= 1e-4
 
 
 def test_edge_inputs_zero_iterations_clamp_and_padded_dualview():
