@@ -47,8 +47,10 @@ __global__ void __launch_bounds__(256) k_affine_warp(float *__restrict__ out, co
 // is the very float the reference's tex3D returns, and the eight gathers + fixed-point weights leave the SM's issue slots.
 // HW = false: the software restatement of that fetch (tex_sw.cuh), bit-identical to the CPU oracle; kept as the parity twin.
 #define REG_ZT 8
+// occupancy: the texture path is latency-bound (ncu: long-scoreboard stalls dominate), so the single-candidate variant is
+// held to 32 registers (8 CTAs = 64 warps per SM)
 template <int K, bool HW>
-__global__ void __launch_bounds__(256) k_zncc(const float *__restrict__ tgt, const float *__restrict__ src, cudaTextureObject_t tex, int sx, int sy, int sz,
+__global__ void __launch_bounds__(256, (HW && K == 1) ? 8 : 1) k_zncc(const float *__restrict__ tgt, const float *__restrict__ src, cudaTextureObject_t tex, int sx, int sy, int sz,
 	AffBatch aff, double *__restrict__ partial /* [gridDim.x][K][2] */)
 {
 	__shared__ double sh[8][K][2];
