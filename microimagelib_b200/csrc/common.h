@@ -40,3 +40,18 @@ int milb_snap_transform_size(int n);
 #define MILB_REDUCE_BLOCKS 592 // 4 x 148 SMs
 int milb_sum_f64_async(const float *d_in, long long n, double *d_scratch, double *d_out, cudaStream_t st);
 int milb_sumsq_f64_async(const float *d_in, long long n, double *d_scratch, double *d_out, cudaStream_t st);
+
+// Stream-ordered device allocations from the current device's default pool with its release threshold lifted (set once
+// per device): the malloc / free pairs the reference's call structure implies cost microseconds after the first call.
+int milb_pool_alloc(void **out, size_t bytes);
+void milb_pool_free(void *p);
+
+// How trilinear samples of a source volume are taken by the warp / cost / rotating-projection kernels:
+//   true  (default) the hardware texture unit on a cudaArray copy of the source -- the reference's own mechanism, the very
+//                   float its tex3D returns;
+//   false           the software restatement of that fetch (tex_sw.cuh), bit-identical to the CPU oracle.
+// MILB_TEX_FETCH=sw (or the older MILB_ZNCC_FETCH=sw) selects the software twin; read at every call.
+bool milb_fetch_hardware();
+// texture object {linear, clamp, un-normalised} over a cudaArray copy of a device-resident float volume (per-thread cache by
+// extent; valid until the next call with the same extent on this thread) -- reg.cu
+int milb_source_texture(const float *d_src, int sx, int sy, int sz, cudaStream_t st, cudaTextureObject_t *tex);

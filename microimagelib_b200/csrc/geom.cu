@@ -177,8 +177,9 @@ int milb_warp_u16_dev(unsigned short *d_out, const unsigned short *d_src, int sx
 struct AffMany {
 	float m[64][12];
 };
-__global__ void __launch_bounds__(256) k_rot_mip(float *__restrict__ out, const float *__restrict__ src, int so0, int so1, int so2, int sx, int sy, int sz,
-	AffMany aff, int first)
+template <bool HW>
+__global__ void __launch_bounds__(256) k_rot_mip(float *__restrict__ out, const float *__restrict__ src, cudaTextureObject_t tex, int so0, int so1, int so2,
+	int sx, int sy, int sz, AffMany aff, int first)
 {
 	const int p = blockIdx.y;
 	const float *a = aff.m[p];
@@ -192,7 +193,9 @@ __global__ void __launch_bounds__(256) k_rot_mip(float *__restrict__ out, const 
 			const float fz = (float)z;
 			const float tx = aff_coord(a + 0, fx, fy, fz), ty = aff_coord(a + 4, fx, fy, fz), tz = aff_coord(a + 8, fx, fy, fz);
 			if (tx >= 0 && tx < fsx && ty >= 0 && ty < fsy && tz >= 0 && tz < fsz) {
-				const float v = tex3d_linear(src, sx, sy, sz, tx, ty, tz);
+				float v;
+				if constexpr (HW) v = tex3D<float>(tex, tx, ty, tz);
+				else v = tex3d_linear(src, sx, sy, sz, tx, ty, tz);
 				best = (best > v) ? best : v;
 			}
 		}
@@ -208,12 +211,19 @@ int milb_rot_mip_dev(float *d_out, const float *d_src, const unsigned int *sizeR
 	const long long npix = (long long)sizeRot[0] * sizeRot[1];
 	long long bx = cdiv_ll(npix, 256);
 	if (bx > 148 * 4) bx = 148 * 4;
+	const bool hw = milb_fetch_hardware();
+	cudaTextureObject_t tex = 0;
+	if (hw) MILB_TRY(milb_source_texture(d_src, sizeSrc[0], sizeSrc[1], sizeSrc[2], st, &tex));
 	for (int first = 0; first < nproj; first += 64) {
 		const int cnt = nproj - first < 64 ? nproj - first : 64;
 		AffMany am;
 		memcpy(am.m, matrices + 12ll * first, sizeof(float) * 12 * cnt);
-		k_rot_mip<<<dim3((unsigned)bx, cnt), 256, 0, st>>>(d_out, d_src, sizeRot[0], sizeRot[1], sizeRot[2], sizeSrc[0], sizeSrc[1], sizeSrc[2], am,
-			first);
+		if (hw)
+			k_rot_mip<true><<<dim3((unsigned)bx, cnt), 256, 0, st>>>(d_out, d_src, tex, sizeRot[0], sizeRot[1], sizeRot[2], sizeSrc[0], sizeSrc[1], sizeSrc[2],
+				am, first);
+		else
+			k_rot_mip<false><<<dim3((unsigned)bx, cnt), 256, 0, st>>>(d_out, d_src, 0, sizeRot[0], sizeRot[1], sizeRot[2], sizeSrc[0], sizeSrc[1], sizeSrc[2],
+				am, first);
 		milb_count_launches(1);
 	}
 	MILB_CUDA_TRY(cudaGetLastError());

@@ -61,29 +61,11 @@ bool on_device(const void *p)
 // that the per-call malloc / free pairs of this layer (the reference's structure) cost microseconds after the first call.
 void *tmp_alloc(size_t bytes, const char *what = "****Memory allocating fails... GPU out of memory !!!!*****")
 {
-	static std::mutex mu;
-	static bool tuned[64] = {false};
-	int dev = 0;
-	cudaGetDevice(&dev);
-	{
-		std::lock_guard<std::mutex> lk(mu);
-		if (dev >= 0 && dev < 64 && !tuned[dev]) {
-			cudaMemPool_t pool;
-			if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-				unsigned long long keep = ~0ull;
-				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-			}
-			tuned[dev] = true;
-		}
-	}
 	void *p = nullptr;
-	cuda_fatal(cudaMallocAsync(&p, bytes ? bytes : 1, 0), what);
+	fatal_if(milb_pool_alloc(&p, bytes), what);
 	return p;
 }
-void tmp_free(void *p)
-{
-	if (p) cudaFreeAsync(p, 0);
-}
+void tmp_free(void *p) { milb_pool_free(p); }
 
 // device view of an input volume: the caller's own memory when that is device memory, else an uploaded copy
 template <class T> struct DevIn {

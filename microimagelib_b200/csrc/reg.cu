@@ -15,12 +15,113 @@
 
 #define MILB_REG_MAXK 8
 
+#include <mutex>
+
+int milb_pool_alloc(void **out, size_t bytes)
+{
+	static std::mutex mu;
+	static bool tuned[64] = {false};
+	int dev = 0;
+	cudaGetDevice(&dev);
+	{
+		std::lock_guard<std::mutex> lk(mu);
+		if (dev >= 0 && dev < 64 && !tuned[dev]) {
+			cudaMemPool_t pool;
+			if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+				unsigned long long keep = ~0ull;
+				cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+			}
+			tuned[dev] = true;
+		}
+	}
+	MILB_CUDA_TRY(cudaMallocAsync(out, bytes ? bytes : 1, 0));
+	return MILB_OK;
+}
+void milb_pool_free(void *p)
+{
+	if (p) cudaFreeAsync(p, 0);
+}
+
+bool milb_fetch_hardware()
+{
+	const char *e = getenv("MILB_TEX_FETCH");
+	if (!e) e = getenv("MILB_ZNCC_FETCH");
+	return !(e && (e[0] == 's' || e[0] == '0'));
+}
+
+// A source volume as a 3-D cudaArray behind a {linear filter, clamp, un-normalised coordinates} texture object -- what the
+// reference binds before every warp (cudacopydevicetoarray + BindTexture, src/api_subfunc.cu:868-895).  One array per thread
+// is kept between calls and re-used while the extent matches (the batch app warps a volume of the same size per time point).
+struct SourceTexture {
+	cudaArray_t arr = nullptr;
+	cudaTextureObject_t tex = 0;
+	int sx = 0, sy = 0, sz = 0, dev = -1;
+	void drop()
+	{
+		if (tex) cudaDestroyTextureObject(tex);
+		if (arr) cudaFreeArray(arr);
+		tex = 0;
+		arr = nullptr;
+	}
+	~SourceTexture() {} // freed with the context: a thread-exit destructor may run after the driver has shut down
+	int bind(const float *d_src, int x, int y, int z, cudaStream_t st)
+	{
+		int cur = 0;
+		cudaGetDevice(&cur);
+		if (!arr || x != sx || y != sy || z != sz || cur != dev) {
+			if (dev == cur) drop();
+			else { tex = 0; arr = nullptr; }
+			cudaChannelFormatDesc desc = cudaCreateChannelDesc<float>();
+			MILB_CUDA_TRY(cudaMalloc3DArray(&arr, &desc, make_cudaExtent(x, y, z)));
+			cudaResourceDesc rd;
+			memset(&rd, 0, sizeof rd);
+			rd.resType = cudaResourceTypeArray;
+			rd.res.array.array = arr;
+			cudaTextureDesc td;
+			memset(&td, 0, sizeof td);
+			td.addressMode[0] = td.addressMode[1] = td.addressMode[2] = cudaAddressModeClamp;
+			td.filterMode = cudaFilterModeLinear;
+			td.readMode = cudaReadModeElementType;
+			td.normalizedCoords = 0;
+			MILB_CUDA_TRY(cudaCreateTextureObject(&tex, &rd, &td, nullptr));
+			sx = x; sy = y; sz = z; dev = cur;
+		}
+		cudaMemcpy3DParms cp = {0};
+		cp.srcPtr = make_cudaPitchedPtr((void *)d_src, (size_t)x * sizeof(float), x, y);
+		cp.dstArray = arr;
+		cp.extent = make_cudaExtent(x, y, z);
+		cp.kind = cudaMemcpyDeviceToDevice;
+		MILB_CUDA_TRY(cudaMemcpy3DAsync(&cp, st));
+		return MILB_OK;
+	}
+};
+// a few arrays per thread, by extent (a time point of the batch warps / projects two or three different extents)
+static thread_local SourceTexture t_warp_tex[4];
+static thread_local unsigned t_warp_age[4] = {0, 0, 0, 0}, t_warp_clock = 0;
+
+// the texture object of a device-resident source volume for the warp-type kernels (reg.cu, geom.cu)
+int milb_source_texture(const float *d_src, int sx, int sy, int sz, cudaStream_t st, cudaTextureObject_t *tex)
+{
+	int cur = 0, slot = -1, oldest = 0;
+	cudaGetDevice(&cur);
+	for (int i = 0; i < 4; i++) {
+		if (t_warp_tex[i].arr && t_warp_tex[i].sx == sx && t_warp_tex[i].sy == sy && t_warp_tex[i].sz == sz && t_warp_tex[i].dev == cur) slot = i;
+		if (t_warp_age[i] < t_warp_age[oldest]) oldest = i;
+	}
+	if (slot < 0) slot = oldest;
+	t_warp_age[slot] = ++t_warp_clock;
+	MILB_TRY(t_warp_tex[slot].bind(d_src, sx, sy, sz, st));
+	*tex = t_warp_tex[slot].tex;
+	return MILB_OK;
+}
+
 struct AffBatch {
 	float m[MILB_REG_MAXK][12];
 };
 
 // ---- warp kernel (a17) ------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) k_affine_warp(float *__restrict__ out, const float *__restrict__ src, int sx, int sy, int sz,
+template <bool HW>
+__global__ void __launch_bounds__(256) k_affine_warp(float *__restrict__ out, const float *__restrict__ src, cudaTextureObject_t tex, int sx, int sy, int sz,
 	int sx2, int sy2, int sz2, AffBatch aff)
 {
 	const long long n = (long long)sx * sy * sz;
@@ -32,8 +133,10 @@ __global__ void __launch_bounds__(256) k_affine_warp(float *__restrict__ out, co
 		const float fx = (float)x, fy = (float)y, fz = (float)z;
 		const float tx = aff_coord(a + 0, fx, fy, fz), ty = aff_coord(a + 4, fx, fy, fz), tz = aff_coord(a + 8, fx, fy, fz);
 		float r = 0.f;
-		if (tx >= 0 && tx < (float)sx2 && ty >= 0 && ty < (float)sy2 && tz >= 0 && tz < (float)sz2)
-			r = tex3d_linear(src, sx2, sy2, sz2, tx, ty, tz);
+		if (tx >= 0 && tx < (float)sx2 && ty >= 0 && ty < (float)sy2 && tz >= 0 && tz < (float)sz2) {
+			if constexpr (HW) r = tex3D<float>(tex, tx, ty, tz);
+			else r = tex3d_linear(src, sx2, sy2, sz2, tx, ty, tz);
+		}
 		out[i] = r;
 	}
 }
@@ -47,10 +150,10 @@ __global__ void __launch_bounds__(256) k_affine_warp(float *__restrict__ out, co
 // is the very float the reference's tex3D returns, and the eight gathers + fixed-point weights leave the SM's issue slots.
 // HW = false: the software restatement of that fetch (tex_sw.cuh), bit-identical to the CPU oracle; kept as the parity twin.
 #define REG_ZT 8
-// occupancy: the texture path is latency-bound (ncu: long-scoreboard stalls dominate), so the single-candidate variant is
-// held to 32 registers (8 CTAs = 64 warps per SM)
+// (holding the single-candidate texture variant to 32 registers for 8 CTAs = 64 warps per SM was measured slower:
+// 0.244 -> 0.264 ms per evaluation; more z steps in flight per thread likewise, see the loop)
 template <int K, bool HW>
-__global__ void __launch_bounds__(256, (HW && K == 1) ? 8 : 1) k_zncc(const float *__restrict__ tgt, const float *__restrict__ src, cudaTextureObject_t tex, int sx, int sy, int sz,
+__global__ void __launch_bounds__(256) k_zncc(const float *__restrict__ tgt, const float *__restrict__ src, cudaTextureObject_t tex, int sx, int sy, int sz,
 	AffBatch aff, double *__restrict__ partial /* [gridDim.x][K][2] */)
 {
 	__shared__ double sh[8][K][2];
@@ -163,21 +266,19 @@ int milb_reg_create(milb_reg_t **out, const unsigned int *sizeT)
 	h->n = (long long)h->sx * h->sy * h->sz;
 	const long long ntiles = (long long)((h->sx + 31) / 32) * ((h->sy + 7) / 8) * ((h->sz + REG_ZT - 1) / REG_ZT);
 	h->grid = (int)(ntiles < 148 * 8 ? ntiles : 148 * 8);
-	{
-		const char *fe = getenv("MILB_ZNCC_FETCH");
-		h->hw_fetch = !(fe && (fe[0] == 's' || fe[0] == '0'));
-	}
-	cudaError_t e = cudaMalloc(&h->tgt_raw, sizeof(float) * h->n);
-	if (e == cudaSuccess) e = cudaMalloc(&h->src_raw, sizeof(float) * h->n);
-	if (e == cudaSuccess) e = cudaMalloc(&h->tgt_dm, sizeof(float) * h->n);
-	if (e == cudaSuccess) e = cudaMalloc(&h->src_dm, sizeof(float) * h->n);
-	if (e == cudaSuccess) e = cudaMalloc(&h->tmp, sizeof(float) * h->n);
-	if (e == cudaSuccess) e = cudaMalloc(&h->d_red, sizeof(double) * (2 + MILB_REDUCE_BLOCKS));
-	if (e == cudaSuccess) e = cudaMalloc(&h->d_partial, sizeof(double) * 2 * MILB_REG_MAXK * h->grid);
-	if (e == cudaSuccess) e = cudaMalloc(&h->d_out, sizeof(double) * 2 * MILB_REG_MAXK);
-	if (e == cudaSuccess) e = cudaMallocHost(&h->h_out, sizeof(double) * 2 * MILB_REG_MAXK);
-	if (e != cudaSuccess) {
-		fprintf(stderr, "milb_reg_create: %s\n", cudaGetErrorString(e));
+	h->hw_fetch = milb_fetch_hardware();
+	// pooled (stream-ordered) allocations: a registration handle is created and destroyed per reg3d call, i.e. per time point
+	int rc = milb_pool_alloc((void **)&h->tgt_raw, sizeof(float) * h->n);
+	if (!rc) rc = milb_pool_alloc((void **)&h->src_raw, sizeof(float) * h->n);
+	if (!rc) rc = milb_pool_alloc((void **)&h->tgt_dm, sizeof(float) * h->n);
+	if (!rc) rc = milb_pool_alloc((void **)&h->src_dm, sizeof(float) * h->n);
+	if (!rc) rc = milb_pool_alloc((void **)&h->tmp, sizeof(float) * h->n);
+	if (!rc) rc = milb_pool_alloc((void **)&h->d_red, sizeof(double) * (2 + MILB_REDUCE_BLOCKS));
+	if (!rc) rc = milb_pool_alloc((void **)&h->d_partial, sizeof(double) * 2 * MILB_REG_MAXK * h->grid);
+	if (!rc) rc = milb_pool_alloc((void **)&h->d_out, sizeof(double) * 2 * MILB_REG_MAXK);
+	if (!rc && cudaMallocHost(&h->h_out, sizeof(double) * 2 * MILB_REG_MAXK) != cudaSuccess) rc = MILB_ERR_CUDA;
+	if (rc) {
+		fprintf(stderr, "milb_reg_create: allocation failed\n");
 		milb_reg_destroy(h);
 		return MILB_ERR_CUDA;
 	}
@@ -188,8 +289,9 @@ int milb_reg_create(milb_reg_t **out, const unsigned int *sizeT)
 void milb_reg_destroy(milb_reg_t *h)
 {
 	if (!h) return;
-	cudaFree(h->tgt_raw); cudaFree(h->src_raw); cudaFree(h->tgt_dm); cudaFree(h->src_dm); cudaFree(h->tmp);
-	cudaFree(h->d_red); cudaFree(h->d_partial); cudaFree(h->d_out);
+	cudaDeviceSynchronize(); // like the cudaFree calls this replaces: nothing on any stream still uses the buffers
+	milb_pool_free(h->tgt_raw); milb_pool_free(h->src_raw); milb_pool_free(h->tgt_dm); milb_pool_free(h->src_dm); milb_pool_free(h->tmp);
+	milb_pool_free(h->d_red); milb_pool_free(h->d_partial); milb_pool_free(h->d_out);
 	if (h->h_out) cudaFreeHost(h->h_out);
 	if (h->src_tex) cudaDestroyTextureObject(h->src_tex);
 	if (h->src_arr) cudaFreeArray(h->src_arr);
@@ -215,7 +317,11 @@ static int launch_warp(float *out, const float *src, int sx, int sy, int sz, int
 	AffBatch b;
 	memset(&b, 0, sizeof b);
 	aff_set(b, 0, tmx);
-	k_affine_warp<<<reg_grid_for((long long)sx * sy * sz), 256, 0, st>>>(out, src, sx, sy, sz, sx2, sy2, sz2, b);
+	if (milb_fetch_hardware()) { // the reference's mechanism: array copy of the source + tex3D (affinetransformkernel, cukernel.cuh:500-524)
+		cudaTextureObject_t tex = 0;
+		MILB_TRY(milb_source_texture(src, sx2, sy2, sz2, st, &tex));
+		k_affine_warp<true><<<reg_grid_for((long long)sx * sy * sz), 256, 0, st>>>(out, src, tex, sx, sy, sz, sx2, sy2, sz2, b);
+	} else k_affine_warp<false><<<reg_grid_for((long long)sx * sy * sz), 256, 0, st>>>(out, src, 0, sx, sy, sz, sx2, sy2, sz2, b);
 	milb_count_launches(1);
 	MILB_CUDA_TRY(cudaGetLastError());
 	return MILB_OK;

@@ -180,27 +180,26 @@ extern "C" int milb_reg3d_affine(float *reg_out, float *iTmx, const float *targe
 	// An affMethod outside 0..7 takes the reference's `default:` branch (src/api_subfunc.cu:2945-2978): a warning, no search, and
 	// the source is still warped by the starting matrix (identity, or iTmx when one was given) -- see the switch below.
 	const double t0 = now_s();
-	milb_reg_t *h = nullptr;
-	MILB_TRY(milb_reg_create(&h, size));
-	int rc = milb_reg_set_images(h, target, source, on_device, stream);
-	if (rc != MILB_OK) { milb_reg_destroy(h); return rc; }
-
-	if (affMethod == 0) { // no registration (:2767-2781)
-		if (flagTmx) rc = milb_reg_warp_source(h, iTmx, reg_out, on_device, stream);
+	int rc = MILB_OK;
+	if (affMethod == 0) { // no registration (:2767-2781): warp by the given matrix, or copy -- no cost handle is needed
+		if (flagTmx) rc = milb_affine_warp(reg_out, size, source, size, iTmx, on_device, stream);
 		else { // plain copy of the source and an identity matrix
 			const float ident[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
 			const long long n = (long long)size[0] * size[1] * size[2];
 			if (on_device) {
-				if (cudaMemcpyAsync(reg_out, source, sizeof(float) * n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess ||
-					cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = MILB_ERR_CUDA;
+				if (cudaMemcpyAsync(reg_out, source, sizeof(float) * n, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess) rc = MILB_ERR_CUDA;
 			} else memcpy(reg_out, source, sizeof(float) * n);
 			memcpy(iTmx, ident, sizeof ident);
 		}
+		if (on_device && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) rc = MILB_ERR_CUDA;
 		records[7] = (float)(now_s() - t0);
 		if (verbose) printf("\t... no registration performed!\n");
-		milb_reg_destroy(h);
 		return rc;
 	}
+	milb_reg_t *h = nullptr;
+	MILB_TRY(milb_reg_create(&h, size));
+	rc = milb_reg_set_images(h, target, source, on_device, stream);
+	if (rc != MILB_OK) { milb_reg_destroy(h); return rc; }
 
 	float affInitial[12] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0};
 	const bool prewarp = flagTmx && affMethod != 5;

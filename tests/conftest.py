@@ -41,17 +41,17 @@ def _oracle_built():
     yield
 
 
-# The registration cost kernel samples the source with the hardware texture unit by default (the reference's own
-# mechanism: each sample is the float the reference's tex3D returns).  The CPU oracle restates that fetch in software;
-# its bit-identical CUDA twin is selected with MILB_ZNCC_FETCH=sw.  Tests that compare Powell trajectories / sums
+# The warp, registration-cost and rotating-projection kernels sample the source with the hardware texture unit by default
+# (the reference's own mechanism: each sample is the float the reference's tex3D returns).  The CPU oracle restates that
+# fetch in software; its bit-identical CUDA twin is selected with MILB_TEX_FETCH=sw.  Tests that compare Powell trajectories / sums
 # with the ORACLE bit for bit run the twin; tests marked hw_fetch and tests/test_gpu_reference_pinned.py (product vs
 # the reference itself) run the default.
-_ORACLE_TWIN_MODULES = ("test_gpu_reg", "test_gpu_prealign", "test_gpu_apps", "test_golden_vectors")
+_ORACLE_TWIN_MODULES = ("test_gpu_reg", "test_gpu_prealign", "test_gpu_apps", "test_golden_vectors", "test_gpu_geometry")
 
 
 @pytest.fixture(autouse=True)
 def _zncc_fetch_mode(request, monkeypatch):
     mod = request.module.__name__.split(".")[-1]
     if mod in _ORACLE_TWIN_MODULES and "hw_fetch" not in request.keywords:
-        monkeypatch.setenv("MILB_ZNCC_FETCH", "sw")
+        monkeypatch.setenv("MILB_TEX_FETCH", "sw")
     yield
