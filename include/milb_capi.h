@@ -56,6 +56,11 @@ int milb_decon_set_image(milb_decon_t *h, int view, const float *img, int on_dev
 /* the iteration loop, src/api_subfunc.cu:3404-3416 / 3634-3660.  const_init: flagConstInitial */
 int milb_decon_run(milb_decon_t *h, int iterations, int const_init, void *stream);
 
+/* Phase correlation volume of two images of exactly the handle's FFT box on the project's own 3-D transform: replaces the
+ * cufftExecR2C x 2 + conj / multiply / normalise + cufftExecC2R of reg3d_phasor1 (src/api_subfunc.cu:2466-2496).  Device
+ * pointers; values below 0.01 may come back as 0.01 (only the arg-max is meaningful). */
+int milb_decon_phase_correlate(milb_decon_t *h, const float *d_img1, const float *d_img2, float *d_corr, void *stream);
+
 /* replaces cropgpu + D2H, src/api_decon.cpp:237-243 */
 int milb_decon_get_result(milb_decon_t *h, float *out, int on_device, void *stream);
 

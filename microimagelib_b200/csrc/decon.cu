@@ -636,6 +636,61 @@ int milb_decon_time_kernels(milb_decon_t *h, int reps, float *ms5, void *stream)
 	return MILB_OK;
 }
 
+// ---- phase correlation on the project's own 3-D transform (reg3d_phasor1, src/api_subfunc.cu:2466-2496) ------------------
+// Q = conj(F1) / |conj(F1) * F2| element-wise, in whatever layout / order the handle keeps its spectra (the same for both)
+__global__ void __launch_bounds__(256) k_phase_q(float2 *__restrict__ q_io /* F1 in, Q out */, const float2 *__restrict__ f2, long long n)
+{
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		const float2 a = q_io[i], b = f2[i];
+		const float ay = -a.y;
+		const float c = a.x * b.x - ay * b.y; // conj(F1) * F2  (conj3Dkernel + multicomplexnorm3Dkernel, include/cukernel.cuh:155-176, 209-219)
+		const float d = a.x * b.y + ay * b.x;
+		const float e = sqrtf(c * c + d * d);
+		q_io[i] = (e != 0.f) ? make_float2(a.x / e, ay / e) : make_float2(0.f, 0.f);
+	}
+}
+__global__ void k_fill(float *__restrict__ p, float v, long long n)
+{
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) p[i] = v;
+}
+
+// d_corr <- F^-1( conj(F(img1)) * F(img2) / |.| ), un-normalised, for volumes of exactly the handle's FFT box (no padding: the
+// correlation is periodic over the image size, as in the reference, which transforms the un-padded image with cuFFT).  The
+// product F2 * Q runs through the convolution path of the loop with Q in the OTF's place.  On the compile-time fast path the
+// last X pass is the loop's "update" pass on an estimate of ones, i.e. values below 0.01 come back as 0.01 -- irrelevant for
+// the arg-max the caller takes (the peak is of the order of the voxel count).
+int milb_decon_phase_correlate(milb_decon_t *h, const float *d_img1, const float *d_img2, float *d_corr, void *stream)
+{
+	if (!h || !d_img1 || !d_img2 || !d_corr) return MILB_ERR_ARG;
+	if (h->ix != h->X || h->iy != h->Y || h->iz != h->Z) return MILB_ERR_SIZE;
+	cudaStream_t st = (cudaStream_t)stream;
+	const size_t vb = sizeof(float) * h->nreal, sb = sizeof(float2) * h->nspec;
+	float2 *spec = h->fast ? h->S2 : h->S; // where a forward-only plane stage leaves the spectrum
+	MILB_CUDA_TRY(cudaMemcpyAsync(h->E, d_img1, vb, cudaMemcpyDeviceToDevice, st));
+	launch_xpass<X_FWD_REAL>(h, h->E, nullptr, st);
+	plane_stage(h, nullptr, 1.0f, st);
+	MILB_CUDA_TRY(cudaMemcpyAsync(h->otf[0], spec, sb, cudaMemcpyDeviceToDevice, st)); // F1
+	MILB_CUDA_TRY(cudaMemcpyAsync(h->E, d_img2, vb, cudaMemcpyDeviceToDevice, st));
+	launch_xpass<X_FWD_REAL>(h, h->E, nullptr, st);
+	plane_stage(h, nullptr, 1.0f, st);                                                 // F2
+	k_phase_q<<<grid_for(h->nspec), 256, 0, st>>>(h->otf[0], spec, h->nspec);
+	milb_count_launches(1);
+	launch_xpass<X_FWD_REAL>(h, h->E, nullptr, st);   // the X-only spectrum of img2 again (the generic plane stage works in place)
+	plane_stage(h, h->otf[0], 1.0f, st);              // Y/Z forward, * Q, Y/Z inverse
+	if (h->fast) {
+		k_fill<<<grid_for(h->nreal), 256, 0, st>>>(h->E, 1.0f, h->nreal);
+		milb_count_launches(1);
+		launch_xpass<X_UPDATE_LAST>(h, h->E, nullptr, st); // E = max(1 * C2R(S), 0.01)
+	} else {
+		const long long M = (long long)h->Y * h->Z / 2;
+		k_xpass<X_INV_REAL><<<(unsigned)(M / h->Lx), kThreads, h->smx, st>>>(h->px.dev, M, h->Lx, (float2 *)h->E, nullptr, (float4 *)h->S, 1.0f);
+		milb_count_launches(1);
+	}
+	MILB_CUDA_TRY(cudaMemcpyAsync(d_corr, h->E, vb, cudaMemcpyDeviceToDevice, st));
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
 int milb_decon_get_result(milb_decon_t *h, float *out, int on_device, void *stream)
 {
 	if (!h || !out) return MILB_ERR_ARG;

@@ -277,32 +277,53 @@ int milb_phasor(long long *shift, const float *d_img1, const float *d_img2, cons
 	double *d_work = nullptr;
 	const int g = grid_for(n);
 	MILB_CUDA_TRY(cudaMalloc(&d_s1, sizeof(float2) * ns));
-	MILB_CUDA_TRY(cudaMalloc(&d_s2, sizeof(float2) * ns));
 	MILB_CUDA_TRY(cudaMalloc(&d_peak, sizeof(Peak) * (g + 1)));
 	MILB_CUDA_TRY(cudaMalloc(&d_work, sizeof(double) * (8 + 3 * (size_t)g)));
 	int rc = MILB_OK;
-	cufftHandle fwd = 0, inv = 0;
-	cufftResult cr;
-	if (sz == 1) {
-		cr = cufftPlan2d(&fwd, sy, sx, CUFFT_R2C);
-		if (cr == CUFFT_SUCCESS) cr = cufftPlan2d(&inv, sy, sx, CUFFT_C2R);
-	} else {
-		cr = cufftPlan3d(&fwd, sz, sy, sx, CUFFT_R2C);
-		if (cr == CUFFT_SUCCESS) cr = cufftPlan3d(&inv, sz, sy, sx, CUFFT_C2R);
+	// The correlation volume.  When the image size is one the project's own 3-D transform handles without padding (every
+	// extent a multiple of 64 that snapTransformSize leaves alone: the usual 512 x 512 x 256 ... stacks), it runs on that
+	// transform through the convolution path of the deconvolution loop; arbitrary sizes (and 2-D images) use cuFFT on the
+	// exact size like the reference.  MILB_PHASOR_CUFFT=1 forces the library path.
+	bool own = sz > 1 && sx % 64 == 0 && sy % 64 == 0 && sz % 64 == 0 && milb_snap_transform_size(sx) == sx &&
+		milb_snap_transform_size(sy) == sy && milb_snap_transform_size(sz) == sz;
+	if (const char *e = getenv("MILB_PHASOR_CUFFT")) own = own && e[0] != '1';
+	bool have_corr = false;
+	if (own) {
+		milb_decon_t *dh = nullptr;
+		if (milb_decon_create(&dh, 1, size) == MILB_OK) {
+			if (milb_decon_phase_correlate(dh, d_img1, d_img2, (float *)d_s1, st) == MILB_OK && cudaStreamSynchronize(st) == cudaSuccess) have_corr = true;
+			milb_decon_destroy(dh);
+		}
+		cudaGetLastError();
 	}
-	if (cr == CUFFT_SUCCESS) cr = cufftSetStream(fwd, st);
-	if (cr == CUFFT_SUCCESS) cr = cufftSetStream(inv, st);
-	if (cr == CUFFT_SUCCESS) cr = cufftExecR2C(fwd, (cufftReal *)d_img1, (cufftComplex *)d_s1);
-	if (cr == CUFFT_SUCCESS) cr = cufftExecR2C(fwd, (cufftReal *)d_img2, (cufftComplex *)d_s2);
-	if (cr == CUFFT_SUCCESS) {
-		k_phase_norm<<<grid_for(ns), 256, 0, st>>>(d_s2, d_s1, ns);
-		cr = cufftExecC2R(inv, (cufftComplex *)d_s2, (cufftReal *)d_s1); // correlation volume lands in d_s1 (n floats <= 2*ns)
+	cufftHandle fwd = 0, inv = 0;
+	cufftResult cr = CUFFT_SUCCESS;
+	if (!have_corr) {
+		if (cudaMalloc(&d_s2, sizeof(float2) * ns) != cudaSuccess) cr = CUFFT_ALLOC_FAILED;
+		if (cr == CUFFT_SUCCESS) {
+			if (sz == 1) {
+				cr = cufftPlan2d(&fwd, sy, sx, CUFFT_R2C);
+				if (cr == CUFFT_SUCCESS) cr = cufftPlan2d(&inv, sy, sx, CUFFT_C2R);
+			} else {
+				cr = cufftPlan3d(&fwd, sz, sy, sx, CUFFT_R2C);
+				if (cr == CUFFT_SUCCESS) cr = cufftPlan3d(&inv, sz, sy, sx, CUFFT_C2R);
+			}
+		}
+		if (cr == CUFFT_SUCCESS) cr = cufftSetStream(fwd, st);
+		if (cr == CUFFT_SUCCESS) cr = cufftSetStream(inv, st);
+		if (cr == CUFFT_SUCCESS) cr = cufftExecR2C(fwd, (cufftReal *)d_img1, (cufftComplex *)d_s1);
+		if (cr == CUFFT_SUCCESS) cr = cufftExecR2C(fwd, (cufftReal *)d_img2, (cufftComplex *)d_s2);
+		if (cr == CUFFT_SUCCESS) {
+			k_phase_norm<<<grid_for(ns), 256, 0, st>>>(d_s2, d_s1, ns);
+			milb_count_launches(1);
+			cr = cufftExecC2R(inv, (cufftComplex *)d_s2, (cufftReal *)d_s1); // correlation volume lands in d_s1 (n floats <= 2*ns)
+		}
 	}
 	Peak pk = {0.f, 0};
 	if (cr == CUFFT_SUCCESS) {
 		k_peak_partial<<<g, 256, 0, st>>>((const float *)d_s1, sx, sy, sz, d_peak + 1);
 		k_peak_final<<<1, 256, 0, st>>>(d_peak + 1, g, d_peak);
-		milb_count_launches(3);
+		milb_count_launches(2);
 		if (cudaMemcpyAsync(&pk, d_peak, sizeof pk, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
 			rc = MILB_ERR_CUDA;
 	} else {
@@ -312,7 +333,7 @@ int milb_phasor(long long *shift, const float *d_img1, const float *d_img2, cons
 	if (fwd) cufftDestroy(fwd);
 	if (inv) cufftDestroy(inv);
 	cudaFree(d_s1);
-	cudaFree(d_s2);
+	if (d_s2) cudaFree(d_s2);
 	cudaFree(d_peak);
 	if (rc != MILB_OK) { cudaFree(d_work); return rc; }
 

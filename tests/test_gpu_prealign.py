@@ -111,6 +111,32 @@ def test_phasor_large_shift_alias_and_2d():
     assert device.phasor(img, big) == ro.phasor(img, big)
 
 
+@pytest.mark.parametrize("shape", [(64, 128, 192), (128, 64, 320), (64, 64, 64)])
+def test_phasor_on_the_projects_own_fft(shape, monkeypatch):
+    """Image sizes the project's 3-D transform handles without padding (multiples of 64 that snapTransformSize keeps) run the
+    phase correlation on it (power-of-two and 64*k fast plans); the cuFFT path on the exact size and the CPU oracle give the
+    same shifts, including large shifts that need the alias disambiguation."""
+    from microimagelib_b200 import device
+    from oracle import reg_oracle as ro
+    v = _vol(shape, seed=5)
+    for d in ((5, -3, 2), (0, 0, 0), (shape[2] // 2 - 6, -7, 9), (-11, shape[1] // 3, -shape[0] // 3)):
+        moved = ro.imshift(v, d)
+        want = ro.phasor(v, moved)
+        monkeypatch.setenv("MILB_PHASOR_CUFFT", "0")
+        l0 = device.launch_count()
+        own = device.phasor(v, moved)
+        own_launches = device.launch_count() - l0
+        monkeypatch.setenv("MILB_PHASOR_CUFFT", "1")
+        l0 = device.launch_count()
+        lib = device.phasor(v, moved)
+        lib_launches = device.launch_count() - l0
+        assert own == lib == want
+        assert own_launches > lib_launches + 8          # the transform's own kernels were launched (cuFFT's are not counted)
+    moved = np.roll(v, (4, -9, 17), axis=(0, 1, 2))
+    monkeypatch.setenv("MILB_PHASOR_CUFFT", "0")
+    assert device.phasor(v, moved) == [17, -9, 4]
+
+
 def test_imshift_exact():
     from microimagelib_b200 import device
     from oracle import reg_oracle as ro
