@@ -208,6 +208,7 @@ int milb_rot_mip_dev(float *d_out, const float *d_src, const unsigned int *sizeR
 	cudaStream_t st)
 {
 	if (!d_out || !d_src || !sizeRot || !sizeSrc || !matrices || nproj < 1) return MILB_ERR_ARG;
+	if ((unsigned long long)sizeSrc[0] * sizeSrc[1] * sizeSrc[2] >= (1ull << 31)) return MILB_ERR_SIZE; // 32-bit element indices of the source
 	const long long npix = (long long)sizeRot[0] * sizeRot[1];
 	long long bx = cdiv_ll(npix, 256);
 	if (bx > 148 * 4) bx = 148 * 4;

@@ -261,6 +261,8 @@ static int reg_grid_for(long long n) { long long b = cdiv_ll(n, 256); return (in
 int milb_reg_create(milb_reg_t **out, const unsigned int *sizeT)
 {
 	if (!out || !sizeT || !sizeT[0] || !sizeT[1] || !sizeT[2]) return MILB_ERR_ARG;
+	// the kernels index voxels with 32-bit integers (tex_sw.cuh): refuse volumes of 2^31 voxels or more instead of overflowing
+	if ((unsigned long long)sizeT[0] * sizeT[1] * sizeT[2] >= (1ull << 31)) return MILB_ERR_SIZE;
 	milb_reg *h = new milb_reg();
 	h->sx = (int)sizeT[0]; h->sy = (int)sizeT[1]; h->sz = (int)sizeT[2];
 	h->n = (long long)h->sx * h->sy * h->sz;
@@ -314,6 +316,7 @@ static void aff_set(AffBatch &b, int k, const float *m) { memcpy(b.m[k], m, 12 *
 
 static int launch_warp(float *out, const float *src, int sx, int sy, int sz, int sx2, int sy2, int sz2, const float *tmx, cudaStream_t st)
 {
+	if ((long long)sx2 * sy2 * sz2 >= (1ll << 31)) return MILB_ERR_SIZE; // 32-bit element indices of the source (tex_sw.cuh)
 	AffBatch b;
 	memset(&b, 0, sizeof b);
 	aff_set(b, 0, tmx);

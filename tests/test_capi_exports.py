@@ -52,3 +52,15 @@ def test_host_only_helpers_work_without_gpu():
     from microimagelib_b200 import libapi
     assert libapi.checkmatrix([1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0], 10, 10, 10)
     assert not libapi.checkmatrix([1, 0, 0, 9, 0, 1, 0, 0, 0, 0, 1, 0], 10, 10, 10)
+
+
+def test_volumes_beyond_32_bit_indexing_are_refused():
+    """The warp / cost kernels index voxels with 32-bit integers: a 2048 x 2048 x 512 volume (2^31 voxels) fits a 180 GB GPU
+    but must be refused, not silently mis-indexed (checked before any CUDA call, so this runs without a GPU)."""
+    import ctypes as C
+    from microimagelib_b200 import _lib
+    lib = _lib.load()
+    h = C.c_void_p()
+    size = (C.c_uint * 3)(2048, 2048, 512)
+    assert lib.milb_reg_create(C.byref(h), size) == 3          # MILB_ERR_SIZE
+    assert not h.value
