@@ -61,6 +61,11 @@ int milb_decon_run(milb_decon_t *h, int iterations, int const_init, void *stream
  * pointers; values below 0.01 may come back as 0.01 (only the arg-max is meaningful). */
 int milb_decon_phase_correlate(milb_decon_t *h, const float *d_img1, const float *d_img2, float *d_corr, void *stream);
 
+/* set_image + run + get_result in one call for HOST images of exactly the FFT box size (single or dual view, no constant
+ * initial estimate): the host copies are cut into row ranges and overlapped with the first and the last X pass; same
+ * kernels and results.  MILB_ERR_SIZE (3) = not applicable, use the three calls.  h_img: nviews host pointers. */
+int milb_decon_run_host(milb_decon_t *h, const float *const *h_img, float *h_out, int iterations, int const_init, void *stream);
+
 /* replaces cropgpu + D2H, src/api_decon.cpp:237-243 */
 int milb_decon_get_result(milb_decon_t *h, float *out, int on_device, void *stream);
 

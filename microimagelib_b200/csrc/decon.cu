@@ -318,6 +318,10 @@ void milb_decon_destroy(milb_decon_t *h)
 	if (h->stage) cudaFree(h->stage);
 	if (h->S) cudaFree(h->S);
 	if (h->S2) cudaFree(h->S2);
+	if (h->copy_stream) {
+		cudaStreamDestroy(h->copy_stream);
+		for (auto &e : h->copy_ev) if (e) cudaEventDestroy(e);
+	}
 	if (h->fuse.ring) cudaFree(h->fuse.ring);
 	if (h->fuse.counters) cudaFree(h->fuse.counters);
 	if (h->d_sums) cudaFree(h->d_sums);
@@ -580,6 +584,93 @@ int milb_decon_run(milb_decon_t *h, int iterations, int const_init, void *stream
 		}
 	}
 	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+// ---- host image(s) in, host result out, with the copies pipelined against the first and the last X pass -------------------
+// A = max(A, 0.01) in place and E = A (one view) or (A + B) / 2 (two views) on the rows [y0, y0 + ny) of every x slice
+__global__ void __launch_bounds__(256) k_prep_rows(float *__restrict__ A, float *__restrict__ B, float *__restrict__ E, int X, int Y, int Z, int y0, int ny)
+{
+	const long long per = (long long)ny * Z, n = (long long)X * per;
+	for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+		const long long x = i / per, r = i - x * per;
+		const long long at = (x * Y + y0) * (long long)Z + r;
+		float a = A[at];
+		a = (a > SMALLVALUE_F) ? a : SMALLVALUE_F; // maxvalue3Dgpu, src/api_subfunc.cu:3380
+		A[at] = a;
+		if (B) {
+			float b = B[at];
+			b = (b > SMALLVALUE_F) ? b : SMALLVALUE_F;
+			B[at] = b;
+			E[at] = (a + b) * 0.5f;                 // src/api_subfunc.cu:3616
+		} else E[at] = a;
+	}
+}
+
+// decon_singleview / decon_dualview for HOST images whose size is the FFT box (nothing to pad or crop) on the compile-time
+// fast path: the volume is cut into `chunks` ranges of y rows; chunk c's rows of every slice travel as one strided 2-D copy
+// on a copy stream while chunk c-1 is clamped, turned into the initial estimate and run through the first X pass (which
+// works on column ranges), and at the end chunk c of the result is copied out while the last X pass still works on chunk
+// c+1.  Same kernels, same arithmetic and the same result as set_image + run + get_result; only the serial H2D -> loop -> D2H
+// of that sequence is overlapped.  Returns MILB_ERR_SIZE when the case does not apply (the caller then takes the plain path).
+int milb_decon_run_host(milb_decon_t *h, const float *const *h_img, float *h_out, int iterations, int const_init, void *stream)
+{
+	if (!h || !h_img || !h_out || iterations < 1) return MILB_ERR_ARG;
+	if (!h->fast || const_init || h->ix != h->X || h->iy != h->Y || h->iz != h->Z || h->chunk_planes != 0) return MILB_ERR_SIZE;
+	const int nv = h->nviews;
+	for (int v = 0; v < nv; v++)
+		if (!h->have_psf[v] || !h_img[v]) return MILB_ERR_ARG;
+	const FastAxisOps *ox = milb_fast_ops(h->X);
+	int chunks = 4;
+	if (const char *e = getenv("MILB_HOST_CHUNKS")) chunks = atoi(e);
+	if (chunks < 2 || !ox->xpass_cols) return MILB_ERR_SIZE;
+	while (chunks > 2 && (h->Y % chunks || ((long long)(h->Y / chunks) * h->Z / 2) % 64)) chunks /= 2;
+	if (h->Y % chunks || ((long long)(h->Y / chunks) * h->Z / 2) % 64) return MILB_ERR_SIZE;
+	cudaStream_t st = (cudaStream_t)stream;
+	if (!h->copy_stream) {
+		MILB_CUDA_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+		for (auto &e : h->copy_ev) MILB_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+	}
+	cudaStream_t cs = h->copy_stream;
+	const int ny = h->Y / chunks;
+	const long long M = (long long)h->Y * h->Z / 2, nc = (long long)ny * h->Z / 2;
+	const size_t pitch = sizeof(float) * h->Y * h->Z, width = sizeof(float) * ny * h->Z;
+	// the previous call's work on the launching stream is done before the copy stream overwrites A
+	MILB_CUDA_TRY(cudaEventRecord(h->copy_ev[8], st));
+	MILB_CUDA_TRY(cudaStreamWaitEvent(cs, h->copy_ev[8], 0));
+	for (int c = 0; c < chunks; c++) {
+		const long long off = (long long)c * ny * h->Z;
+		for (int v = 0; v < nv; v++)
+			MILB_CUDA_TRY(cudaMemcpy2DAsync(h->A[v] + off, pitch, h_img[v] + off, pitch, width, h->X, cudaMemcpyHostToDevice, cs));
+		MILB_CUDA_TRY(cudaEventRecord(h->copy_ev[c], cs));
+	}
+	for (int c = 0; c < chunks; c++) {
+		MILB_CUDA_TRY(cudaStreamWaitEvent(st, h->copy_ev[c], 0));
+		k_prep_rows<<<grid_for((long long)h->X * ny * h->Z), 256, 0, st>>>(h->A[0], nv == 2 ? h->A[1] : nullptr, h->E, h->X, h->Y, h->Z, c * ny, ny);
+		ox->xpass_cols(X_FWD_REAL, (float2 *)h->E + c * nc, nullptr, (float4 *)h->S + c * nc, h->px.d_tw, M, nc, st);
+		milb_count_launches(2);
+	}
+	for (int v = 0; v < nv; v++) h->have_img[v] = true;
+	for (int it = 0; it < iterations; it++) {
+		for (int v = 0; v < nv; v++) {
+			plane_stage(h, h->otf[v], 1.0f, st);
+			launch_xpass<X_RATIO>(h, nullptr, h->A[v], st);
+			plane_stage(h, h->otf_bp[v], 1.0f, st);
+			const bool last = (it == iterations - 1) && (v == nv - 1);
+			if (!last) { launch_xpass<X_UPDATE>(h, h->E, nullptr, st); continue; }
+			for (int c = 0; c < chunks; c++) { // the last X pass chunk by chunk, each chunk's rows leaving as soon as they are final
+				ox->xpass_cols(X_UPDATE_LAST, (float2 *)h->E + c * nc, nullptr, (float4 *)h->S + c * nc, h->px.d_tw, M, nc, st);
+				milb_count_launches(1);
+				MILB_CUDA_TRY(cudaEventRecord(h->copy_ev[4 + c], st));
+				MILB_CUDA_TRY(cudaStreamWaitEvent(cs, h->copy_ev[4 + c], 0));
+				const long long off = (long long)c * ny * h->Z;
+				MILB_CUDA_TRY(cudaMemcpy2DAsync(h_out + off, pitch, h->E + off, pitch, width, h->X, cudaMemcpyDeviceToHost, cs));
+			}
+		}
+	}
+	MILB_CUDA_TRY(cudaGetLastError());
+	MILB_CUDA_TRY(cudaStreamSynchronize(cs));
+	MILB_CUDA_TRY(cudaStreamSynchronize(st));
 	return MILB_OK;
 }
 

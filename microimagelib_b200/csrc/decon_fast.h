@@ -30,6 +30,9 @@ struct FastAxisOps {
 	int (*setup)() = nullptr;
 	// mode: 0 fwd-real, 1 ratio, 2 update, 3 update-last (XF_* in fft_fast.cuh); M = columns of float2 pairs
 	void (*xpass)(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const float2 *tw, long long M, cudaStream_t st) = nullptr;
+	// the same on a range of ncols columns: the three pointers already point at the range's first column, M stays the row pitch
+	// (lets the first and the last X pass of a call run chunk by chunk while the host copies of the other chunks are in flight)
+	void (*xpass_cols)(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const float2 *tw, long long M, long long ncols, cudaStream_t st) = nullptr;
 	// planes [n rows][cols] -> [cols rows][n], forward transform along the rows index
 	void (*passT)(const float2 *in, float2 *out, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st) = nullptr;
 	// in-place inverse along rows: planes [n rows][cols]

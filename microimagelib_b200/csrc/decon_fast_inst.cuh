@@ -128,22 +128,28 @@ int setup()
 	return bad;
 }
 
-void xpass(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const float2 *tw, long long M, cudaStream_t st)
+// X pass over ncols columns starting at the pointers given; M = row pitch in column pairs (ncols == M: the whole volume)
+void xpass_cols(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const float2 *tw, long long M, long long ncols, cudaStream_t st)
 {
-	if (mode != XF_FWD_REAL && (M % XL) == 0) {
-		const int ntiles = (int)(M / XL), cap = XCTAS * g_sms, grid = ntiles < cap ? ntiles : cap;
+	if (mode != XF_FWD_REAL && (ncols % XL) == 0) {
+		const int ntiles = (int)(ncols / XL), cap = XCTAS * g_sms, grid = ntiles < cap ? ntiles : cap;
 		if (mode == XF_RATIO) k_xpassP<N, XL, XT, XF_RATIO><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles);
 		else if (mode == XF_UPDATE) k_xpassP<N, XL, XT, XF_UPDATE><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles);
 		else k_xpassP<N, XL, XT, XF_UPDATE_LAST><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles);
 		return;
 	}
-	const unsigned grid = (unsigned)(M / L);
+	const unsigned grid = (unsigned)(ncols / L);
 	switch (mode) {
 	case XF_FWD_REAL: k_xpassF<N, L, TXF, XF_FWD_REAL><<<grid, TXF, SM1, st>>>(vol_io, aux, spec, tw, M); break;
 	case XF_RATIO: k_xpassF<N, L, TXF, XF_RATIO><<<grid, TXF, SM1, st>>>(vol_io, aux, spec, tw, M); break;
 	case XF_UPDATE: k_xpassF<N, L, TXF, XF_UPDATE><<<grid, TXF, SM1, st>>>(vol_io, aux, spec, tw, M); break;
 	default: k_xpassF<N, L, TXF, XF_UPDATE_LAST><<<grid, TXF, SM1, st>>>(vol_io, aux, spec, tw, M); break;
 	}
+}
+
+void xpass(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const float2 *tw, long long M, cudaStream_t st)
+{
+	xpass_cols(mode, vol_io, aux, spec, tw, M, M, st);
 }
 
 // distributed variants: the output spectrum is stored into the owning ranks' buffers (peer memory)
@@ -243,7 +249,7 @@ void fwd_scaled(float2 *spec, const float2 *tw, int cols, int plane0, int nplane
 const FastAxisOps *MILB_CAT(milb_fast_ops_, MILB_FAST_N)()
 {
 	static FastAxisOps ops;
-	ops.n = N; ops.lanes = L; ops.xlanes = XL > L ? XL : L; ops.setup = setup; ops.xpass = xpass; ops.passT = passT; ops.pass_inv = pass_inv;
+	ops.n = N; ops.lanes = L; ops.xlanes = XL > L ? XL : L; ops.setup = setup; ops.xpass = xpass; ops.xpass_cols = xpass_cols; ops.passT = passT; ops.pass_inv = pass_inv;
 	ops.convT = convT; ops.fwd_scaled = fwd_scaled; ops.planes_fused = kPow2 ? planes_fused : nullptr;
 	ops.xpass_peer = kPow2 ? xpass_peer : nullptr; ops.pass_inv_peer = kPow2 ? pass_inv_peer : nullptr; ops.grid_cap = &g_cap;
 	return &ops;

@@ -31,6 +31,8 @@ struct milb_decon {
 	float2 *S2 = nullptr;          // fast path: transposed planes [kx][z][ky']
 	float2 *otf[2] = {nullptr, nullptr}, *otf_bp[2] = {nullptr, nullptr};
 	PlaneFuse fuse;                // fast path, square planes: state of the fused plane stage (ring == nullptr: three launches)
+	cudaStream_t copy_stream = nullptr; // milb_decon_run_host: host copies overlapped with the first / last X pass
+	cudaEvent_t copy_ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 	double *d_sums = nullptr;      // [0..1] sums, [2..] reduction scratch
 	bool have_psf[2] = {false, false}, have_img[2] = {false, false};
 	// raw PSFs kept on the host for the cuFFT yardstick: [view][0 = forward, 1 = back projector]

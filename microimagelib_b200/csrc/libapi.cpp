@@ -223,11 +223,27 @@ int decon_common(int nviews, float *h_decon, float *const h_img[2], unsigned int
 	}
 	deconRecords[2] = (hit && same_handle) ? deconRecords[1] : free_mb();
 	printf("...GPU free memory(after mallocing) is %.0f MBites\n", deconRecords[2]);
-	for (int v = 0; v < nviews; v++)
-		fatal_if(milb_decon_set_image(c.h, v, h_img[v], on_device(h_img[v]) ? 1 : 0, nullptr), "****Image preparation failed !!!!*****");
-	const double t2 = now_s();
-	fatal_if(milb_decon_run(c.h, itNumForDecon, flagConstInitial ? 1 : 0, nullptr), "decon iterration error");
-	fatal_if(milb_decon_get_result(c.h, h_decon, on_device(h_decon) ? 1 : 0, nullptr), "decon result transfer");
+	// host images of exactly the FFT box size: copies overlapped with the first / last X pass (MILB_HOST_PIPELINE=0: plain sequence)
+	bool piped = false;
+	double t2 = now_s();
+	{
+		const char *pe = getenv("MILB_HOST_PIPELINE");
+		bool host = !on_device(h_decon) && itNumForDecon > 0 && !(pe && pe[0] == '0');
+		for (int v = 0; v < nviews; v++) host = host && !on_device(h_img[v]);
+		if (host) {
+			const float *imgs[2] = {h_img[0], h_img[1]};
+			const int rc = milb_decon_run_host(c.h, imgs, h_decon, itNumForDecon, flagConstInitial ? 1 : 0, nullptr);
+			if (rc == MILB_OK) piped = true;
+			else if (rc != MILB_ERR_SIZE) fatal_if(rc, "decon iterration error");
+		}
+	}
+	if (!piped) {
+		for (int v = 0; v < nviews; v++)
+			fatal_if(milb_decon_set_image(c.h, v, h_img[v], on_device(h_img[v]) ? 1 : 0, nullptr), "****Image preparation failed !!!!*****");
+		t2 = now_s();
+		fatal_if(milb_decon_run(c.h, itNumForDecon, flagConstInitial ? 1 : 0, nullptr), "decon iterration error");
+		fatal_if(milb_decon_get_result(c.h, h_decon, on_device(h_decon) ? 1 : 0, nullptr), "decon result transfer");
+	}
 	const double t3 = now_s();
 	deconRecords[4] = (hit && same_handle) ? deconRecords[1] : free_mb();
 	printf("...GPU free memory (after processing) is %.0f MBites\n", deconRecords[4]);
