@@ -1,5 +1,6 @@
 """CPU restatement of the Richardson-Lucy path of microImageLib.  TEST INFRASTRUCTURE ONLY
-(see oracle/__init__.py: parity unpinned by the reference, pinned by KATs in tests/).
+(see oracle/__init__.py: pinned to the reference's own GPU build -- tests/test_gpu_reference_pinned.py, the committed
+tests/golden/reference_vectors.npz -- and by KATs in tests/).
 
 Arrays are numpy, C-order, shape ``(slices, H, W)``: the same bytes as the reference's x-fastest
 TIFF layout.  The reference's decon code calls those axes ``(x, y, z)`` with z fastest

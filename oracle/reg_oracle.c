@@ -1,6 +1,6 @@
 /* CPU restatement of the registration cost path of microImageLib.  TEST INFRASTRUCTURE ONLY.
- * (see oracle/__init__.py: parity unpinned by the reference; pinned by KATs in tests/ and by a
- *  hardware tex3D cross-check run on the GPU box.)
+ * (see oracle/__init__.py: pinned to the reference's own GPU build -- coordinate expression read off its SASS, texture
+ *  filter fitted to its tex3D output, costs / warps / registrations compared three ways on the GPU -- and by KATs in tests/.)
  *
  * Build: gcc -O2 -fopenmp -ffp-contract=off -shared -fPIC  (oracle/Makefile).
  * -ffp-contract=off matters: every float expression below is evaluated exactly as written.
