@@ -26,6 +26,33 @@
 
 #define SMALLVALUE_FAST 0.01f // src/api_subfunc.cu:24
 
+// The ratio A / T (div3Dkernel, include/cukernel.cuh:194-206).  The reference compiles `a / b` to the IEEE division sequence
+// (reciprocal, two refinement steps, range fix-ups: about ten instructions, 35 MUFU + slow-path code in the ratio pass).
+//   MILB_FAST_DIV = 1 (default): q = a * rcp(b), then one Newton step on the quotient with fused multiply-adds:
+//       e = fma(-b, q, a) (exact residual), q' = fma(e, rcp(b), q).  The un-rounded q' is within 2^-46 relative of a / b, so the
+//       result is the correctly rounded quotient except when a / b lies within 2^-46 of a rounding boundary (about one
+//       division in four million, then one ulp off); operands here are images >= 0.01 and their blurred estimates, far from
+//       the exponent extremes the IEEE sequence's fix-ups exist for.  Ratio pass at 512^3: 391 -> 338 us (the same as
+//       __fdividef), 2.111 -> 2.075 ms per iteration; the 512x512x256 result came out bit-identical to the IEEE build's.
+//   MILB_FAST_DIV = 0: the plain operator.     MILB_FAST_DIV = 2: __fdividef (<= 2 ulp), for reference only.
+#ifndef MILB_FAST_DIV
+#define MILB_FAST_DIV 1
+#endif
+__device__ __forceinline__ float rl_div(float a, float b)
+{
+#if MILB_FAST_DIV == 2
+	return __fdividef(a, b);
+#elif MILB_FAST_DIV == 1
+	float r;
+	asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+	const float q = a * r;
+	const float e = __fmaf_rn(-b, q, a);
+	return __fmaf_rn(e, r, q);
+#else
+	return a / b;
+#endif
+}
+
 template <int N> struct FastPlan;
 #define MILB_FAST_PLAN(N_, S_, A, B, C, D)                    \
 	template <> struct FastPlan<N_> {                         \
@@ -248,8 +275,9 @@ template <int N, int L, int T> __device__ __forceinline__ void fwd_tail_smem(flo
 	}
 }
 
-// inverse stages S-1..1, all in `tile` (stage 0 is done by the caller)
-template <int N, int L, int T> __device__ __forceinline__ void inv_head_smem(float2 *tile, const float2 *tw)
+// inverse stages S-1..1, all in `tile` (stage 0 is done by the caller).  FINAL_SYNC = false leaves the barrier after the last
+// of them to the caller (who merges it with another one)
+template <int N, int L, int T, bool FINAL_SYNC = true> __device__ __forceinline__ void inv_head_smem(float2 *tile, const float2 *tw)
 {
 	using P = FastPlan<N>;
 	auto sl = [tile](int r, int l) { return tile[r * L + l]; };
@@ -264,7 +292,7 @@ template <int N, int L, int T> __device__ __forceinline__ void inv_head_smem(flo
 		__syncthreads();
 	}
 	fstage<N, L, T, P::r1, ns1, true>(tw, sl, ss);
-	__syncthreads();
+	if (FINAL_SYNC) __syncthreads();
 }
 
 // inverse: the first stage (S-1) reads through ldf, stage 0 writes through st0
@@ -979,7 +1007,7 @@ k_xpassF(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 #pragma unroll
 			for (int j = 0; j < R0; j++) a[j] = aux[(long long)(q + j * M0) * M + col0 + lane];
 #pragma unroll
-			for (int j = 0; j < R0; j++) { v[j].x = a[j].x / v[j].x; v[j].y = a[j].y / v[j].y; } // div3Dkernel
+			for (int j = 0; j < R0; j++) { v[j].x = rl_div(a[j].x, v[j].x); v[j].y = rl_div(a[j].y, v[j].y); } // div3Dkernel
 		} else {
 			float2 e[R0];
 #pragma unroll
@@ -1114,9 +1142,9 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 		__syncthreads();
 		if (tn < ntiles) load_spec(tn);
 		cp_async_commit();
-		inv_head_smem<N, L, T>(W, tw);
+		inv_head_smem<N, L, T, false>(W, tw);
 		cp_async_wait<1>(); // aux of this tile landed (the next spectrum may still be in flight)
-		__syncthreads();
+		__syncthreads();    // one barrier for both: the last inverse stage's writes to W and everybody's aux rows
 		float2 v[R0];
 #pragma unroll
 		for (int j = 0; j < R0; j++) v[j] = W[(q + j * M0) * L + lane];
@@ -1127,7 +1155,7 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 #pragma unroll
 			for (int j = 0; j < R0; j++) {
 				const float2 a = AL[(q + j * M0) * L + lane];
-				v[j].x = a.x / v[j].x; v[j].y = a.y / v[j].y; // div3Dkernel
+				v[j].x = rl_div(a.x, v[j].x); v[j].y = rl_div(a.y, v[j].y); // div3Dkernel
 			}
 		} else {
 #pragma unroll
