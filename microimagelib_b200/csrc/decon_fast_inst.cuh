@@ -45,7 +45,11 @@ constexpr int TXF = (N / R0) * L;                   // threads of the non-persis
 #ifndef MILB_X_WIDE512
 #define MILB_X_WIDE512 1
 #endif
-constexpr bool kXWide = MILB_X_WIDE || (MILB_X_WIDE512 && N == 512);
+// MILB_X_WIDE_NP2 (default): 8192-point X tiles for the 64*k lengths too (their 4096-point tiles are 4 - 16 column pairs wide)
+#ifndef MILB_X_WIDE_NP2
+#define MILB_X_WIDE_NP2 1
+#endif
+constexpr bool kXWide = MILB_X_WIDE || (MILB_X_WIDE512 && N == 512) || (MILB_X_WIDE_NP2 && !kPow2);
 constexpr int XL = pow2_floor((kXWide ? 8192 : kXNarrow ? 2048 : 4096) / N), XT = (N / R0) * XL;
 constexpr int XCTAS = xpassP_ctas<N, XL, XT>();
 constexpr size_t SMX = (size_t)(2 * N * XL + 2 * (N / 2 + 1) * XL + N) * sizeof(float2);
