@@ -339,7 +339,7 @@ def run_config3(args, rank, local_rank, world, barrier):
     dist.all_gather(parts, E)
     same = None
     if rank == 0:
-        s = device.Decon(small, 2)
+        s = device.Decon(small, 2, row_conv=False)  # the slab path runs the transposing plane kernels
         s.set_psf(0, pa)
         s.set_psf(1, pb)
         s.set_image(0, va)

@@ -263,8 +263,15 @@ int milb_decon_create(milb_decon_t **out, int nviews, const unsigned int *imSize
 		}
 	}
 	cudaError_t e = cudaSuccess;
-	if (h->fast) e = cudaMalloc(&h->S2, sizeof(float2) * h->nspec);
-	if (h->fast && e == cudaSuccess && h->Y == h->Z && milb_fast_ops(h->Y)->planes_fused) {
+	{
+		// Row convolution along Z (fft_fast.cuh k_zrow): in place, so S2 and both transposing passes go away.  Default where the
+		// Z length has a two-stage plan; MILB_ZROW=0 keeps the transposing kernels (the distributed path always uses those).
+		const char *ze = getenv("MILB_ZROW"), *pf = getenv("MILB_PLANES_FUSED");
+		h->zrow = h->fast && milb_fast_ops(h->Z)->conv_rows && milb_fast_ops(h->Y)->pass_fwd && !(ze && ze[0] == '0') && !(pf && pf[0] == '1') &&
+				  h->chunk_planes == 0;
+	}
+	if (h->fast && !h->zrow) e = cudaMalloc(&h->S2, sizeof(float2) * h->nspec);
+	if (h->fast && !h->zrow && e == cudaSuccess && h->Y == h->Z && milb_fast_ops(h->Y)->planes_fused) {
 		// Fused plane stage (one persistent launch per convolution, hand-overs L2-resident; fft_fast.cuh k_planes_fused).
 		// Measured on B200 at 512x512x256: DRAM traffic of the stage 1.75 -> 1.03 GB per convolution, but 375 us against
 		// 356 us for the three launches -- with one 8192-point tile per SM the tiles are bound by the SM (shared-memory pipe,
@@ -367,6 +374,7 @@ int milb_decon_plane_stage_fused(const milb_decon_t *h) { return (h && h->fuse.r
 int milb_decon_set_chunk_planes(milb_decon_t *h, int planes)
 {
 	if (!h || planes < 0) return MILB_ERR_ARG;
+	if (h->zrow) return MILB_OK; // the in-place row convolution has no transposed scratch to chunk: nothing to do
 	h->chunk_planes = planes;
 	return MILB_OK;
 }
@@ -400,6 +408,20 @@ static void plane_stage(milb_decon *h, const float2 *otf, float scale, cudaStrea
 	if (h->fast) {
 		// S [y][z] -Y fwd-> S2 [z][ky'] -Z fwd * otf Z inv-> S [ky'][z] -Y inv-> S [y][z], chunk by chunk in L2
 		const FastAxisOps *oy = milb_fast_ops(h->Y), *oz = milb_fast_ops(h->Z);
+		if (h->zrow) {
+			// S [y][z] -Y fwd-> S [ky'][z] -Z fwd * otf Z inv (rows, in place)-> S [ky'][z] -Y inv-> S [y][z]
+			const long long rows = (long long)planes * h->Y;
+			oy->pass_fwd(h->S, h->py.d_tw, h->Z, 0, planes, st);
+			if (otf) {
+				oz->conv_rows(h->S, otf, h->pz.d_tw, rows, st);
+				oy->pass_inv(h->S, h->py.d_tw, h->Z, 0, planes, st);
+				milb_count_launches(3);
+			} else {
+				oz->fwd_rows(h->S, h->pz.d_tw, rows, scale, st); // spectrum stays in S, rows in k_zrow's OTF order
+				milb_count_launches(2);
+			}
+			return;
+		}
 		if (otf && h->fuse.ring && h->chunk_planes == 0 && oy->planes_fused(h->S, otf, h->py.d_tw, &h->fuse, st)) {
 			milb_count_launches(1);
 			return;
@@ -499,7 +521,7 @@ static int gen_otf(milb_decon *h, float2 *dst, const float *d_psf, int px, int p
 	milb_count_launches(1);
 	launch_xpass<X_FWD_REAL>(h, h->E, nullptr, st);
 	plane_stage(h, nullptr, (float)(1.0 / (double)h->nreal), st);
-	MILB_CUDA_TRY(cudaMemcpyAsync(dst, h->fast ? h->S2 : h->S, sizeof(float2) * h->nspec, cudaMemcpyDeviceToDevice, st));
+	MILB_CUDA_TRY(cudaMemcpyAsync(dst, (h->fast && !h->zrow) ? h->S2 : h->S, sizeof(float2) * h->nspec, cudaMemcpyDeviceToDevice, st));
 	MILB_CUDA_TRY(cudaGetLastError());
 	return MILB_OK;
 }
@@ -676,7 +698,7 @@ int milb_decon_run_host(milb_decon_t *h, const float *const *h_img, float *h_out
 
 // Per-kernel timing of the loop (bench.py's roofline break-down): `reps` iterations of view 0 with CUDA
 // events around every launch; ms5 = average ms per launch of
-// {Y-forward (k_ypassT), Z-conv (k_zconvT), Y-inverse (k_ypassF), X ratio (k_xpassP), X update (k_xpassP)}.
+// {Y-forward (k_ypassF or k_ypassT), Z-conv (k_zrow or k_zconvT), Y-inverse (k_ypassF), X ratio (k_xpassP), X update (k_xpassP)}.
 // Power-of-two boxes only (the fast kernels); the estimate E is advanced like by milb_decon_run.
 int milb_decon_time_kernels(milb_decon_t *h, int reps, float *ms5, void *stream)
 {
@@ -698,6 +720,13 @@ int milb_decon_time_kernels(milb_decon_t *h, int reps, float *ms5, void *stream)
 				oy->planes_fused(h->S, otf, h->py.d_tw, &h->fuse, st);
 				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
 				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+			} else if (h->zrow) {
+				oy->pass_fwd(h->S, h->py.d_tw, h->Z, 0, planes, st);
+				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+				oz->conv_rows(h->S, otf, h->pz.d_tw, (long long)planes * h->Y, st);
+				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
+				oy->pass_inv(h->S, h->py.d_tw, h->Z, 0, planes, st);
 				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
 			} else {
 				oy->passT(h->S, h->S2, h->py.d_tw, h->Z, 0, planes, st);
@@ -756,7 +785,7 @@ int milb_decon_phase_correlate(milb_decon_t *h, const float *d_img1, const float
 	if (h->ix != h->X || h->iy != h->Y || h->iz != h->Z) return MILB_ERR_SIZE;
 	cudaStream_t st = (cudaStream_t)stream;
 	const size_t vb = sizeof(float) * h->nreal, sb = sizeof(float2) * h->nspec;
-	float2 *spec = h->fast ? h->S2 : h->S; // where a forward-only plane stage leaves the spectrum
+	float2 *spec = (h->fast && !h->zrow) ? h->S2 : h->S; // where a forward-only plane stage leaves the spectrum
 	MILB_CUDA_TRY(cudaMemcpyAsync(h->E, d_img1, vb, cudaMemcpyDeviceToDevice, st));
 	launch_xpass<X_FWD_REAL>(h, h->E, nullptr, st);
 	plane_stage(h, nullptr, 1.0f, st);

@@ -82,9 +82,40 @@ template <typename K> int optin(K k, size_t bytes)
 	return cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) == cudaSuccess ? 0 : 1;
 }
 
+// the row convolution along the contiguous axis (k_zrow), for the lengths with a two-stage plan
+template <int M, bool OK = ZPlan<M>::ok> struct ZRow {
+	static int setup() { return 0; }
+	static void conv(float2 *, const float2 *, const float2 *, long long, cudaStream_t) {}
+	static void fwd(float2 *, const float2 *, long long, float, cudaStream_t) {}
+};
+template <int M> struct ZRow<M, true> {
+	using G = ZRowGeom<M, ZPlan<M>::r0, ZPlan<M>::r1>;
+	static constexpr int NW = zrow_warps<M>();
+	static constexpr size_t SMZ = (size_t)(M + NW * zrow_warp_elems<M, G>()) * sizeof(float2);
+	static int setup() { return optin(k_zrow<M, true>, SMZ) | optin(k_zrow<M, false>, SMZ); }
+	static int grid(long long units)
+	{
+		const long long want = (units + NW - 1) / NW;
+		const int cap = (g_cap > 0 && g_cap < g_sms) ? g_cap : g_sms;
+		return (int)(want < cap ? want : cap);
+	}
+	static void conv(float2 *S, const float2 *otf, const float2 *tw, long long rows, cudaStream_t st)
+	{
+		const long long units = rows / G::PPW;
+		k_zrow<M, true><<<grid(units), NW * 32, SMZ, st>>>(S, otf, tw, units, 1.0f);
+	}
+	static void fwd(float2 *S, const float2 *tw, long long rows, float scale, cudaStream_t st)
+	{
+		const long long units = rows / G::PPW;
+		k_zrow<M, false><<<grid(units), NW * 32, SMZ, st>>>(S, nullptr, tw, units, scale);
+	}
+};
+
 int setup()
 {
 	int bad = 0;
+	bad |= ZRow<N>::setup();
+	bad |= optin(k_ypassF<N, PL, PT, false>, SMP2);
 	bad |= optin(k_xpassF<N, L, TXF, XF_FWD_REAL>, SM1);
 	bad |= optin(k_xpassF<N, L, TXF, XF_RATIO>, SM1);
 	bad |= optin(k_xpassF<N, L, TXF, XF_UPDATE>, SM1);
@@ -111,6 +142,7 @@ int setup()
 		}
 	}
 	if constexpr (kTmaTiles) {
+		bad |= optin(k_ypassF<N, PL, PT, false, false, true>, SMP2);
 		bad |= optin(k_ypassF<N, PL, PT, true, false, true>, SMP2);
 		bad |= optin(k_ypassF<N, PL, PT, true, true, true>, SMP2);
 		const char *e = getenv("MILB_TMA");
@@ -206,6 +238,22 @@ void pass_inv(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes,
 	k_ypassF<N, PL, PT, true><<<tiles < g_ctas ? tiles : g_ctas, PT, SMP2, st>>>(spec, tw, cols, plane0, nplanes);
 }
 
+void pass_fwd(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
+{
+	const int tiles = (cols / PL) * nplanes;
+	if constexpr (kTmaTiles) {
+		TileMap tm;
+		if (g_use_tma && make_tile_map(tm, spec, cols, (long long)N * (plane0 + nplanes))) {
+			k_ypassF<N, PL, PT, false, false, true><<<plane_grid(tiles), PT, SMP2, st>>>(spec, tw, cols, plane0, nplanes, PeerMap(), tm);
+			return;
+		}
+	}
+	k_ypassF<N, PL, PT, false><<<plane_grid(tiles), PT, SMP2, st>>>(spec, tw, cols, plane0, nplanes);
+}
+
+void conv_rows(float2 *spec, const float2 *otf, const float2 *tw, long long rows, cudaStream_t st) { ZRow<N>::conv(spec, otf, tw, rows, st); }
+void fwd_rows(float2 *spec, const float2 *tw, long long rows, float scale, cudaStream_t st) { ZRow<N>::fwd(spec, tw, rows, scale, st); }
+
 void convT(float2 *in, float2 *out, const float2 *otf, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
 {
 	const int tiles = (cols / PL) * nplanes;
@@ -255,6 +303,7 @@ const FastAxisOps *MILB_CAT(milb_fast_ops_, MILB_FAST_N)()
 	static FastAxisOps ops;
 	ops.n = N; ops.lanes = L; ops.xlanes = XL > L ? XL : L; ops.setup = setup; ops.xpass = xpass; ops.xpass_cols = xpass_cols; ops.passT = passT; ops.pass_inv = pass_inv;
 	ops.convT = convT; ops.fwd_scaled = fwd_scaled; ops.planes_fused = kPow2 ? planes_fused : nullptr;
+	ops.pass_fwd = pass_fwd; ops.conv_rows = ZPlan<N>::ok ? conv_rows : nullptr; ops.fwd_rows = ZPlan<N>::ok ? fwd_rows : nullptr;
 	ops.xpass_peer = kPow2 ? xpass_peer : nullptr; ops.pass_inv_peer = kPow2 ? pass_inv_peer : nullptr; ops.grid_cap = &g_cap;
 	return &ops;
 }

@@ -28,6 +28,7 @@ struct milb_decon {
 	float *E = nullptr;
 	float *stage = nullptr;        // staging for host uploads / crop output (nreal floats)
 	float2 *S = nullptr;
+	bool zrow = false;             // fast path: Z convolution along the contiguous axis in place (k_zrow), no S2, OTFs in its per-row order
 	float2 *S2 = nullptr;          // fast path: transposed planes [kx][z][ky']
 	float2 *otf[2] = {nullptr, nullptr}, *otf_bp[2] = {nullptr, nullptr};
 	PlaneFuse fuse;                // fast path, square planes: state of the fused plane stage (ring == nullptr: three launches)

@@ -23,6 +23,7 @@
 #include "decon_fast.h"
 #include "fft_core.h"
 #include "plane_sched.h"
+#include "zrow_core.h"
 
 #define SMALLVALUE_FAST 0.01f // src/api_subfunc.cu:24
 
@@ -741,6 +742,105 @@ k_zconvT(float2 *__restrict__ in, float2 *__restrict__ out, const float2 *__rest
 		}
 		__syncthreads();
 		store_transposed<N, L, T>(tile2, out + (long long)(t / tpp + plane0) * N * Yc + (long long)(t % tpp) * L * N, N);
+	}
+}
+
+// ------------------------------------------------------------------------------------------------
+// Z convolution along the CONTIGUOUS axis, in place, one warp per group of rows (zrow_core.h):
+//     S [kx][ky'][z]  --Z forward, * otf, Z inverse-->  S [kx][ky'][z]
+// replaces k_ypassT's transposed output + k_zconvT's two shared-memory transpositions: the Y passes before and after it
+// are both the plain in-place k_ypassF.  A warp owns PPW = 32 / TP whole rows (contiguous in HBM), so
+//   * the rows arrive by ONE bulk copy of the copy engine (cp.async.bulk + mbarrier per landing buffer, double-buffered per
+//     warp): no LDGSTS instructions, no address registers, and the next rows fly while these are transformed;
+//   * the two exchanges between the stages are warp-private (__syncwarp): no CTA barrier anywhere in the loop, the warps of
+//     an SM run out of phase and keep the FP32 pipe, the shared-memory pipe and the memory system busy at the same time;
+//   * the result leaves straight from the registers of the last inverse stage (lanes along z: 128-byte segments) and the
+//     OTF comes straight into registers (kept in the per-row order the middle stage reads it in, zrow_otf_index), issued
+//     before stage 0 so that its latency hides behind the butterflies.
+// Shared-memory traffic per point: 6 eight-byte accesses (k_zconvT: 12); HBM traffic: the same 8 + 8 + 8 bytes.
+// !CONV: forward only, scaled, the row rewritten in the OTF order (OTF generation, phase correlation).
+template <int N> struct ZPlan {
+	static constexpr bool ok = FastPlan<N>::S == 2;
+	static constexpr int r0 = FastPlan<N>::r0, r1 = FastPlan<N>::r1;
+};
+template <> struct ZPlan<1024> { // the row kernel's own two-stage plan (the Z axis' position order is private to it and its OTFs)
+	static constexpr bool ok = true;
+	static constexpr int r0 = 32, r1 = 32;
+};
+// Long rows (N >= 512, 8 KB per warp and landing buffer): ONE landing buffer per warp, refilled as soon as stage 0 has read it
+// (the copy has the middle and the inverse stage to land), which leaves room for 12 warps per SM instead of 8 -- with
+// 2 warps per scheduler the row convolution measured 334 us at 512^3 (0.74 of the HBM peak), latency-bound.  Shorter rows:
+// 16 warps, two landing buffers each.
+template <int N> __host__ __device__ constexpr bool zrow_double() { return N < 512; }
+template <int N> __host__ __device__ constexpr int zrow_warps() { return N >= 512 ? 12 : 16; }
+template <int N, class G> __host__ __device__ constexpr int zrow_warp_elems() { return (zrow_double<N>() ? 2 : 1) * G::PPW * G::LS + G::PPW * G::ES; }
+
+__device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(smem_dst)), "l"(gsrc),
+				 "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int N, bool CONV>
+__global__ void __launch_bounds__(zrow_warps<N>() * 32, 1)
+k_zrow(float2 *__restrict__ S, const float2 *__restrict__ otf, const float2 *__restrict__ g_tw, long long nunits, float scale)
+{
+	using G = ZRowGeom<N, ZPlan<N>::r0, ZPlan<N>::r1>;
+	constexpr int NW = zrow_warps<N>();
+	constexpr bool DB = zrow_double<N>();
+	constexpr int LAND = G::PPW * G::LS; // one landing buffer
+	extern __shared__ __align__(128) float2 sm[];
+	__shared__ __align__(8) unsigned long long bars[NW][2];
+	const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+	const int pen = lane / G::TP, j = lane % G::TP;
+	float2 *tws = sm;
+	float2 *land0 = sm + N + warp * zrow_warp_elems<N, G>();
+	float2 *ex = land0 + (DB ? 2 : 1) * LAND + pen * G::ES;
+	for (int i = threadIdx.x; i < N; i += NW * 32) tws[i] = g_tw[(i / G::r1) * (i % G::r1)];
+	if (lane == 0) {
+		mbar_init(&bars[warp][0], 1);
+		mbar_init(&bars[warp][1], 1);
+		asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+	}
+	__syncthreads();
+	const long long stride = (long long)gridDim.x * NW;
+	auto issue = [&](long long u, int buf) { // lane 0: rows u * PPW .. + PPW - 1 -> landing buffer `buf`
+		asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+		mbar_expect_tx(&bars[warp][buf], (unsigned)(G::PPW * N * sizeof(float2)));
+		if constexpr (G::LS == N) {
+			bulk_load_1d(land0 + buf * LAND, S + u * G::PPW * N, (unsigned)(G::PPW * N * sizeof(float2)), &bars[warp][buf]);
+		} else {
+#pragma unroll
+			for (int p = 0; p < G::PPW; p++)
+				bulk_load_1d(land0 + buf * LAND + p * G::LS, S + (u * G::PPW + p) * N, (unsigned)(N * sizeof(float2)), &bars[warp][buf]);
+		}
+	};
+	long long u = (long long)blockIdx.x * NW + warp;
+	if (u < nunits && lane == 0) issue(u, 0);
+	for (int it = 0; u < nunits; u += stride, it++) {
+		const int cur = DB ? (it & 1) : 0;
+		__syncwarp(); // every lane is done with the exchange buffer (previous rows) and, DB, with the other landing buffer
+		if constexpr (DB)
+			if (u + stride < nunits && lane == 0) issue(u + stride, cur ^ 1);
+		float2 *row = S + (u * G::PPW + pen) * N;
+		float2 o[G::B1][G::r1];
+		if constexpr (CONV) {
+			const float2 *orow = otf + (u * G::PPW + pen) * N;
+#pragma unroll
+			for (int i = 0; i < G::B1; i++)
+#pragma unroll
+				for (int k2 = 0; k2 < G::r1; k2++) o[i][k2] = __ldg(orow + zrow_otf_index<G>(j + G::TP * i, k2));
+		}
+		mbar_wait(&bars[warp][cur], DB ? ((it >> 1) & 1) : (it & 1));
+		zrow_fwd0<G>(j, land0 + cur * LAND + pen * G::LS, ex, tws);
+		__syncwarp();
+		if constexpr (!DB)
+			if (u + stride < nunits && lane == 0) issue(u + stride, 0); // the landing buffer is free again: refill it behind the other stages
+		zrow_mid<G, CONV>(j, ex, o, row, scale);
+		if constexpr (CONV) {
+			__syncwarp();
+			zrow_inv0<G>(j, ex, tws, row);
+		}
 	}
 }
 

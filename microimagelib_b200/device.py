@@ -7,6 +7,7 @@ float32 ``(slices, H, W)``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 
@@ -57,12 +58,24 @@ def launch_count() -> int:
 class Decon:
     """Richardson-Lucy state for one image size: OTFs, views, estimate (milb_decon_t)."""
 
-    def __init__(self, im_shape, nviews=1):
+    def __init__(self, im_shape, nviews=1, row_conv=None):
+        """row_conv: None = the library's default (the in-place row convolution k_zrow where the Z length has a two-stage
+        plan); False = the transposing plane kernels (k_ypassT / k_zconvT), which the distributed path always uses."""
         self.lib = _lib.load()
         self.im_shape = tuple(int(s) for s in im_shape)
         self.nviews = nviews
         self._h = C.c_void_p()
-        _check(self.lib.milb_decon_create(C.byref(self._h), nviews, _size(self.im_shape)), "milb_decon_create")
+        old = os.environ.get("MILB_ZROW")
+        if row_conv is not None:
+            os.environ["MILB_ZROW"] = "1" if row_conv else "0"
+        try:
+            _check(self.lib.milb_decon_create(C.byref(self._h), nviews, _size(self.im_shape)), "milb_decon_create")
+        finally:
+            if row_conv is not None:
+                if old is None:
+                    os.environ.pop("MILB_ZROW", None)
+                else:
+                    os.environ["MILB_ZROW"] = old
         fs = (C.c_uint * 3)()
         self.lib.milb_decon_fft_size(self._h, fs)
         self.fft_shape = (int(fs[2]), int(fs[1]), int(fs[0]))

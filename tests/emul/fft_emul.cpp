@@ -2,7 +2,56 @@
 // Test code: builds with plain g++, no CUDA.
 #include "../../microimagelib_b200/csrc/fft_plan.h"
 #include "../../microimagelib_b200/csrc/plane_sched.h"
+#include "../../microimagelib_b200/csrc/zrow_core.h"
+#include <math.h>
+#include <vector>
 #include <string.h>
+
+
+// k_zrow's lanes replayed one after the other for ONE pencil (zrow_core.h): conv = 1: row <- F^-1(F(row) * otf) with otf in the
+// kernel's per-row order; conv = 0: row <- F(row) * scale in that order.  Also reports whether any 16-lane group of a 64-bit
+// shared access touched the same 8-byte bank twice (the layout's conflict-freedom claim) through *conflicts.
+template <class G> static int zrow_run(float *data, const float *otf, int conv, float scale, int *conflicts)
+{
+	std::vector<float2> tws(G::N), land(G::PPW * G::LS), ex(G::PPW * G::ES);
+	for (int k1 = 0; k1 < G::r0; k1++)
+		for (int b = 0; b < G::r1; b++) {
+			const double ang = -2.0 * M_PI * (double)(b * k1) / G::N;
+			tws[k1 * G::r1 + b] = make_float2((float)cos(ang), (float)sin(ang));
+		}
+	float2 *row = (float2 *)data;
+	for (int i = 0; i < G::N; i++) land[i] = row[i];
+	float2 o[G::B1][G::r1];
+	for (int j = 0; j < G::TP; j++) zrow_fwd0<G>(j, land.data(), ex.data(), tws.data());
+	for (int j = 0; j < G::TP; j++) {
+		if (conv)
+			for (int i = 0; i < G::B1; i++)
+				for (int k2 = 0; k2 < G::r1; k2++) o[i][k2] = ((const float2 *)otf)[zrow_otf_index<G>(j + G::TP * i, k2)];
+		if (conv) zrow_mid<G, true>(j, ex.data(), o, row, scale);
+		else zrow_mid<G, false>(j, ex.data(), o, row, scale);
+	}
+	if (conv)
+		for (int j = 0; j < G::TP; j++) zrow_inv0<G>(j, ex.data(), tws.data(), row);
+	// bank check: lanes of one 16-lane group = (pencil, j) pairs; word address mod 16 must be distinct within the group
+	int bad = 0;
+	auto group_ok = [&](auto addr_of /* (pencil, j) -> word index */) {
+		for (int g = 0; g < 2; g++) {
+			unsigned seen = 0;
+			for (int l = 16 * g; l < 16 * g + 16; l++) {
+				const int pen = l / G::TP, j = l % G::TP;
+				const unsigned bit = 1u << (addr_of(pen, j) & 15);
+				if (seen & bit) bad++;
+				seen |= bit;
+			}
+		}
+	};
+	for (int a = 0; a < G::r0; a++) group_ok([&](int pen, int j) { return pen * G::LS + G::r1 * a + j; });                  // landing reads
+	for (int k1 = 0; k1 < G::r0; k1++) group_ok([&](int pen, int j) { return pen * G::ES + G::ex(k1, j); });               // stage-0 writes
+	for (int k2 = 0; k2 < G::r1; k2++) group_ok([&](int pen, int j) { return pen * G::ES + G::ex(j, k2); });               // middle reads
+	*conflicts = bad;
+	return 0;
+}
+
 
 extern "C" {
 
@@ -115,5 +164,24 @@ int emul_bfly(int r, float *data /* r complex, interleaved */, int inverse)
 	default: return -1;
 	}
 	return 0;
+}
+
+int emul_zrow(int n, float *data, const float *otf, int conv, float scale, int *conflicts)
+{
+	switch (n) {
+	case 64: return zrow_run<ZRowGeom<64, 8, 8>>(data, otf, conv, scale, conflicts);
+	case 128: return zrow_run<ZRowGeom<128, 8, 16>>(data, otf, conv, scale, conflicts);
+	case 256: return zrow_run<ZRowGeom<256, 16, 16>>(data, otf, conv, scale, conflicts);
+	case 512: return zrow_run<ZRowGeom<512, 16, 32>>(data, otf, conv, scale, conflicts);
+	case 1024: return zrow_run<ZRowGeom<1024, 32, 32>>(data, otf, conv, scale, conflicts);
+	default: return -1;
+	}
+}
+// position r1 * k1 + k2 -> frequency k1 + r0 * k2, and its index in the OTF row
+int emul_zrow_maps(int n, int r0, int r1, int *freq_of_otf_index)
+{
+	for (int k1 = 0; k1 < r0; k1++)
+		for (int k2 = 0; k2 < r1; k2++) freq_of_otf_index[k2 * r0 + k1] = k1 + r0 * k2;
+	return n == r0 * r1 ? 0 : -1;
 }
 }

@@ -87,3 +87,30 @@ def test_odd_radix_register_butterflies(lib, r):
         assert lib.emul_bfly_odd(r, d.ctypes.data_as(F), inverse) == 0
         ref = np.fft.ifft(x.astype(np.complex128)) * r if inverse else np.fft.fft(x.astype(np.complex128))
         assert np.abs(d - ref).max() <= 1e-6 * np.abs(ref).max()
+
+
+ZROW = {64: (8, 8), 128: (8, 16), 256: (16, 16), 512: (16, 32), 1024: (32, 32)}
+
+
+@pytest.mark.parametrize("n", sorted(ZROW))
+def test_row_convolution_lanes(lib, n):
+    """k_zrow's per-lane stage code (csrc/zrow_core.h) replayed lane by lane: the forward-only mode yields numpy's FFT in the
+    kernel's per-row OTF order, the convolution mode with that OTF equals the circular convolution, and no 16-lane group of a
+    shared-memory access hits a bank twice."""
+    r0, r1 = ZROW[n]
+    rng = np.random.default_rng(n + 7)
+    freq = np.zeros(n, np.int32)
+    assert lib.emul_zrow_maps(n, r0, r1, freq.ctypes.data_as(I)) == 0
+    assert sorted(freq.tolist()) == list(range(n))
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    k = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    conflicts = C.c_int(-1)
+    K = k.copy()
+    assert lib.emul_zrow(n, K.ctypes.data_as(F), None, 0, C.c_float(1.0 / n), C.byref(conflicts)) == 0
+    assert conflicts.value == 0
+    ref_K = np.fft.fft(k.astype(np.complex128)) / n
+    assert np.linalg.norm(K - ref_K[freq]) / np.linalg.norm(ref_K) < 5e-7
+    d = x.copy()
+    assert lib.emul_zrow(n, d.ctypes.data_as(F), K.ctypes.data_as(F), 1, C.c_float(1.0), C.byref(conflicts)) == 0
+    ref = np.fft.ifft(np.fft.fft(x.astype(np.complex128)) * np.fft.fft(k.astype(np.complex128)))
+    assert np.linalg.norm(d - ref) / np.linalg.norm(ref) < 1e-6
