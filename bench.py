@@ -226,7 +226,7 @@ def measure_traffic(shape, timeout_s=240):
     log = os.path.join(tmp, "t.csv")
     env = dict(os.environ, PROBE_ITERS="3", PROBE_SHAPE=",".join(str(s) for s in shape), PROBE_NOISE="0")
     cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum", "--clock-control", "none",
-           "-k", "regex:k_planes_fused|k_ypassT|k_zconvT|k_ypassF|k_xpassP|k_xpass|k_ypass|k_zpass", "--csv", "--log-file", log,
+           "-k", "regex:k_planes_fused|k_ypassT|k_zconvT|k_zrow|k_ypassF|k_xpassP|k_xpass|k_ypass|k_zpass", "--csv", "--log-file", log,
            sys.executable, os.path.join(ROOT, "scripts", "prof_run.py")]
     try:
         r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=timeout_s)
@@ -339,7 +339,7 @@ def run_config3(args, rank, local_rank, world, barrier):
     dist.all_gather(parts, E)
     same = None
     if rank == 0:
-        s = device.Decon(small, 2, row_conv=False)  # the slab path runs the transposing plane kernels
+        s = device.Decon(small, 2)
         s.set_psf(0, pa)
         s.set_psf(1, pb)
         s.set_image(0, va)
@@ -524,6 +524,9 @@ def main():
             nspec = float(d.fft_shape[0] // 2 + 1) * d.fft_shape[1] * d.fft_shape[2]
             if fused:
                 rows = [("k_planes_fused (Y forward, Z forward * OTF, Z inverse, Y inverse; intermediates in L2)", 24 * nspec, kms[0], 2)]
+            elif d.row_convolution():
+                rows = [("k_ypassF (Y forward, in place)", 16 * nspec, kms[0], 2), ("k_zrow (Z forward * OTF, Z inverse, rows in place)", 24 * nspec, kms[1], 2),
+                        ("k_ypassF (Y inverse)", 16 * nspec, kms[2], 2)]
             else:
                 rows = [("k_ypassT (Y forward, transposing)", 16 * nspec, kms[0], 2), ("k_zconvT (Z forward * OTF, Z inverse)", 24 * nspec, kms[1], 2),
                         ("k_ypassF (Y inverse)", 16 * nspec, kms[2], 2)]

@@ -86,6 +86,11 @@ int milb_decon_set_chunk_planes(milb_decon_t *h, int planes);
 /* 1 if the loop runs the plane stage of a convolution (cufftExecR2C's Y/Z part, multicomplex3Dkernel, cufftExecC2R's
  * Y/Z part; src/api_subfunc.cu:3406-3413) as ONE persistent launch whose intermediates stay in L2 (square planes) */
 int milb_decon_plane_stage_fused(const milb_decon_t *h);
+/* 1 if the Z part of that stage (the Z transforms of cufftExecR2C / cufftExecC2R around multicomplex3Dkernel,
+ * src/api_subfunc.cu:3406-3413) runs in place along the contiguous axis (k_zrow, warp-private rows) between two plain Y
+ * passes; 0 if it runs on transposed planes (k_ypassT / k_zconvT).  Default where the Z length has a two-stage plan
+ * (64, 128, 256, 512, 1024); MILB_ZROW=0 at handle creation selects the transposing kernels. */
+int milb_decon_row_convolution(const milb_decon_t *h);
 
 /* yardstick: the same loop through cuFFT + unfused element-wise kernels, i.e. the reference's own
  * launch structure (src/api_subfunc.cu:3404-3416) on this GPU.  Used by bench.py only. */

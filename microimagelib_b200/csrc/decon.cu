@@ -265,7 +265,7 @@ int milb_decon_create(milb_decon_t **out, int nviews, const unsigned int *imSize
 	cudaError_t e = cudaSuccess;
 	{
 		// Row convolution along Z (fft_fast.cuh k_zrow): in place, so S2 and both transposing passes go away.  Default where the
-		// Z length has a two-stage plan; MILB_ZROW=0 keeps the transposing kernels (the distributed path always uses those).
+		// Z length has a two-stage plan; MILB_ZROW=0 keeps the transposing kernels.
 		const char *ze = getenv("MILB_ZROW"), *pf = getenv("MILB_PLANES_FUSED");
 		h->zrow = h->fast && milb_fast_ops(h->Z)->conv_rows && milb_fast_ops(h->Y)->pass_fwd && !(ze && ze[0] == '0') && !(pf && pf[0] == '1') &&
 				  h->chunk_planes == 0;
@@ -370,6 +370,8 @@ int milb_decon_fft_size(const milb_decon_t *h, unsigned int *fftSize)
 }
 
 int milb_decon_plane_stage_fused(const milb_decon_t *h) { return (h && h->fuse.ring && h->chunk_planes == 0) ? 1 : 0; }
+
+int milb_decon_row_convolution(const milb_decon_t *h) { return (h && h->zrow) ? 1 : 0; }
 
 int milb_decon_set_chunk_planes(milb_decon_t *h, int planes)
 {

@@ -28,6 +28,7 @@ struct milb_dslab {
 	cudaStream_t side = nullptr;
 	cudaEvent_t ev_z[8] = {}, ev_done = nullptr;
 	int chunks = 4, side_ctas = 48;
+	bool zrow = false; // Z convolution by the in-place row kernel (k_zrow) between two plain Y passes; S2 then only receives OTFs
 };
 
 static int upload_tw(float2 **dst, int n)
@@ -49,6 +50,10 @@ extern "C" int milb_dslab_create(milb_dslab_t **out, const unsigned int *fftSize
 	if (fx->setup() || fy->setup() || fz->setup()) return MILB_ERR_CUDA;
 	milb_dslab *h = new milb_dslab();
 	h->X = X; h->Y = Y; h->Z = Z; h->y0 = y0; h->ny = ny; h->np = planes_local;
+	{
+		const char *ze = getenv("MILB_ZROW");
+		h->zrow = fz->conv_rows && fy->pass_fwd && !(ze && ze[0] == '0');
+	}
 	int rc;
 	if ((rc = upload_tw(&h->tw[0], X)) || (rc = upload_tw(&h->tw[1], Y)) || (rc = upload_tw(&h->tw[2], Z))) {
 		milb_dslab_destroy(h);
@@ -88,13 +93,29 @@ extern "C" int milb_dslab_xpass(milb_dslab_t *h, int mode, float *vol_io, const 
 
 // plane passes on my np whole planes: S [np][Y][Z] in place (S2 [np][Z][Y] is scratch).
 // otf != NULL: S <- F^-1(F(S) * otf), otf in S2's layout.  otf == NULL: forward only, the scaled
-// spectrum is left in S2 (OTF generation).
+// spectrum is left in S2 (OTF generation).  With the row convolution (h->zrow) everything happens in place in S and the
+// OTF layout is k_zrow's per-row order; the forward-only spectrum is still handed over in S2.
 extern "C" int milb_dslab_planes(milb_dslab_t *h, void *S, void *S2, const void *otf, float scale, void *stream)
 {
 	if (!h || !S || !S2) return MILB_ERR_ARG;
 	if (h->np == 0) return MILB_OK;
 	cudaStream_t st = (cudaStream_t)stream;
 	const FastAxisOps *oy = milb_fast_ops(h->Y), *oz = milb_fast_ops(h->Z);
+	if (h->zrow) {
+		const long long rows = (long long)h->np * h->Y;
+		oy->pass_fwd((float2 *)S, h->tw[1], h->Z, 0, h->np, st);
+		if (otf) {
+			oz->conv_rows((float2 *)S, (const float2 *)otf, h->tw[2], rows, st);
+			oy->pass_inv((float2 *)S, h->tw[1], h->Z, 0, h->np, st);
+			milb_count_launches(3);
+		} else {
+			oz->fwd_rows((float2 *)S, h->tw[2], rows, scale, st);
+			MILB_CUDA_TRY(cudaMemcpyAsync(S2, S, sizeof(float2) * rows * h->Z, cudaMemcpyDeviceToDevice, st));
+			milb_count_launches(2);
+		}
+		MILB_CUDA_TRY(cudaGetLastError());
+		return MILB_OK;
+	}
 	oy->passT((const float2 *)S, (float2 *)S2, h->tw[1], h->Z, 0, h->np, st);
 	if (otf) {
 		oz->convT((float2 *)S2, (float2 *)S, (const float2 *)otf, h->tw[2], h->Y, 0, h->np, st);
@@ -215,9 +236,15 @@ extern "C" int milb_dslab_planes_peer(milb_dslab_t *h, void *S, void *S2, const 
 		cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	}
 	const int C = (h->chunks <= h->np) ? h->chunks : h->np;
+	const long long pe = (long long)h->Y * h->Z; // elements per plane
 	if (C <= 1 || h->side_ctas <= 0 || h->side_ctas >= sms) {
-		oy->passT((const float2 *)S, (float2 *)S2, h->tw[1], h->Z, 0, h->np, st);
-		oz->convT((float2 *)S2, (float2 *)S, (const float2 *)otf, h->tw[2], h->Y, 0, h->np, st);
+		if (h->zrow) {
+			oy->pass_fwd((float2 *)S, h->tw[1], h->Z, 0, h->np, st);
+			oz->conv_rows((float2 *)S, (const float2 *)otf, h->tw[2], (long long)h->np * h->Y, st);
+		} else {
+			oy->passT((const float2 *)S, (float2 *)S2, h->tw[1], h->Z, 0, h->np, st);
+			oz->convT((float2 *)S2, (float2 *)S, (const float2 *)otf, h->tw[2], h->Y, 0, h->np, st);
+		}
 		oy->pass_inv_peer((const float2 *)S, h->tw[1], h->Z, 0, h->np, &h->to_slabs, st);
 		milb_count_launches(3);
 		MILB_CUDA_TRY(cudaGetLastError());
@@ -235,8 +262,13 @@ extern "C" int milb_dslab_planes_peer(milb_dslab_t *h, void *S, void *S2, const 
 	for (int c = 0; c < C; c++) {
 		const int p0 = (int)((long long)h->np * c / C), p1 = (int)((long long)h->np * (c + 1) / C);
 		*cap_y = *cap_z = (c == 0) ? 0 : sms - h->side_ctas;
-		oy->passT((const float2 *)S, (float2 *)S2, h->tw[1], h->Z, p0, p1 - p0, st);
-		oz->convT((float2 *)S2, (float2 *)S, (const float2 *)otf, h->tw[2], h->Y, p0, p1 - p0, st);
+		if (h->zrow) {
+			oy->pass_fwd((float2 *)S, h->tw[1], h->Z, p0, p1 - p0, st);
+			oz->conv_rows((float2 *)S + p0 * pe, (const float2 *)otf + p0 * pe, h->tw[2], (long long)(p1 - p0) * h->Y, st);
+		} else {
+			oy->passT((const float2 *)S, (float2 *)S2, h->tw[1], h->Z, p0, p1 - p0, st);
+			oz->convT((float2 *)S2, (float2 *)S, (const float2 *)otf, h->tw[2], h->Y, p0, p1 - p0, st);
+		}
 		MILB_CUDA_TRY(cudaEventRecord(h->ev_z[c], st));
 		MILB_CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_z[c], 0));
 		*cap_y = (c == C - 1) ? 0 : h->side_ctas;

@@ -815,13 +815,16 @@ k_zrow(float2 *__restrict__ S, const float2 *__restrict__ otf, const float2 *__r
 				bulk_load_1d(land0 + buf * LAND + p * G::LS, S + (u * G::PPW + p) * N, (unsigned)(N * sizeof(float2)), &bars[warp][buf]);
 		}
 	};
-	long long u = (long long)blockIdx.x * NW + warp;
-	if (u < nunits && lane == 0) issue(u, 0);
-	for (int it = 0; u < nunits; u += stride, it++) {
+	// Rows are walked from the LAST plane down: the Y-forward pass in front of this kernel walks the planes upwards, so the
+	// rows it wrote last are still in L2 when this kernel starts with them, and the Y-inverse pass behind it (upwards again)
+	// starts with the rows this kernel wrote last.
+	long long u = nunits - 1 - ((long long)blockIdx.x * NW + warp);
+	if (u >= 0 && lane == 0) issue(u, 0);
+	for (int it = 0; u >= 0; u -= stride, it++) {
 		const int cur = DB ? (it & 1) : 0;
 		__syncwarp(); // every lane is done with the exchange buffer (previous rows) and, DB, with the other landing buffer
 		if constexpr (DB)
-			if (u + stride < nunits && lane == 0) issue(u + stride, cur ^ 1);
+			if (u - stride >= 0 && lane == 0) issue(u - stride, cur ^ 1);
 		float2 *row = S + (u * G::PPW + pen) * N;
 		float2 o[G::B1][G::r1];
 		if constexpr (CONV) {
@@ -835,7 +838,7 @@ k_zrow(float2 *__restrict__ S, const float2 *__restrict__ otf, const float2 *__r
 		zrow_fwd0<G>(j, land0 + cur * LAND + pen * G::LS, ex, tws);
 		__syncwarp();
 		if constexpr (!DB)
-			if (u + stride < nunits && lane == 0) issue(u + stride, 0); // the landing buffer is free again: refill it behind the other stages
+			if (u - stride >= 0 && lane == 0) issue(u - stride, 0); // the landing buffer is free again: refill it behind the other stages
 		zrow_mid<G, CONV>(j, ex, o, row, scale);
 		if constexpr (CONV) {
 			__syncwarp();
@@ -1161,6 +1164,24 @@ template <int N, int L, int T> constexpr int xpassP_ctas()
 //   AL aux landing buffer      N x L float2         (A for RATIO, E for UPDATE; consumed by stage 0)
 // As soon as a landing buffer has been consumed the next tile's rows are already requested, so the
 // spectrum and aux loads of tile t+1 overlap the butterflies of tile t.
+// MILB_X_FOLD (default): for the two-stage plans on 16-lane tiles (N = 256, 512) the merge of the half spectrum is folded into
+// the loads of the inverse radix-r1 stage and the split into the epilogue of the forward radix-r1 stage:
+//   * a thread of that stage owns row k1 of the position-ordered pencil = frequencies k1 + r0 * k2; for k2 < r1 / 2 they are
+//     rows of the half spectrum themselves, the others are mirrors N - k of rows (r0 - k1) + r0 * (r1 - 1 - k2), so the thread
+//     builds its 32 inputs straight from the landing buffer (one float4 each) -- no merge pass over a working tile;
+//   * after the forward stage the mirror partner C[N - k] of a thread's outputs sits in the registers of the thread that owns
+//     row r0 - k1.  Rows (k1, r0 - k1) are given to the two halves of ONE warp (rows 0 and r0 / 2, which mirror onto themselves,
+//     share warp 0), so the partners arrive by __shfl_xor and the A / B rows leave straight from registers -- no split pass.
+// Per tile that is 3 CTA barriers instead of 6 and 9 instead of 13 shared-memory accesses per point.
+#ifndef MILB_X_FOLD
+#define MILB_X_FOLD 1
+#endif
+template <int R0> __device__ __forceinline__ int xfold_row(int slot)
+{
+	const int w = slot >> 1, h = slot & 1;
+	return w == 0 ? (h ? R0 / 2 : 0) : (h ? R0 - w : w);
+}
+
 template <int N, int L, int T, int MODE, bool PEER = false>
 __global__ void __launch_bounds__(T, xpassP_ctas<N, L, T>())
 k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M, int ntiles,
@@ -1181,6 +1202,9 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 	// structured merge / split indexing (see the merge loop): needs whole row blocks per iteration
 	constexpr int RIT = T / L, NB = N / RIT, NIT = half / RIT;
 	constexpr bool kStructured = (T % L == 0) && ((RIT & (RIT - 1)) == 0) && (RIT * NB == N) && (NIT * RIT == half) && (RIT <= half);
+	constexpr int R1 = P::r1;
+	constexpr bool kFold = MILB_X_FOLD && (P::S == 2) && (L == 16) && (R0 * L <= T);
+	const int frow = xfold_row<R0>(threadIdx.x / L);               // kFold: my row of the radix-r1 stages (threads < R0 * L)
 	const int k0 = threadIdx.x / L, lane0 = threadIdx.x % L;
 	const int pA0 = fast_pos<N>(k0) * L + lane0;                    // position of row k0 (+ lane)
 	const int pB0 = fast_pos<N>((RIT - k0) % RIT) * L + lane0;      // position of the low bits of N - k0 (+ lane)
@@ -1205,6 +1229,32 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 		const int tn = t + gridDim.x;
 		cp_async_wait<1>(); // spectrum of this tile landed (the aux group may still be in flight)
 		__syncthreads();
+		if constexpr (kFold) {
+			if (threadIdx.x < R0 * L) {
+				float2 v[R1];
+				const float4 *sd = SL + frow * L + lane0;                         // rows k1 + R0 * k2, k2 < R1 / 2
+				const float4 *sm_ = SL + (frow ? R0 - frow : R0) * L + lane0;     // mirrors: rows mb + R0 * (R1 - 1 - k2), k2 >= R1 / 2
+#pragma unroll
+				for (int k2 = 0; k2 < R1 / 2; k2++) {
+					float4 ab = sd[k2 * R0 * L];
+					if (k2 == 0 && frow == 0) { ab.y = 0.f; ab.w = 0.f; }          // k = 0 pairs with itself
+					v[k2] = make_float2(ab.x - ab.w, ab.y + ab.z);                  // merge_pair: C[k]
+				}
+#pragma unroll
+				for (int k2 = R1 / 2; k2 < R1; k2++) {
+					float4 ab = sm_[(R1 - 1 - k2) * R0 * L];
+					if (k2 == R1 / 2 && frow == 0) { ab.y = 0.f; ab.w = 0.f; }     // k = N / 2 pairs with itself
+					v[k2] = make_float2(ab.x + ab.w, ab.z - ab.y);                  // merge_pair: C[N - k]
+				}
+				fbfly<R1, true>(v);
+#pragma unroll
+				for (int b = 0; b < R1; b++) W[(R1 * frow + b) * L + lane0] = v[b];
+			}
+			cp_async_wait<0>(); // aux of this tile landed
+			__syncthreads();    // W complete, SL consumed, everybody's aux rows visible
+			if (tn < ntiles) load_spec(tn);
+			cp_async_commit();
+		} else {
 		if constexpr (kStructured) {
 			// rows k = k0 + RIT*i: with power-of-two radices the position is a bit permutation, so
 			// pos(k) = pos(k0) + pos(RIT*i) and pos(N-k) = pos(m0) + pos(RIT*(NB-1-i)) (m0 = RIT - k0; the
@@ -1245,6 +1295,7 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 		inv_head_smem<N, L, T, false>(W, tw);
 		cp_async_wait<1>(); // aux of this tile landed (the next spectrum may still be in flight)
 		__syncthreads();    // one barrier for both: the last inverse stage's writes to W and everybody's aux rows
+		}
 		float2 v[R0];
 #pragma unroll
 		for (int j = 0; j < R0; j++) v[j] = W[(q + j * M0) * L + lane];
@@ -1279,6 +1330,32 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 		if (tn < ntiles) load_aux(tn);
 		cp_async_commit();
 		if (MODE == XF_UPDATE_LAST) continue;
+		if constexpr (kFold) {
+			if (threadIdx.x < R0 * L) {
+				float2 c[R1];
+#pragma unroll
+				for (int b = 0; b < R1; b++) c[b] = W[(R1 * frow + b) * L + lane0];
+				fbfly<R1, false>(c);                                               // c[k2] = C[frow + R0 * k2]
+				if (threadIdx.x >= 2 * L) {                                        // rows (k1, R0 - k1): the mirror partner is the other half-warp
+#pragma unroll
+					for (int k2 = 0; k2 < R1 / 2; k2++) {
+						float2 cn;
+						cn.x = __shfl_xor_sync(0xffffffffu, c[R1 - 1 - k2].x, 16);
+						cn.y = __shfl_xor_sync(0xffffffffu, c[R1 - 1 - k2].y, 16);
+						spec_row_dst<PEER>(spec, M, col0, frow + R0 * k2, pm)[lane0] = split_pair(c[k2], cn);
+					}
+				} else if (threadIdx.x < L) {                                      // row 0: N - R0 * k2 = R0 * (R1 - k2), my own outputs
+#pragma unroll
+					for (int k2 = 0; k2 <= R1 / 2; k2++)
+						spec_row_dst<PEER>(spec, M, col0, R0 * k2, pm)[lane0] = split_pair(c[k2], c[(R1 - k2) % R1]);
+				} else {                                                           // row R0 / 2: mirrors onto itself, k2 -> R1 - 1 - k2
+#pragma unroll
+					for (int k2 = 0; k2 < R1 / 2; k2++)
+						spec_row_dst<PEER>(spec, M, col0, R0 / 2 + R0 * k2, pm)[lane0] = split_pair(c[k2], c[R1 - 1 - k2]);
+				}
+			}
+			continue;
+		}
 		fwd_tail_smem<N, L, T>(W, tw);
 		if constexpr (kStructured) {
 #pragma unroll

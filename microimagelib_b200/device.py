@@ -60,7 +60,7 @@ class Decon:
 
     def __init__(self, im_shape, nviews=1, row_conv=None):
         """row_conv: None = the library's default (the in-place row convolution k_zrow where the Z length has a two-stage
-        plan); False = the transposing plane kernels (k_ypassT / k_zconvT), which the distributed path always uses."""
+        plan); False = the transposing plane kernels (k_ypassT / k_zconvT)."""
         self.lib = _lib.load()
         self.im_shape = tuple(int(s) for s in im_shape)
         self.nviews = nviews
@@ -126,6 +126,10 @@ class Decon:
     def plane_stage_fused(self):
         """True if the plane stage of a convolution runs as one persistent launch (k_planes_fused)"""
         return bool(self.lib.milb_decon_plane_stage_fused(self._h))
+
+    def row_convolution(self):
+        """True if the Z convolution runs in place along the contiguous axis (k_zrow) instead of on transposed planes"""
+        return bool(self.lib.milb_decon_row_convolution(self._h))
 
     def set_chunk_planes(self, planes):
         _check(self.lib.milb_decon_set_chunk_planes(self._h, int(planes)), "milb_decon_set_chunk_planes")

@@ -8,7 +8,7 @@ mkdir -p gpurun_out profiles
 export PROBE_ITERS=3
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$TAG.csv python scripts/prof_run.py > gpurun_out/launches_$TAG.log 2>&1
 export PROBE_ITERS=2
-ncu --set full --clock-control none --import-source on -k regex:'k_ypassT|k_zconvT|k_ypassF|k_xpassP' -s 6 -c 8 -o gpurun_out/prof_$TAG -f python scripts/prof_run.py > gpurun_out/prof_full_$TAG.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:'k_ypassT|k_zconvT|k_zrow|k_ypassF|k_xpassP' -s 6 -c 8 -o gpurun_out/prof_$TAG -f python scripts/prof_run.py > gpurun_out/prof_full_$TAG.log 2>&1
 # registration cost kernel
 cat > /tmp/prof_reg.py <<'PY'
 import os, sys

@@ -26,7 +26,7 @@ def _inputs(shape, dual):
 def _single_gpu(shape, dual, iters):
     from microimagelib_b200 import device
     a, b, pa, pb = _inputs(shape, dual)
-    d = device.Decon(shape, 2 if dual else 1, row_conv=False)   # the distributed path runs the transposing plane kernels
+    d = device.Decon(shape, 2 if dual else 1)
     d.set_psf(0, pa)
     d.set_image(0, a)
     if dual:
