@@ -91,6 +91,10 @@ int milb_decon_plane_stage_fused(const milb_decon_t *h);
  * passes; 0 if it runs on transposed planes (k_ypassT / k_zconvT).  Default where the Z length has a two-stage plan
  * (64, 128, 256, 512, 1024); MILB_ZROW=0 at handle creation selects the transposing kernels. */
 int milb_decon_row_convolution(const milb_decon_t *h);
+/* experiment (MILB_PLANE_PIPE=1: the three plane kernels of a convolution side by side on disjoint SMs, planes handed over through
+ * L2): ms of {Y forward, row convolution, Y inverse, whole stage}, each start-to-end on its own stream.  MILB_ERR_ARG if the handle
+ * does not run the pipeline. */
+int milb_decon_time_pipe(milb_decon_t *h, int reps, float *ms4, void *stream);
 
 /* yardstick: the same loop through cuFFT + unfused element-wise kernels, i.e. the reference's own
  * launch structure (src/api_subfunc.cu:3404-3416) on this GPU.  Used by bench.py only. */

@@ -63,6 +63,7 @@ CAPI_PROTOS = {
     "milb_decon_set_chunk_planes": (C.c_int, [_VP, C.c_int]),
     "milb_decon_plane_stage_fused": (C.c_int, [_VP]),
     "milb_decon_row_convolution": (C.c_int, [_VP]),
+    "milb_decon_time_pipe": (C.c_int, [_VP, C.c_int, _F, _VP]),
     "milb_decon_run_host": (C.c_int, [_VP, C.POINTER(_VP), _VP, C.c_int, C.c_int, _VP]),
     "milb_decon_phase_correlate": (C.c_int, [_VP, _VP, _VP, _VP, _VP]),
     "milb_decon_alive": (C.c_int, [_VP]),

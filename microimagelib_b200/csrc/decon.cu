@@ -270,7 +270,25 @@ int milb_decon_create(milb_decon_t **out, int nviews, const unsigned int *imSize
 		h->zrow = h->fast && milb_fast_ops(h->Z)->conv_rows && milb_fast_ops(h->Y)->pass_fwd && !(ze && ze[0] == '0') && !(pf && pf[0] == '1') &&
 				  h->chunk_planes == 0;
 	}
-	if (h->fast && !h->zrow) e = cudaMalloc(&h->S2, sizeof(float2) * h->nspec);
+	if (h->zrow && h->Y == h->Z && milb_fast_ops(h->Y)->planes_pipe) {
+		// Plane pipeline (fft_fast.cuh PipeSync): Y forward, row convolution and Y inverse of a convolution as three kernels side
+		// by side on disjoint SMs, handing planes over through L2.  MILB_PLANE_PIPE=0 runs them one after the other;
+		// MILB_PIPE_SPLIT="a,b" = share of the SMs for the Y-forward kernel / the row convolution.
+		const char *pe = getenv("MILB_PLANE_PIPE"), *se = getenv("MILB_PIPE_SPLIT");
+		if (pe && pe[0] == '1') {
+			PlanePipe &p = h->pipe;
+			p.planes = h->X / 2 + 1;
+			if (se) {
+				float a = 0, b = 0;
+				if (sscanf(se, "%f,%f", &a, &b) == 2 && a > 0 && b > 0 && a + b < 1) { p.share[0] = a; p.share[1] = b; }
+			}
+			e = cudaMalloc(&p.counters, sizeof(unsigned) * 2 * p.planes);
+			if (e == cudaSuccess) e = cudaMemset(p.counters, 0, sizeof(unsigned) * 2 * p.planes);
+			for (int i = 0; i < 2 && e == cudaSuccess; i++) e = cudaStreamCreateWithFlags(&h->pipe_st[i], cudaStreamNonBlocking);
+			for (int i = 0; i < 3 && e == cudaSuccess; i++) e = cudaEventCreateWithFlags(&h->pipe_ev[i], cudaEventDisableTiming);
+		}
+	}
+	if (h->fast && !h->zrow && e == cudaSuccess) e = cudaMalloc(&h->S2, sizeof(float2) * h->nspec);
 	if (h->fast && !h->zrow && e == cudaSuccess && h->Y == h->Z && milb_fast_ops(h->Y)->planes_fused) {
 		// Fused plane stage (one persistent launch per convolution, hand-overs L2-resident; fft_fast.cuh k_planes_fused).
 		// Measured on B200 at 512x512x256: DRAM traffic of the stage 1.75 -> 1.03 GB per convolution, but 375 us against
@@ -329,6 +347,9 @@ void milb_decon_destroy(milb_decon_t *h)
 		cudaStreamDestroy(h->copy_stream);
 		for (auto &e : h->copy_ev) if (e) cudaEventDestroy(e);
 	}
+	if (h->pipe.counters) cudaFree(h->pipe.counters);
+	for (auto &s : h->pipe_st) if (s) cudaStreamDestroy(s);
+	for (auto &ev : h->pipe_ev) if (ev) cudaEventDestroy(ev);
 	if (h->fuse.ring) cudaFree(h->fuse.ring);
 	if (h->fuse.counters) cudaFree(h->fuse.counters);
 	if (h->d_sums) cudaFree(h->d_sums);
@@ -413,6 +434,20 @@ static void plane_stage(milb_decon *h, const float2 *otf, float scale, cudaStrea
 		if (h->zrow) {
 			// S [y][z] -Y fwd-> S [ky'][z] -Z fwd * otf Z inv (rows, in place)-> S [ky'][z] -Y inv-> S [y][z]
 			const long long rows = (long long)planes * h->Y;
+			if (otf && h->pipe.counters) {
+				// the three kernels on three streams, all of them after what `st` has queued so far, and `st` after all of them
+				cudaEventRecord(h->pipe_ev[0], st);
+				cudaStreamWaitEvent(h->pipe_st[0], h->pipe_ev[0], 0);
+				cudaStreamWaitEvent(h->pipe_st[1], h->pipe_ev[0], 0);
+				if (oy->planes_pipe(h->S, otf, h->py.d_tw, &h->pipe, st, h->pipe_st[0], h->pipe_st[1])) {
+					cudaEventRecord(h->pipe_ev[1], h->pipe_st[0]);
+					cudaEventRecord(h->pipe_ev[2], h->pipe_st[1]);
+					cudaStreamWaitEvent(st, h->pipe_ev[1], 0);
+					cudaStreamWaitEvent(st, h->pipe_ev[2], 0);
+					milb_count_launches(3);
+					return;
+				}
+			}
 			oy->pass_fwd(h->S, h->py.d_tw, h->Z, 0, planes, st);
 			if (otf) {
 				oz->conv_rows(h->S, otf, h->pz.d_tw, rows, st);
@@ -754,6 +789,45 @@ int milb_decon_time_kernels(milb_decon_t *h, int reps, float *ms5, void *stream)
 	}
 	for (auto &e : ev) cudaEventDestroy(e);
 	for (int i = 0; i < 5; i++) ms5[i] = (float)(acc[i] / reps);
+	MILB_CUDA_TRY(cudaGetLastError());
+	return MILB_OK;
+}
+
+// Plane pipeline only: average ms of {Y-forward kernel, row convolution, Y-inverse kernel, whole stage} of one convolution, each
+// timed start-to-end on its own stream while the three run side by side (the stage is as long as the slowest of them).
+int milb_decon_time_pipe(milb_decon_t *h, int reps, float *ms4, void *stream)
+{
+	if (!h || reps < 1 || !ms4 || !h->pipe.counters || !h->have_psf[0] || !h->have_img[0]) return MILB_ERR_ARG;
+	cudaStream_t st = (cudaStream_t)stream, sb = h->pipe_st[0], sc = h->pipe_st[1];
+	const FastAxisOps *oy = milb_fast_ops(h->Y);
+	cudaEvent_t ev[7];
+	for (auto &e : ev) MILB_CUDA_TRY(cudaEventCreate(&e));
+	double acc[4] = {0, 0, 0, 0};
+	launch_xpass<X_FWD_REAL>(h, h->E, nullptr, st);
+	for (int r = 0; r < reps; r++) {
+		MILB_CUDA_TRY(cudaEventRecord(ev[0], st));
+		MILB_CUDA_TRY(cudaStreamWaitEvent(sb, ev[0], 0));
+		MILB_CUDA_TRY(cudaStreamWaitEvent(sc, ev[0], 0));
+		MILB_CUDA_TRY(cudaEventRecord(ev[1], sb));
+		MILB_CUDA_TRY(cudaEventRecord(ev[2], sc));
+		if (!oy->planes_pipe(h->S, (r & 1) ? h->otf_bp[0] : h->otf[0], h->py.d_tw, &h->pipe, st, sb, sc)) return MILB_ERR_SIZE;
+		MILB_CUDA_TRY(cudaEventRecord(ev[3], st));
+		MILB_CUDA_TRY(cudaEventRecord(ev[4], sb));
+		MILB_CUDA_TRY(cudaEventRecord(ev[5], sc));
+		MILB_CUDA_TRY(cudaStreamWaitEvent(st, ev[4], 0));
+		MILB_CUDA_TRY(cudaStreamWaitEvent(st, ev[5], 0));
+		MILB_CUDA_TRY(cudaEventRecord(ev[6], st));
+		launch_xpass<X_RATIO>(h, nullptr, h->A[0], st); // a fresh spectrum for the next round
+		MILB_CUDA_TRY(cudaStreamSynchronize(st));
+		float a, b, c, w;
+		MILB_CUDA_TRY(cudaEventElapsedTime(&a, ev[0], ev[3]));
+		MILB_CUDA_TRY(cudaEventElapsedTime(&b, ev[1], ev[4]));
+		MILB_CUDA_TRY(cudaEventElapsedTime(&c, ev[2], ev[5]));
+		MILB_CUDA_TRY(cudaEventElapsedTime(&w, ev[0], ev[6]));
+		acc[0] += a; acc[1] += b; acc[2] += c; acc[3] += w;
+	}
+	for (auto &e : ev) cudaEventDestroy(e);
+	for (int i = 0; i < 4; i++) ms4[i] = (float)(acc[i] / reps);
 	MILB_CUDA_TRY(cudaGetLastError());
 	return MILB_OK;
 }

@@ -22,6 +22,21 @@ struct PlaneFuse {
 	float share[2] = {0.285f, 0.46f}; // fraction of the CTAs that run phase A / phase B (the rest run phase C)
 };
 
+// Hand-over between the three plane kernels when they run SIDE BY SIDE as a dataflow pipeline over the kx planes (Y forward
+// -> Z row convolution -> Y inverse, each on its own share of the SMs and its own stream, all in place in S, so that a plane
+// is still in L2 when the next phase picks it up): per-plane completion counters in global memory.
+struct PipeSync {
+	const unsigned *wait = nullptr; // counter of the producing phase, per plane: a tile / row group of plane p is loaded only once wait[p] >= wait_target
+	unsigned *sig = nullptr;        // my own counter, per plane: += 1 per finished tile / row group
+	unsigned wait_target = 0;
+};
+struct PlanePipe {
+	unsigned *counters = nullptr;   // 2 x planes: tiles finished by the Y-forward kernel / row groups finished by the row convolution, cumulative over launches
+	unsigned launches = 0;
+	int planes = 0;
+	float share[2] = {0.294f, 0.428f}; // fraction of the SMs given to the Y-forward kernel / the row convolution (the rest: Y inverse)
+};
+
 struct FastAxisOps {
 	int n = 0;                 // FFT length
 	int lanes = 0;             // pencils per CTA
@@ -56,6 +71,9 @@ struct FastAxisOps {
 	// two-stage plan.  fwd_rows: forward only, scaled, rows left in that order (OTF generation)
 	void (*conv_rows)(float2 *spec, const float2 *otf, const float2 *tw, long long rows, cudaStream_t st) = nullptr;
 	void (*fwd_rows)(float2 *spec, const float2 *tw, long long rows, float scale, cudaStream_t st) = nullptr;
+	// square planes (n x n), row convolution available: the three plane kernels of a convolution as a pipeline (see PlanePipe) on
+	// three streams; the caller orders the streams around the call.  Returns false if the kernels cannot all be resident.
+	bool (*planes_pipe)(float2 *S, const float2 *otf, const float2 *tw, PlanePipe *pp, cudaStream_t sa, cudaStream_t sb, cudaStream_t sc) = nullptr;
 	// in-place forward only, scaled (OTF generation)
 	void (*fwd_scaled)(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, float scale, cudaStream_t st) = nullptr;
 };

@@ -53,6 +53,13 @@ constexpr bool kXWide = MILB_X_WIDE || (MILB_X_WIDE512 && N == 512) || (MILB_X_W
 constexpr int XL = pow2_floor((kXWide ? 8192 : kXNarrow ? 2048 : 4096) / N), XT = (N / R0) * XL;
 constexpr int XCTAS = xpassP_ctas<N, XL, XT>();
 constexpr size_t SMX = (size_t)(2 * N * XL + 2 * (N / 2 + 1) * XL + N) * sizeof(float2);
+// MILB_Y_BUFS: landing buffers of the TMA-fed in-place Y passes (2 or 3).  Three keep two 64 KB tiles per SM in flight; measured
+// at 512^3 that is SLOWER (Y forward 179 -> 199 us, Y inverse 177 -> 190 us, 1.93 -> 2.00 ms per iteration), so the default is 2.
+#ifndef MILB_Y_BUFS
+#define MILB_Y_BUFS 2
+#endif
+constexpr int YB = (MILB_Y_BUFS == 3 && (size_t)(3 * TileGeom<N, PL>::elems + N) * sizeof(float2) <= 200 * 1024) ? 3 : 2;
+constexpr size_t SMPY = (size_t)(YB * TileGeom<N, PL>::elems + N) * sizeof(float2);
 int g_ctas = 0, g_sms = 0; // persistent grids
 int g_fused_per_sm = 0, g_fused_ctas = 0; // co-resident CTAs of the fused plane stage (its tiles wait for each other)
 int g_cap = 0;              // override (FastAxisOps::grid_cap)
@@ -87,12 +94,17 @@ template <int M, bool OK = ZPlan<M>::ok> struct ZRow {
 	static int setup() { return 0; }
 	static void conv(float2 *, const float2 *, const float2 *, long long, cudaStream_t) {}
 	static void fwd(float2 *, const float2 *, long long, float, cudaStream_t) {}
+	static void conv_pipe(float2 *, const float2 *, const float2 *, long long, int, int, const PipeSync &, cudaStream_t) {}
 };
 template <int M> struct ZRow<M, true> {
 	using G = ZRowGeom<M, ZPlan<M>::r0, ZPlan<M>::r1>;
 	static constexpr int NW = zrow_warps<M>();
 	static constexpr size_t SMZ = (size_t)(M + NW * zrow_warp_elems<M, G>()) * sizeof(float2);
-	static int setup() { return optin(k_zrow<M, true>, SMZ) | optin(k_zrow<M, false>, SMZ); }
+	static int setup() { return optin(k_zrow<M, true>, SMZ) | optin(k_zrow<M, false>, SMZ) | optin(k_zrow<M, true, true>, SMZ); }
+	static void conv_pipe(float2 *S, const float2 *otf, const float2 *tw, long long rows, int rows_per_plane, int ctas, const PipeSync &ps, cudaStream_t st)
+	{
+		k_zrow<M, true, true><<<ctas, NW * 32, SMZ, st>>>(S, otf, tw, rows / G::PPW, 1.0f, ps, rows_per_plane / G::PPW);
+	}
 	static int grid(long long units)
 	{
 		const long long want = (units + NW - 1) / NW;
@@ -111,9 +123,45 @@ template <int M> struct ZRow<M, true> {
 	}
 };
 
+// The three plane kernels of one convolution side by side (square planes N x N): Y forward on `sa` with nA CTAs, the row
+// convolution on `sb` with nB, Y inverse on `sc` with the rest -- one CTA per SM each (shared memory), together exactly the
+// machine, so all of them are resident and the per-plane counters (PipeSync) can never be waited for in vain.
+template <int M, bool OK = (kTmaTiles && ZPlan<M>::ok)> struct Pipe {
+	static int setup() { return 0; }
+	static bool run(float2 *, const float2 *, const float2 *, PlanePipe *, cudaStream_t, cudaStream_t, cudaStream_t) { return false; }
+};
+template <int M> struct Pipe<M, true> {
+	static int setup() { return optin(k_ypassF<M, PL, PT, false, false, true, true, YB>, SMPY) | optin(k_ypassF<M, PL, PT, true, false, true, true, YB>, SMPY); }
+	static bool run(float2 *S, const float2 *otf, const float2 *tw, PlanePipe *pp, cudaStream_t sa, cudaStream_t sb, cudaStream_t sc)
+	{
+		if (!g_use_tma || !pp || !pp->counters || g_sms < 3 || M * PL <= 4096) return false; // one CTA per SM for each of the kernels
+		TileMap tm;
+		if (!make_tile_map(tm, S, M, (long long)M * pp->planes)) return false;
+		int nA = (int)(g_sms * pp->share[0] + 0.5f), nB = (int)(g_sms * pp->share[1] + 0.5f);
+		nA = nA < 1 ? 1 : nA;
+		nB = nB < 1 ? 1 : nB;
+		if (nA + nB > g_sms - 1) return false;
+		const int nC = g_sms - nA - nB;
+		constexpr int TPP = M / PL;                 // Y-pass tiles per plane
+		using G = ZRowGeom<M, ZPlan<M>::r0, ZPlan<M>::r1>;
+		constexpr int UPP = M / G::PPW;             // row groups per plane
+		pp->launches++;
+		unsigned *doneA = pp->counters, *doneB = pp->counters + pp->planes;
+		PipeSync a, b, c;
+		a.sig = doneA;
+		b.wait = doneA; b.wait_target = pp->launches * (unsigned)TPP; b.sig = doneB;
+		c.wait = doneB; c.wait_target = pp->launches * (unsigned)UPP;
+		k_ypassF<M, PL, PT, false, false, true, true, YB><<<nA, PT, SMPY, sa>>>(S, tw, M, 0, pp->planes, PeerMap(), tm, a);
+		ZRow<M>::conv_pipe(S, otf, tw, (long long)pp->planes * M, M, nB, b, sb);
+		k_ypassF<M, PL, PT, true, false, true, true, YB><<<nC, PT, SMPY, sc>>>(S, tw, M, 0, pp->planes, PeerMap(), tm, c);
+		return true;
+	}
+};
+
 int setup()
 {
 	int bad = 0;
+	bad |= Pipe<N>::setup();
 	bad |= ZRow<N>::setup();
 	bad |= optin(k_ypassF<N, PL, PT, false>, SMP2);
 	bad |= optin(k_xpassF<N, L, TXF, XF_FWD_REAL>, SM1);
@@ -142,8 +190,8 @@ int setup()
 		}
 	}
 	if constexpr (kTmaTiles) {
-		bad |= optin(k_ypassF<N, PL, PT, false, false, true>, SMP2);
-		bad |= optin(k_ypassF<N, PL, PT, true, false, true>, SMP2);
+		bad |= optin(k_ypassF<N, PL, PT, false, false, true, false, YB>, SMPY);
+		bad |= optin(k_ypassF<N, PL, PT, true, false, true, false, YB>, SMPY);
 		bad |= optin(k_ypassF<N, PL, PT, true, true, true>, SMP2);
 		const char *e = getenv("MILB_TMA");
 		if (!(e && e[0] == '0')) {
@@ -160,6 +208,7 @@ int setup()
 	cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
 	g_ctas = ((N * PL <= 4096) ? 2 : 1) * sms;
 	g_sms = sms;
+	if (const char *ce = getenv("MILB_GRID_CAP")) g_cap = atoi(ce); // experiments: CTAs of the persistent plane kernels (0 = one per SM)
 	g_fused_ctas = g_fused_per_sm * sms;
 	return bad;
 }
@@ -231,7 +280,7 @@ void pass_inv(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes,
 	if constexpr (kTmaTiles) {
 		TileMap tm;
 		if (g_use_tma && make_tile_map(tm, spec, cols, (long long)N * (plane0 + nplanes))) {
-			k_ypassF<N, PL, PT, true, false, true><<<plane_grid(tiles), PT, SMP2, st>>>(spec, tw, cols, plane0, nplanes, PeerMap(), tm);
+			k_ypassF<N, PL, PT, true, false, true, false, YB><<<plane_grid(tiles), PT, SMPY, st>>>(spec, tw, cols, plane0, nplanes, PeerMap(), tm);
 			return;
 		}
 	}
@@ -244,7 +293,7 @@ void pass_fwd(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes,
 	if constexpr (kTmaTiles) {
 		TileMap tm;
 		if (g_use_tma && make_tile_map(tm, spec, cols, (long long)N * (plane0 + nplanes))) {
-			k_ypassF<N, PL, PT, false, false, true><<<plane_grid(tiles), PT, SMP2, st>>>(spec, tw, cols, plane0, nplanes, PeerMap(), tm);
+			k_ypassF<N, PL, PT, false, false, true, false, YB><<<plane_grid(tiles), PT, SMPY, st>>>(spec, tw, cols, plane0, nplanes, PeerMap(), tm);
 			return;
 		}
 	}
@@ -289,6 +338,11 @@ bool planes_fused(float2 *S, const float2 *otf, const float2 *tw, PlaneFuse *pf,
 	}
 }
 
+bool planes_pipe(float2 *S, const float2 *otf, const float2 *tw, PlanePipe *pp, cudaStream_t sa, cudaStream_t sb, cudaStream_t sc)
+{
+	return Pipe<N>::run(S, otf, tw, pp, sa, sb, sc);
+}
+
 void fwd_scaled(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, float scale, cudaStream_t st)
 {
 	const int tiles = (cols / PL) * nplanes;
@@ -304,6 +358,7 @@ const FastAxisOps *MILB_CAT(milb_fast_ops_, MILB_FAST_N)()
 	ops.n = N; ops.lanes = L; ops.xlanes = XL > L ? XL : L; ops.setup = setup; ops.xpass = xpass; ops.xpass_cols = xpass_cols; ops.passT = passT; ops.pass_inv = pass_inv;
 	ops.convT = convT; ops.fwd_scaled = fwd_scaled; ops.planes_fused = kPow2 ? planes_fused : nullptr;
 	ops.pass_fwd = pass_fwd; ops.conv_rows = ZPlan<N>::ok ? conv_rows : nullptr; ops.fwd_rows = ZPlan<N>::ok ? fwd_rows : nullptr;
+	ops.planes_pipe = (kTmaTiles && ZPlan<N>::ok) ? planes_pipe : nullptr;
 	ops.xpass_peer = kPow2 ? xpass_peer : nullptr; ops.pass_inv_peer = kPow2 ? pass_inv_peer : nullptr; ops.grid_cap = &g_cap;
 	return &ops;
 }

@@ -31,6 +31,9 @@ struct milb_decon {
 	bool zrow = false;             // fast path: Z convolution along the contiguous axis in place (k_zrow), no S2, OTFs in its per-row order
 	float2 *S2 = nullptr;          // fast path: transposed planes [kx][z][ky']
 	float2 *otf[2] = {nullptr, nullptr}, *otf_bp[2] = {nullptr, nullptr};
+	PlanePipe pipe;                // row convolution, square planes: the three plane kernels side by side (counters == nullptr: one after the other)
+	cudaStream_t pipe_st[2] = {nullptr, nullptr};
+	cudaEvent_t pipe_ev[3] = {nullptr, nullptr, nullptr};
 	PlaneFuse fuse;                // fast path, square planes: state of the fused plane stage (ring == nullptr: three launches)
 	cudaStream_t copy_stream = nullptr; // milb_decon_run_host: host copies overlapped with the first / last X pass
 	cudaEvent_t copy_ev[9] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};

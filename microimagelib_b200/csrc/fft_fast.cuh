@@ -554,6 +554,47 @@ template <int N, int L, int T, bool SKIP_FIRST> __device__ __forceinline__ void 
 	}
 }
 
+// ---- completion counters between kernels / roles that run side by side (PipeSync, PlaneSched) ---------------------------
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
+{
+	unsigned v;
+	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ void spin_until(const unsigned *p, unsigned target)
+{
+	for (unsigned n = 0; (int)(ld_relaxed_u32(p) - target) < 0; n++) {
+		__nanosleep(64);
+		if (n > (1u << 24)) __trap();
+	}
+	__threadfence();
+}
+// Consumer side of a hand-over: acquire loads of the producer's counter (no fence: a membar would wait for the polling thread's
+// own outstanding stores of the previous tile, measured as a stall of about a third of a tile), then the copy-engine request.
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p)
+{
+	unsigned v;
+	asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+	return v;
+}
+__device__ __forceinline__ bool pipe_ready(const unsigned *p, unsigned target) { return (int)(ld_acquire_u32(p) - target) >= 0; }
+__device__ __forceinline__ void pipe_wait(const unsigned *p, unsigned target)
+{
+	for (unsigned n = 0; !pipe_ready(p, target); n++) {
+		__nanosleep(64);
+		if (n > (1u << 24)) __trap();
+	}
+}
+// Producer side, every thread, after its global stores of a tile: they were made through the generic proxy and the consumer
+// reads them with the copy engine (async proxy)
+__device__ __forceinline__ void pipe_stores_done() { asm volatile("fence.proxy.async.global;\n" ::: "memory"); }
+// one thread, after a barrier that ordered the other threads' stores before it
+__device__ __forceinline__ void pipe_release(unsigned *sig)
+{
+	__threadfence();
+	atomicAdd(sig, 1u);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Y forward, transposing:  in plane [N = Y rows][Z]  ->  out plane [Z rows][N = Y]
 template <int N, int L, int T>
@@ -590,21 +631,30 @@ k_ypassT(const float2 *__restrict__ in, float2 *__restrict__ out, const float2 *
 // PEER: the output row y of plane kx is not written back in place but into the slab buffer of the
 // rank that owns row y -- slab_d[kx][y - d*ny][z] -- through peer memory (NVLink): the backward
 // exchange of the slab-decomposed FFT rides on this kernel's stores, tile by tile.
-template <int N, int L, int T, bool INV, bool PEER = false, bool TMA = false>
+// TMA: the tiles land in a ring of NBUF buffers (one mbarrier each), requested NBUF - 1 tiles ahead by thread 0.  A quarter of
+// the Y-inverse pass's stall samples sit in the wait for the tile, but a third buffer (two tiles per SM in flight) measured
+// slower, not faster (decon_fast_inst.cuh MILB_Y_BUFS): the pass is bound by HBM throughput, not by the request depth.
+// PIPE: the kernel is one phase of the plane pipeline (PipeSync): a tile of plane p is requested only once ps.wait[p] has
+// reached its target (polled without blocking while tiles already requested remain; blocking only when the tile is the one
+// needed now), and ps.sig[p] is bumped per finished tile -- one tile LATER, right after the next tile's top barrier, when the
+// signalling thread's own stores have long drained and the fence costs nothing.
+template <int N, int L, int T, bool INV, bool PEER = false, bool TMA = false, bool PIPE = false, int NBUF = 2>
 __global__ void __launch_bounds__(T, (N * L <= 4096) ? 2 : 1)
 k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes, const __grid_constant__ PeerMap pm = PeerMap(),
-	const __grid_constant__ TileMap tmap = TileMap())
+	const __grid_constant__ TileMap tmap = TileMap(), PipeSync ps = PipeSync())
 {
+	static_assert(!PIPE || (TMA && !PEER), "the pipeline phases load their tiles with the copy engine");
+	static_assert(NBUF == 2 || TMA, "the cp.async path is double-buffered");
 	using P = FastPlan<N>;
 	using G = TileGeom<N, L>;
 	extern __shared__ __align__(128) float2 sm[];
-	float2 *tw = sm + 2 * G::elems;
-	__shared__ __align__(8) unsigned long long bars[2];
+	float2 *tw = sm + NBUF * G::elems;
+	__shared__ __align__(8) unsigned long long bars[NBUF];
 	if constexpr (TMA) {
 		static_assert(L > 8, "TMA tiles need dense (unskewed) shared rows");
 		if (threadIdx.x == 0) {
-			mbar_init(&bars[0], 1);
-			mbar_init(&bars[1], 1);
+#pragma unroll
+			for (int b = 0; b < NBUF; b++) mbar_init(&bars[b], 1);
 			asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
 		}
 	}
@@ -618,19 +668,42 @@ k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int 
 	const int tpp = Z / L, ntiles = nplanes * tpp;
 	auto ptr_of = [&](int t) { return spec + (long long)(t / tpp + plane0) * N * Z + (long long)(t % tpp) * L; };
 	auto tma_issue = [&](int t, int buf) { tma_tile_load<N, L>(sm + buf * G::elems, &tmap, (t / tpp + plane0) * N, (t % tpp) * L, &bars[buf]); };
-	int t = blockIdx.x, cur = 0;
+	int t = blockIdx.x;
+	unsigned *pend = nullptr;  // PIPE: counter of the tile whose stores are out but not yet signalled
+	int next_req = 0;          // TMA, thread 0: my tiles [0, next_req) have been requested (my k-th tile = blockIdx.x + k * gridDim.x)
+	// request my tiles up to number `upto` (their buffers are free); stops at the first whose plane is not ready unless `block`
+	auto request_upto = [&](int upto, bool block) {
+		for (; next_req <= upto; next_req++) {
+			const int tr = blockIdx.x + next_req * gridDim.x;
+			if (tr >= ntiles) break;
+			if constexpr (PIPE) {
+				if (ps.wait) {
+					const unsigned *c = ps.wait + (tr / tpp + plane0);
+					if (block) pipe_wait(c, ps.wait_target);
+					else if (!pipe_ready(c, ps.wait_target)) break;
+				}
+			}
+			tma_issue(tr, next_req % NBUF);
+		}
+	};
 	if constexpr (TMA) {
-		if (t < ntiles && threadIdx.x == 0) tma_issue(t, 0);
+		if (threadIdx.x == 0) request_upto(NBUF - 2, false);
 	} else {
 		if (t < ntiles) tile_load_async<N, L, T>(sm, ptr_of(t), Z);
 		cp_async_commit();
 	}
-	for (int it = 0; t < ntiles; t += gridDim.x, cur ^= 1, it++) {
+	for (int it = 0; t < ntiles; t += gridDim.x, it++) {
 		const int tn = t + gridDim.x;
+		const int cur = TMA ? it % NBUF : (it & 1);
 		if constexpr (TMA) {
-			mbar_wait(&bars[cur], (it >> 1) & 1); // this buffer's (it / 2)-th fill has landed
-			__syncthreads();                       // everybody is done with the other buffer (previous tile)
-			if (tn < ntiles && threadIdx.x == 0) tma_issue(tn, cur ^ 1);
+			if (threadIdx.x == 0 && next_req <= it) request_upto(it, true); // the tile needed now has not even been requested: wait for its producer
+			mbar_wait(&bars[cur], (it / NBUF) & 1); // this buffer's (it / NBUF)-th fill has landed
+			__syncthreads();                         // everybody is done with the previous tile's buffer
+			if constexpr (PIPE) {
+				if (pend && threadIdx.x == 0) pipe_release(pend);
+				pend = ps.sig ? ps.sig + (t / tpp + plane0) : nullptr;
+			}
+			if (threadIdx.x == 0) request_upto(it + NBUF - 1, false);
 		} else {
 			cp_async_wait<0>();
 			__syncthreads();
@@ -670,6 +743,12 @@ k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int 
 				fwd_last<N, L, T>(tile, tw, gs);
 			}
 		}
+		if constexpr (PIPE)
+			if (ps.sig) pipe_stores_done();
+	}
+	if constexpr (PIPE) {
+		__syncthreads();
+		if (pend && threadIdx.x == 0) pipe_release(pend);
 	}
 	if constexpr (PEER) __threadfence_system();
 }
@@ -781,9 +860,13 @@ __device__ __forceinline__ void bulk_load_1d(void *smem_dst, const void *gsrc, u
 				 "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
-template <int N, bool CONV>
+// PIPE: phase B of the plane pipeline (PipeSync): rows are walked UPWARDS like the other phases' planes, a row group of
+// plane p (upp groups per plane) is requested only once the Y-forward kernel has finished p, and ps.sig[p] is bumped per
+// finished group, one group later.
+template <int N, bool CONV, bool PIPE = false>
 __global__ void __launch_bounds__(zrow_warps<N>() * 32, 1)
-k_zrow(float2 *__restrict__ S, const float2 *__restrict__ otf, const float2 *__restrict__ g_tw, long long nunits, float scale)
+k_zrow(float2 *__restrict__ S, const float2 *__restrict__ otf, const float2 *__restrict__ g_tw, long long nunits, float scale, PipeSync ps = PipeSync(),
+	int upp = 1)
 {
 	using G = ZRowGeom<N, ZPlan<N>::r0, ZPlan<N>::r1>;
 	constexpr int NW = zrow_warps<N>();
@@ -815,16 +898,37 @@ k_zrow(float2 *__restrict__ S, const float2 *__restrict__ otf, const float2 *__r
 				bulk_load_1d(land0 + buf * LAND + p * G::LS, S + (u * G::PPW + p) * N, (unsigned)(N * sizeof(float2)), &bars[warp][buf]);
 		}
 	};
-	// Rows are walked from the LAST plane down: the Y-forward pass in front of this kernel walks the planes upwards, so the
-	// rows it wrote last are still in L2 when this kernel starts with them, and the Y-inverse pass behind it (upwards again)
-	// starts with the rows this kernel wrote last.
-	long long u = nunits - 1 - ((long long)blockIdx.x * NW + warp);
-	if (u >= 0 && lane == 0) issue(u, 0);
-	for (int it = 0; u >= 0; u -= stride, it++) {
+	// Rows are walked from the LAST plane down (unless PIPE): the Y-forward pass in front of this kernel walks the planes
+	// upwards, so the rows it wrote last are still in L2 when this kernel starts with them, and the Y-inverse pass behind it
+	// (upwards again) starts with the rows this kernel wrote last.
+	const long long first = (long long)blockIdx.x * NW + warp;
+	long long u = PIPE ? first : nunits - 1 - first;
+	const long long step = PIPE ? stride : -stride;
+	auto valid = [&](long long v) { return v >= 0 && v < nunits; };
+	unsigned *pend = nullptr; // PIPE: counter of the row group whose stores are out but not yet signalled
+	auto request = [&](long long v, int buf, bool block) -> bool { // lane 0: wait for / check the producer of v's plane, then issue
+		if constexpr (PIPE) {
+			if (ps.wait) {
+				const unsigned *c = ps.wait + (int)(v / upp);
+				if (block) pipe_wait(c, ps.wait_target);
+				else if (!pipe_ready(c, ps.wait_target)) return false;
+			}
+		}
+		issue(v, buf);
+		return true;
+	};
+	if (valid(u) && lane == 0) request(u, 0, true);
+	for (int it = 0; valid(u); u += step, it++) {
 		const int cur = DB ? (it & 1) : 0;
+		const long long un = u + step;
+		bool deferred = false; // lane 0: the next group's plane was not ready when polled
 		__syncwarp(); // every lane is done with the exchange buffer (previous rows) and, DB, with the other landing buffer
+		if constexpr (PIPE) {
+			if (pend && lane == 0) pipe_release(pend);
+			pend = ps.sig ? ps.sig + (int)(u / upp) : nullptr;
+		}
 		if constexpr (DB)
-			if (u - stride >= 0 && lane == 0) issue(u - stride, cur ^ 1);
+			if (valid(un) && lane == 0) deferred = !request(un, cur ^ 1, false);
 		float2 *row = S + (u * G::PPW + pen) * N;
 		float2 o[G::B1][G::r1];
 		if constexpr (CONV) {
@@ -838,12 +942,20 @@ k_zrow(float2 *__restrict__ S, const float2 *__restrict__ otf, const float2 *__r
 		zrow_fwd0<G>(j, land0 + cur * LAND + pen * G::LS, ex, tws);
 		__syncwarp();
 		if constexpr (!DB)
-			if (u - stride >= 0 && lane == 0) issue(u - stride, 0); // the landing buffer is free again: refill it behind the other stages
+			if (valid(un) && lane == 0) deferred = !request(un, 0, false); // the landing buffer is free again: refill it behind the other stages
 		zrow_mid<G, CONV>(j, ex, o, row, scale);
 		if constexpr (CONV) {
 			__syncwarp();
 			zrow_inv0<G>(j, ex, tws, row);
 		}
+		if constexpr (PIPE) {
+			if (ps.sig) pipe_stores_done();
+			if (deferred) request(un, DB ? (cur ^ 1) : 0, true);
+		}
+	}
+	if constexpr (PIPE) {
+		__syncwarp();
+		if (pend && lane == 0) pipe_release(pend);
 	}
 }
 
@@ -872,20 +984,6 @@ k_zrow(float2 *__restrict__ S, const float2 *__restrict__ otf, const float2 *__r
 //            the CTA's pending signal has been sent, so CTAs never wait on each other's unsent signals).
 // All CTAs are co-resident (grid <= resident CTAs) and every dependency points to an earlier plane or an earlier phase of
 // the same plane, so the pipeline cannot deadlock; a poll that never succeeds traps instead of hanging the GPU.
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned *p)
-{
-	unsigned v;
-	asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
-	return v;
-}
-__device__ __forceinline__ void spin_until(const unsigned *p, unsigned target)
-{
-	for (unsigned n = 0; (int)(ld_relaxed_u32(p) - target) < 0; n++) {
-		__nanosleep(64);
-		if (n > (1u << 24)) __trap();
-	}
-	__threadfence();
-}
 __device__ __forceinline__ void plane_signal(unsigned *&sig)
 {
 	if (sig && threadIdx.x == 0) {

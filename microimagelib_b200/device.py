@@ -127,6 +127,12 @@ class Decon:
         """True if the plane stage of a convolution runs as one persistent launch (k_planes_fused)"""
         return bool(self.lib.milb_decon_plane_stage_fused(self._h))
 
+    def time_pipe(self, reps=5, stream=None):
+        """plane pipeline only: ms of (Y forward, row convolution, Y inverse, whole stage), each on its own stream"""
+        ms = np.zeros(4, np.float32)
+        _check(self.lib.milb_decon_time_pipe(self._h, int(reps), ms.ctypes.data_as(_F), _stream(stream)), "milb_decon_time_pipe")
+        return ms
+
     def row_convolution(self):
         """True if the Z convolution runs in place along the contiguous axis (k_zrow) instead of on transposed planes"""
         return bool(self.lib.milb_decon_row_convolution(self._h))
