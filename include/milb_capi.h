@@ -81,7 +81,9 @@ int milb_decon_psf_matches(const milb_decon_t *h, int view, const float *psf, co
 void milb_decon_cache_release(void);
 
 /* tuning: planes of the half spectrum processed per launch of the three plane passes (0 = whole volume; any other
- * value also switches the fused plane stage off) */
+ * value also switches the fused plane stage off).  Accepted and ignored when the Z convolution runs in place
+ * (milb_decon_row_convolution: there is no transposed scratch to chunk); MILB_CHUNK_PLANES at handle creation
+ * selects the transposing kernels, which honour it. */
 int milb_decon_set_chunk_planes(milb_decon_t *h, int planes);
 /* 1 if the loop runs the plane stage of a convolution (cufftExecR2C's Y/Z part, multicomplex3Dkernel, cufftExecC2R's
  * Y/Z part; src/api_subfunc.cu:3406-3413) as ONE persistent launch whose intermediates stay in L2 (square planes) */
