@@ -16,9 +16,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-BUILD = os.path.join(HERE, "build")
+# MILB_BUILD_TAG=x builds a variant (with MILB_NVCC_FLAGS) into build_x/ and lib/libapi_x.so for A/B runs (MILB_LIBAPI selects it)
+_TAG = os.environ.get("MILB_BUILD_TAG", "")
+BUILD = os.path.join(HERE, "build" + ("_" + _TAG if _TAG else ""))
 LIBDIR = os.path.join(HERE, "lib")
-LIB = os.path.join(LIBDIR, "libapi.so")
+LIB = os.path.join(LIBDIR, "libapi" + ("_" + _TAG if _TAG else "") + ".so")
 
 SOURCES = ["decon.cu", "decon_fast.cu", "decon_fast_n64.cu", "decon_fast_n128.cu", "decon_fast_n256.cu", "decon_fast_n512.cu", "decon_fast_n1024.cu", "decon_fast_n192.cu", "decon_fast_n320.cu", "decon_fast_n384.cu", "decon_fast_n448.cu", "decon_fast_n576.cu", "decon_fast_n640.cu", "decon_fast_n768.cu", "dslab.cu", "reg.cu", "prealign.cu", "geom.cu", "yardstick.cu", "reg_driver.cpp", "powell.cpp", "libapi.cpp", "tiff_io.cpp"]
 

@@ -1262,14 +1262,15 @@ template <int N, int L, int T> constexpr int xpassP_ctas()
 //   AL aux landing buffer      N x L float2         (A for RATIO, E for UPDATE; consumed by stage 0)
 // As soon as a landing buffer has been consumed the next tile's rows are already requested, so the
 // spectrum and aux loads of tile t+1 overlap the butterflies of tile t.
-// MILB_X_FOLD (default): for the two-stage plans on 16-lane tiles (N = 256, 512) the merge of the half spectrum is folded into
+// MILB_X_FOLD (default): for the two-stage plans on 16- or 8-lane tiles (N = 256, 512) the merge of the half spectrum is folded into
 // the loads of the inverse radix-r1 stage and the split into the epilogue of the forward radix-r1 stage:
 //   * a thread of that stage owns row k1 of the position-ordered pencil = frequencies k1 + r0 * k2; for k2 < r1 / 2 they are
 //     rows of the half spectrum themselves, the others are mirrors N - k of rows (r0 - k1) + r0 * (r1 - 1 - k2), so the thread
 //     builds its 32 inputs straight from the landing buffer (one float4 each) -- no merge pass over a working tile;
 //   * after the forward stage the mirror partner C[N - k] of a thread's outputs sits in the registers of the thread that owns
 //     row r0 - k1.  Rows (k1, r0 - k1) are given to the two halves of ONE warp (rows 0 and r0 / 2, which mirror onto themselves,
-//     share warp 0), so the partners arrive by __shfl_xor and the A / B rows leave straight from registers -- no split pass.
+//     share the first 2 L lanes), so the partners arrive by __shfl_xor and the A / B rows leave straight from registers -- no
+//     split pass.
 // Per tile that is 3 CTA barriers instead of 6 and 9 instead of 13 shared-memory accesses per point.
 #ifndef MILB_X_FOLD
 #define MILB_X_FOLD 1
@@ -1301,7 +1302,9 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 	constexpr int RIT = T / L, NB = N / RIT, NIT = half / RIT;
 	constexpr bool kStructured = (T % L == 0) && ((RIT & (RIT - 1)) == 0) && (RIT * NB == N) && (NIT * RIT == half) && (RIT <= half);
 	constexpr int R1 = P::r1;
-	constexpr bool kFold = MILB_X_FOLD && (P::S == 2) && (L == 16) && (R0 * L <= T);
+	constexpr bool kFold = MILB_X_FOLD && (P::S == 2) && (L == 16 || L == 8) && (R0 * L <= T);
+	// the lanes that hold a mirror pair of rows (2 * L of them) exchange by shuffles among themselves
+	const unsigned pair_mask = (L == 16) ? 0xffffffffu : (0xffffu << (threadIdx.x & 16));
 	const int frow = xfold_row<R0>(threadIdx.x / L);               // kFold: my row of the radix-r1 stages (threads < R0 * L)
 	const int k0 = threadIdx.x / L, lane0 = threadIdx.x % L;
 	const int pA0 = fast_pos<N>(k0) * L + lane0;                    // position of row k0 (+ lane)
@@ -1438,8 +1441,8 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 #pragma unroll
 					for (int k2 = 0; k2 < R1 / 2; k2++) {
 						float2 cn;
-						cn.x = __shfl_xor_sync(0xffffffffu, c[R1 - 1 - k2].x, 16);
-						cn.y = __shfl_xor_sync(0xffffffffu, c[R1 - 1 - k2].y, 16);
+						cn.x = __shfl_xor_sync(pair_mask, c[R1 - 1 - k2].x, L);
+						cn.y = __shfl_xor_sync(pair_mask, c[R1 - 1 - k2].y, L);
 						spec_row_dst<PEER>(spec, M, col0, frow + R0 * k2, pm)[lane0] = split_pair(c[k2], cn);
 					}
 				} else if (threadIdx.x < L) {                                      // row 0: N - R0 * k2 = R0 * (R1 - k2), my own outputs
