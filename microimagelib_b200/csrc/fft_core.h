@@ -42,12 +42,13 @@ struct AxisPlanDev {
 
 MILB_HD float2 cmul(float2 a, float2 b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
 MILB_HD float2 cmulc(float2 a, float2 b) { return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y); } // a*conj(b)
-#if defined(MILB_USE_F32X2) && defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
-// sm_100 packed fp32: one FADD2 / FMUL2 / FFMA2 per complex add / scale / multiply-add.  Operand
-// negation and the (y, -x) swizzle of a multiplication by -+i fold into the instruction's modifiers.
-// Measured on B200 (round 1): the packed forms halve the FP instruction count of the butterflies
-// but the RL iteration got 3 % SLOWER (FP32 lane throughput is unchanged, and register pairs cost
-// moves), so this path is opt-in (-DMILB_USE_F32X2) and off by default.
+#if !defined(MILB_NO_F32X2) && defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+// sm_100 packed fp32: one FADD2 / FMUL2 per complex add / scale (operand negation folds into the instruction's modifiers).
+// The packed forms halve the add / scale instruction count of the butterflies (k_zrow: 1905 -> 1233 FP instructions per
+// thread and row pair, + 91 register moves); FP32 lane throughput is unchanged, so the gain is only what instruction issue
+// was costing.  Round 1 (CTA-lockstep kernels): 3 % SLOWER, opt-in.  Round 2 (row convolution, folded X pass): 1 % faster
+// both in short and in sustained runs at 512^3 (100.4 -> 99.3 ms per 50 iterations), so it is now the default;
+// -DMILB_NO_F32X2 restores the scalar forms.  The explicit-rounding intrinsics are never contracted into FMAs.
 #define MILB_PACKED_F32X2 1
 MILB_HD float2 cadd(float2 a, float2 b) { return __fadd2_rn(a, b); }
 MILB_HD float2 csub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
