@@ -52,6 +52,11 @@ constexpr int TXF = (N / R0) * L;                   // threads of the non-persis
 constexpr bool kXWide = MILB_X_WIDE || (MILB_X_WIDE512 && N == 512) || (MILB_X_WIDE_NP2 && !kPow2);
 constexpr int XL = pow2_floor((kXWide ? 8192 : kXNarrow ? 2048 : 4096) / N), XT = (N / R0) * XL;
 constexpr int XCTAS = xpassP_ctas<N, XL, XT>();
+// MILB_X_TMA (default): tiles of the persistent X pass loaded by the copy engine (k_xpassP XTMA) where its tile loop is the folded one
+#ifndef MILB_X_TMA
+#define MILB_X_TMA 1
+#endif
+constexpr bool kXTma = MILB_X_TMA && MILB_X_FOLD && kPow2 && (FastPlan<N>::S == 2) && (XL == 16) && (R0 * XL <= XT) && ((N / 2) % 128 == 0);
 constexpr size_t SMX = (size_t)(2 * N * XL + 2 * (N / 2 + 1) * XL + N) * sizeof(float2);
 // MILB_Y_BUFS: landing buffers of the TMA-fed in-place Y passes (2 or 3).  Three keep two 64 KB tiles per SM in flight; measured
 // at 512^3 that is SLOWER (Y forward 179 -> 199 us, Y inverse 177 -> 190 us, 1.93 -> 2.00 ms per iteration), so the default is 2.
@@ -79,6 +84,18 @@ bool make_tile_map(TileMap &tm, const void *base, int cols, long long rows_total
 	const cuuint64_t gdim[2] = {(cuuint64_t)2 * cols, (cuuint64_t)rows_total};
 	const cuuint64_t gstride[1] = {(cuuint64_t)cols * sizeof(float2)};
 	const cuuint32_t box[2] = {(cuuint32_t)2 * PL, (cuuint32_t)(N < 256 ? N : 256)};
+	const cuuint32_t estr[2] = {1, 1};
+	return g_encode(&tm.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+			   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+// general 2-D float tensor [rows][width floats], row pitch in bytes, box = box_w floats x box_rows rows
+bool make_map2d(TileMap &tm, const void *base, long long width_floats, long long rows, long long pitch_bytes, int box_w, int box_rows)
+{
+	if (!g_encode) return false;
+	const cuuint64_t gdim[2] = {(cuuint64_t)width_floats, (cuuint64_t)rows};
+	const cuuint64_t gstride[1] = {(cuuint64_t)pitch_bytes};
+	const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_rows};
 	const cuuint32_t estr[2] = {1, 1};
 	return g_encode(&tm.m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
 			   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
@@ -158,10 +175,41 @@ template <int M> struct Pipe<M, true> {
 	}
 };
 
+// the persistent X pass with copy-engine loads; false if the tensor maps cannot be built (then the cp.async kernel runs)
+template <int M_, bool OK = kXTma> struct XTma {
+	static bool run(int, float2 *, const float2 *, float4 *, const float2 *, long long, long long, int, int, cudaStream_t) { return false; }
+	static int setup() { return 0; }
+};
+template <int M_> struct XTma<M_, true> {
+	static int setup()
+	{
+		return optin(k_xpassP<M_, XL, XT, XF_RATIO, false, true>, SMX) | optin(k_xpassP<M_, XL, XT, XF_UPDATE, false, true>, SMX) |
+			   optin(k_xpassP<M_, XL, XT, XF_UPDATE_LAST, false, true>, SMX);
+	}
+	static bool run(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const float2 *tw, long long M, long long ncols, int ntiles, int grid,
+		cudaStream_t st)
+	{
+		// measured at 512^3: ratio pass 309 -> 278 us with the copy-engine loads, update pass 377 -> 396 us (it is the HBM-bound one
+		// of the two and stores E in place while the next tile's E rows are requested), so only the ratio pass uses them
+		if (!g_use_tma || mode != XF_RATIO) return false;
+		constexpr int half = M_ / 2;
+		TileMap sm_, sl_, am_;
+		const float2 *auxsrc = (mode == XF_RATIO) ? aux : (const float2 *)vol_io;
+		if (!make_map2d(sm_, spec, 4 * ncols, half + 1, M * (long long)sizeof(float4), 4 * XL, half < 256 ? half : 256)) return false;
+		if (!make_map2d(sl_, spec, 4 * ncols, half + 1, M * (long long)sizeof(float4), 4 * XL, 1)) return false;
+		if (!make_map2d(am_, auxsrc, 2 * ncols, M_, M * (long long)sizeof(float2), 2 * XL, M_ < 256 ? M_ : 256)) return false;
+		if (mode == XF_RATIO) k_xpassP<M_, XL, XT, XF_RATIO, false, true><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles, PeerMap(), sm_, sl_, am_);
+		else if (mode == XF_UPDATE) k_xpassP<M_, XL, XT, XF_UPDATE, false, true><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles, PeerMap(), sm_, sl_, am_);
+		else k_xpassP<M_, XL, XT, XF_UPDATE_LAST, false, true><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles, PeerMap(), sm_, sl_, am_);
+		return true;
+	}
+};
+
 int setup()
 {
 	int bad = 0;
 	bad |= Pipe<N>::setup();
+	bad |= XTma<N>::setup();
 	bad |= ZRow<N>::setup();
 	bad |= optin(k_ypassF<N, PL, PT, false>, SMP2);
 	bad |= optin(k_xpassF<N, L, TXF, XF_FWD_REAL>, SM1);
@@ -218,6 +266,7 @@ void xpass_cols(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const
 {
 	if (mode != XF_FWD_REAL && (ncols % XL) == 0) {
 		const int ntiles = (int)(ncols / XL), cap = XCTAS * g_sms, grid = ntiles < cap ? ntiles : cap;
+		if (XTma<N>::run(mode, vol_io, aux, spec, tw, M, ncols, ntiles, grid, st)) return;
 		if (mode == XF_RATIO) k_xpassP<N, XL, XT, XF_RATIO><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles);
 		else if (mode == XF_UPDATE) k_xpassP<N, XL, XT, XF_UPDATE><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles);
 		else k_xpassP<N, XL, XT, XF_UPDATE_LAST><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles);

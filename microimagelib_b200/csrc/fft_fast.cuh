@@ -1281,15 +1281,20 @@ template <int R0> __device__ __forceinline__ int xfold_row(int slot)
 	return w == 0 ? (h ? R0 / 2 : 0) : (h ? R0 - w : w);
 }
 
-template <int N, int L, int T, int MODE, bool PEER = false>
+// XTMA: the half-spectrum rows and the aux rows of a tile arrive by the copy engine (three tensor maps: spectrum rows in boxes of
+// min(N / 2, 256) rows, the last spectrum row, aux rows; one mbarrier per landing buffer) instead of 16 cp.async per thread,
+// whose issue loops with their address arithmetic were a tenth of the pass's stall samples.
+template <int N, int L, int T, int MODE, bool PEER = false, bool XTMA = false>
 __global__ void __launch_bounds__(T, xpassP_ctas<N, L, T>())
 k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M, int ntiles,
-	const __grid_constant__ PeerMap pm = PeerMap())
+	const __grid_constant__ PeerMap pm = PeerMap(), const __grid_constant__ TileMap smap = TileMap(), const __grid_constant__ TileMap slast = TileMap(),
+	const __grid_constant__ TileMap amap = TileMap())
 {
 	using P = FastPlan<N>;
 	constexpr int R0 = P::r0;
 	static_assert((N / R0) * L == T, "stage 0 must be one butterfly per thread");
-	extern __shared__ float2 sm[];
+	extern __shared__ __align__(128) float2 sm[];
+	__shared__ __align__(8) unsigned long long xbar[2]; // XTMA: spectrum / aux landing buffer filled
 	constexpr int half = N / 2, M0 = N / R0;
 	float2 *W = sm;
 	float4 *SL = (float4 *)(sm + N * L);
@@ -1310,25 +1315,56 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 	const int pA0 = fast_pos<N>(k0) * L + lane0;                    // position of row k0 (+ lane)
 	const int pB0 = fast_pos<N>((RIT - k0) % RIT) * L + lane0;      // position of the low bits of N - k0 (+ lane)
 
+	if constexpr (XTMA) {
+		static_assert(L * sizeof(float4) >= 128 && (N / 2) % 128 == 0, "box shapes of the X-pass tensor maps");
+		if (threadIdx.x == 0) {
+			mbar_init(&xbar[0], 1);
+			mbar_init(&xbar[1], 1);
+			asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+		}
+		__syncthreads();
+	}
+	constexpr int SROWS = (half < 256) ? half : 256, AROWS = (N < 256) ? N : 256; // rows per box
 	auto load_spec = [&](int t) {
-		const float4 *src = spec + (long long)t * L;
-		for (int c = threadIdx.x; c < (half + 1) * L; c += T) cp_async16(SL + c, src + (long long)(c / L) * M + (c % L));
+		if constexpr (XTMA) {
+			if (threadIdx.x == 0) {
+				asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+				mbar_expect_tx(&xbar[0], (unsigned)((half + 1) * L * sizeof(float4)));
+#pragma unroll
+				for (int r = 0; r < half; r += SROWS) tma_load_2d(SL + r * L, &smap, 4 * t * L, r, &xbar[0]);
+				tma_load_2d(SL + half * L, &slast, 4 * t * L, half, &xbar[0]);
+			}
+		} else {
+			const float4 *src = spec + (long long)t * L;
+			for (int c = threadIdx.x; c < (half + 1) * L; c += T) cp_async16(SL + c, src + (long long)(c / L) * M + (c % L));
+		}
 	};
 	auto load_aux = [&](int t) {
-		const float2 *src = auxsrc + (long long)t * L;
-		constexpr int CPR = L / 2;
-		for (int c = threadIdx.x; c < N * CPR; c += T) cp_async16(AL + (c / CPR) * L + 2 * (c % CPR), src + (long long)(c / CPR) * M + 2 * (c % CPR));
+		if constexpr (XTMA) {
+			if (threadIdx.x == 0) {
+				asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+				mbar_expect_tx(&xbar[1], (unsigned)(N * L * sizeof(float2)));
+#pragma unroll
+				for (int r = 0; r < N; r += AROWS) tma_load_2d(AL + r * L, &amap, 2 * t * L, r, &xbar[1]);
+			}
+		} else {
+			const float2 *src = auxsrc + (long long)t * L;
+			constexpr int CPR = L / 2;
+			for (int c = threadIdx.x; c < N * CPR; c += T) cp_async16(AL + (c / CPR) * L + 2 * (c % CPR), src + (long long)(c / CPR) * M + 2 * (c % CPR));
+		}
 	};
 
+	static_assert(!XTMA || kFold, "the copy-engine loads are wired into the folded tile loop only");
 	int t = blockIdx.x;
 	if (t < ntiles) load_spec(t);
 	cp_async_commit();
 	if (t < ntiles) load_aux(t);
 	cp_async_commit();
-	for (; t < ntiles; t += gridDim.x) {
+	for (int it = 0; t < ntiles; t += gridDim.x, it++) {
 		const long long col0 = (long long)t * L;
 		const int tn = t + gridDim.x;
-		cp_async_wait<1>(); // spectrum of this tile landed (the aux group may still be in flight)
+		if constexpr (XTMA) mbar_wait(&xbar[0], it & 1);
+		else cp_async_wait<1>(); // spectrum of this tile landed (the aux group may still be in flight)
 		__syncthreads();
 		if constexpr (kFold) {
 			if (threadIdx.x < R0 * L) {
@@ -1351,7 +1387,8 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 #pragma unroll
 				for (int b = 0; b < R1; b++) W[(R1 * frow + b) * L + lane0] = v[b];
 			}
-			cp_async_wait<0>(); // aux of this tile landed
+			if constexpr (XTMA) mbar_wait(&xbar[1], it & 1);
+			else cp_async_wait<0>(); // aux of this tile landed
 			__syncthreads();    // W complete, SL consumed, everybody's aux rows visible
 			if (tn < ntiles) load_spec(tn);
 			cp_async_commit();
