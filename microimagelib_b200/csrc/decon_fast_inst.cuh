@@ -56,6 +56,10 @@ constexpr int XCTAS = xpassP_ctas<N, XL, XT>();
 #ifndef MILB_X_TMA
 #define MILB_X_TMA 1
 #endif
+// update pass: 0 = cp.async for both landing buffers, 1 = copy engine for both, 2 = copy engine for the spectrum rows only
+#ifndef MILB_X_TMA_UPDATE
+#define MILB_X_TMA_UPDATE 0
+#endif
 constexpr bool kXTma = MILB_X_TMA && MILB_X_FOLD && kPow2 && (FastPlan<N>::S == 2) && (XL == 16) && (R0 * XL <= XT) && ((N / 2) % 128 == 0);
 constexpr size_t SMX = (size_t)(2 * N * XL + 2 * (N / 2 + 1) * XL + N) * sizeof(float2);
 // MILB_Y_BUFS: landing buffers of the TMA-fed in-place Y passes (2 or 3).  Three keep two 64 KB tiles per SM in flight; measured
@@ -183,24 +187,25 @@ template <int M_, bool OK = kXTma> struct XTma {
 template <int M_> struct XTma<M_, true> {
 	static int setup()
 	{
-		return optin(k_xpassP<M_, XL, XT, XF_RATIO, false, true>, SMX) | optin(k_xpassP<M_, XL, XT, XF_UPDATE, false, true>, SMX) |
-			   optin(k_xpassP<M_, XL, XT, XF_UPDATE_LAST, false, true>, SMX);
+		return optin(k_xpassP<M_, XL, XT, XF_RATIO, false, 1>, SMX) | optin(k_xpassP<M_, XL, XT, XF_UPDATE, false, MILB_X_TMA_UPDATE>, SMX) |
+			   optin(k_xpassP<M_, XL, XT, XF_UPDATE_LAST, false, MILB_X_TMA_UPDATE>, SMX);
 	}
 	static bool run(int mode, float2 *vol_io, const float2 *aux, float4 *spec, const float2 *tw, long long M, long long ncols, int ntiles, int grid,
 		cudaStream_t st)
 	{
 		// measured at 512^3: ratio pass 309 -> 278 us with the copy-engine loads, update pass 377 -> 396 us (it is the HBM-bound one
 		// of the two and stores E in place while the next tile's E rows are requested), so only the ratio pass uses them
-		if (!g_use_tma || mode != XF_RATIO) return false;
+		if (!g_use_tma || (mode != XF_RATIO && MILB_X_TMA_UPDATE == 0)) return false;
 		constexpr int half = M_ / 2;
 		TileMap sm_, sl_, am_;
 		const float2 *auxsrc = (mode == XF_RATIO) ? aux : (const float2 *)vol_io;
 		if (!make_map2d(sm_, spec, 4 * ncols, half + 1, M * (long long)sizeof(float4), 4 * XL, half < 256 ? half : 256)) return false;
 		if (!make_map2d(sl_, spec, 4 * ncols, half + 1, M * (long long)sizeof(float4), 4 * XL, 1)) return false;
 		if (!make_map2d(am_, auxsrc, 2 * ncols, M_, M * (long long)sizeof(float2), 2 * XL, M_ < 256 ? M_ : 256)) return false;
-		if (mode == XF_RATIO) k_xpassP<M_, XL, XT, XF_RATIO, false, true><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles, PeerMap(), sm_, sl_, am_);
-		else if (mode == XF_UPDATE) k_xpassP<M_, XL, XT, XF_UPDATE, false, true><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles, PeerMap(), sm_, sl_, am_);
-		else k_xpassP<M_, XL, XT, XF_UPDATE_LAST, false, true><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles, PeerMap(), sm_, sl_, am_);
+		if (mode == XF_RATIO) k_xpassP<M_, XL, XT, XF_RATIO, false, 1><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles, PeerMap(), sm_, sl_, am_);
+		else if (mode == XF_UPDATE)
+			k_xpassP<M_, XL, XT, XF_UPDATE, false, MILB_X_TMA_UPDATE><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles, PeerMap(), sm_, sl_, am_);
+		else k_xpassP<M_, XL, XT, XF_UPDATE_LAST, false, MILB_X_TMA_UPDATE><<<grid, XT, SMX, st>>>(vol_io, aux, spec, tw, M, ntiles, PeerMap(), sm_, sl_, am_);
 		return true;
 	}
 };

@@ -1284,7 +1284,8 @@ template <int R0> __device__ __forceinline__ int xfold_row(int slot)
 // XTMA: the half-spectrum rows and the aux rows of a tile arrive by the copy engine (three tensor maps: spectrum rows in boxes of
 // min(N / 2, 256) rows, the last spectrum row, aux rows; one mbarrier per landing buffer) instead of 16 cp.async per thread,
 // whose issue loops with their address arithmetic were a tenth of the pass's stall samples.
-template <int N, int L, int T, int MODE, bool PEER = false, bool XTMA = false>
+// XTMA = 2: the spectrum rows only (the aux rows by cp.async).
+template <int N, int L, int T, int MODE, bool PEER = false, int XTMA = 0>
 __global__ void __launch_bounds__(T, xpassP_ctas<N, L, T>())
 k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__restrict__ spec, const float2 *__restrict__ g_tw, long long M, int ntiles,
 	const __grid_constant__ PeerMap pm = PeerMap(), const __grid_constant__ TileMap smap = TileMap(), const __grid_constant__ TileMap slast = TileMap(),
@@ -1340,7 +1341,7 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 		}
 	};
 	auto load_aux = [&](int t) {
-		if constexpr (XTMA) {
+		if constexpr (XTMA == 1) {
 			if (threadIdx.x == 0) {
 				asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
 				mbar_expect_tx(&xbar[1], (unsigned)(N * L * sizeof(float2)));
@@ -1387,7 +1388,7 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 #pragma unroll
 				for (int b = 0; b < R1; b++) W[(R1 * frow + b) * L + lane0] = v[b];
 			}
-			if constexpr (XTMA) mbar_wait(&xbar[1], it & 1);
+			if constexpr (XTMA == 1) mbar_wait(&xbar[1], it & 1);
 			else cp_async_wait<0>(); // aux of this tile landed
 			__syncthreads();    // W complete, SL consumed, everybody's aux rows visible
 			if (tn < ntiles) load_spec(tn);
