@@ -245,3 +245,27 @@ def test_row_convolution_equals_the_transposing_plane_kernels(shape, dual):
         assert rel_l2(outs[0], outs[1]) <= 1e-6
     else:
         assert np.array_equal(outs[0], outs[1])
+
+
+def test_plane_pipeline_equals_the_three_launches(monkeypatch):
+    """MILB_PLANE_PIPE=1 (Y forward | row convolution | Y inverse side by side on disjoint SMs, planes handed over through
+    per-plane counters): an experiment that is off by default, but it must stay bit-identical to the three launches and must
+    not hang (its polls trap)."""
+    from microimagelib_b200 import device
+    shape = (64, 256, 256)
+    psf = synth.gaussian_psf((17, 17, 17), (2.5, 2.0, 1.5))
+    img = synth.bead_image(shape, psf, density=1 / 4096.0)
+    outs = []
+    for pipe in ("1", "0"):
+        monkeypatch.setenv("MILB_PLANE_PIPE", pipe)
+        d = device.Decon(shape, 1)
+        assert d.row_convolution()
+        d.set_psf(0, psf)
+        d.set_image(0, img)
+        d.run(4)
+        outs.append(d.result().copy())
+        if pipe == "1":
+            ms = d.time_pipe(2)
+            assert ms.shape == (4,) and (ms > 0).all()
+        d.close()
+    assert np.array_equal(outs[0], outs[1])
