@@ -451,7 +451,7 @@ static void plane_stage(milb_decon *h, const float2 *otf, float scale, cudaStrea
 			oy->pass_fwd(h->S, h->py.d_tw, h->Z, 0, planes, st);
 			if (otf) {
 				oz->conv_rows(h->S, otf, h->pz.d_tw, rows, st);
-				oy->pass_inv(h->S, h->py.d_tw, h->Z, 0, planes, st);
+				oy->pass_inv_rows(h->S, h->py.d_tw, h->Z, 0, planes, st);
 				milb_count_launches(3);
 			} else {
 				oz->fwd_rows(h->S, h->pz.d_tw, rows, scale, st); // spectrum stays in S, rows in k_zrow's OTF order
@@ -763,7 +763,7 @@ int milb_decon_time_kernels(milb_decon_t *h, int reps, float *ms5, void *stream)
 				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
 				oz->conv_rows(h->S, otf, h->pz.d_tw, (long long)planes * h->Y, st);
 				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
-				oy->pass_inv(h->S, h->py.d_tw, h->Z, 0, planes, st);
+				oy->pass_inv_rows(h->S, h->py.d_tw, h->Z, 0, planes, st);
 				MILB_CUDA_TRY(cudaEventRecord(ev[k++], st));
 			} else {
 				oy->passT(h->S, h->S2, h->py.d_tw, h->Z, 0, planes, st);

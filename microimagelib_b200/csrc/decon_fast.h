@@ -65,8 +65,11 @@ struct FastAxisOps {
 	// square planes (n x n): Y forward, Z forward * otf, Z inverse, Y inverse of all planes in ONE persistent launch whose
 	// intermediates stay in L2 (k_planes_fused); returns false if the kernel cannot run (not enough co-resident CTAs)
 	bool (*planes_fused)(float2 *S, const float2 *otf, const float2 *tw, PlaneFuse *pf, cudaStream_t st) = nullptr;
-	// in-place forward along rows: planes [n rows][cols] (the Y pass in front of conv_rows)
+	// in-place forward along rows: planes [n rows][cols] (the Y pass in front of conv_rows), and the inverses that belong to it
+	// (at n = 1024 this trio is k_ypassW with its own position order; elsewhere the same kernels as pass_inv / pass_inv_peer)
 	void (*pass_fwd)(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st) = nullptr;
+	void (*pass_inv_rows)(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st) = nullptr;
+	void (*pass_inv_peer_rows)(const float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, const PeerMap *pm, cudaStream_t st) = nullptr;
 	// rows of n contiguous points, in place: forward, * otf (per-row order of k_zrow), inverse -- nullptr if the length has no
 	// two-stage plan.  fwd_rows: forward only, scaled, rows left in that order (OTF generation)
 	void (*conv_rows)(float2 *spec, const float2 *otf, const float2 *tw, long long rows, cudaStream_t st) = nullptr;

@@ -210,9 +210,32 @@ template <int M_> struct XTma<M_, true> {
 	}
 };
 
+// Y passes of the row-convolution mode at N = 1024: k_ypassW (16-lane single-buffer tiles, two radix-32 stages).  Its Y position
+// order differs from FastPlan<1024>'s, so a handle uses it for ALL its Y transforms or for none: g_ywide is decided once, in setup().
+constexpr bool kYWide = (N == 1024);
+bool g_ywide = false;
+template <int M, bool OK = (M == 1024)> struct YWide {
+	static int setup() { return 0; }
+	static void run(bool, float2 *, const float2 *, int, int, int, const PeerMap *, cudaStream_t) {}
+};
+template <int M> struct YWide<M, true> {
+	static constexpr size_t SMW = (size_t)(M * 16 + M) * sizeof(float2);
+	static int setup() { return optin(k_ypassW<M, false>, SMW) | optin(k_ypassW<M, true>, SMW) | optin(k_ypassW<M, true, true>, SMW); }
+	static void run(bool inv, float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, const PeerMap *pm, cudaStream_t st)
+	{
+		TileMap tm;
+		make_map2d(tm, spec, 2ll * cols, (long long)M * (plane0 + nplanes), (long long)cols * sizeof(float2), 32, 256);
+		const int tiles = (cols / 16) * nplanes, cap = (g_cap > 0 && g_cap < g_sms) ? g_cap : g_sms, grid = tiles < cap ? tiles : cap;
+		if (pm) k_ypassW<M, true, true><<<grid, 512, SMW, st>>>(spec, tw, cols, plane0, nplanes, *pm, tm);
+		else if (inv) k_ypassW<M, true><<<grid, 512, SMW, st>>>(spec, tw, cols, plane0, nplanes, PeerMap(), tm);
+		else k_ypassW<M, false><<<grid, 512, SMW, st>>>(spec, tw, cols, plane0, nplanes, PeerMap(), tm);
+	}
+};
+
 int setup()
 {
 	int bad = 0;
+	bad |= YWide<N>::setup();
 	bad |= Pipe<N>::setup();
 	bad |= XTma<N>::setup();
 	bad |= ZRow<N>::setup();
@@ -246,6 +269,8 @@ int setup()
 		bad |= optin(k_ypassF<N, PL, PT, false, false, true, false, YB>, SMPY);
 		bad |= optin(k_ypassF<N, PL, PT, true, false, true, false, YB>, SMPY);
 		bad |= optin(k_ypassF<N, PL, PT, true, true, true>, SMP2);
+	}
+	if constexpr (kTmaTiles || kYWide) {
 		const char *e = getenv("MILB_TMA");
 		if (!(e && e[0] == '0')) {
 			void *fn = nullptr;
@@ -255,6 +280,8 @@ int setup()
 				g_use_tma = true;
 			}
 		}
+		const char *we = getenv("MILB_Y_WIDE");
+		g_ywide = kYWide && g_use_tma && !(we && we[0] == '0');
 	}
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
@@ -341,8 +368,23 @@ void pass_inv(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes,
 	k_ypassF<N, PL, PT, true><<<tiles < g_ctas ? tiles : g_ctas, PT, SMP2, st>>>(spec, tw, cols, plane0, nplanes);
 }
 
+void pass_inv(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st);
+void pass_inv_peer(const float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, const PeerMap *pm, cudaStream_t st);
+// the Y inverse that belongs to pass_fwd (row-convolution mode): the same kernels except at N = 1024
+void pass_inv_rows(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
+{
+	if (g_ywide && cols % 16 == 0) { YWide<N>::run(true, spec, tw, cols, plane0, nplanes, nullptr, st); return; }
+	pass_inv(spec, tw, cols, plane0, nplanes, st);
+}
+void pass_inv_peer_rows(const float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, const PeerMap *pm, cudaStream_t st)
+{
+	if (g_ywide && cols % 16 == 0) { YWide<N>::run(true, const_cast<float2 *>(spec), tw, cols, plane0, nplanes, pm, st); return; }
+	pass_inv_peer(spec, tw, cols, plane0, nplanes, pm, st);
+}
+
 void pass_fwd(float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, cudaStream_t st)
 {
+	if (g_ywide && cols % 16 == 0) { YWide<N>::run(false, spec, tw, cols, plane0, nplanes, nullptr, st); return; }
 	const int tiles = (cols / PL) * nplanes;
 	if constexpr (kTmaTiles) {
 		TileMap tm;
@@ -411,6 +453,7 @@ const FastAxisOps *MILB_CAT(milb_fast_ops_, MILB_FAST_N)()
 	static FastAxisOps ops;
 	ops.n = N; ops.lanes = L; ops.xlanes = XL > L ? XL : L; ops.setup = setup; ops.xpass = xpass; ops.xpass_cols = xpass_cols; ops.passT = passT; ops.pass_inv = pass_inv;
 	ops.convT = convT; ops.fwd_scaled = fwd_scaled; ops.planes_fused = kPow2 ? planes_fused : nullptr;
+	ops.pass_inv_rows = pass_inv_rows; ops.pass_inv_peer_rows = kPow2 ? pass_inv_peer_rows : nullptr;
 	ops.pass_fwd = pass_fwd; ops.conv_rows = ZPlan<N>::ok ? conv_rows : nullptr; ops.fwd_rows = ZPlan<N>::ok ? fwd_rows : nullptr;
 	ops.planes_pipe = (kTmaTiles && ZPlan<N>::ok) ? planes_pipe : nullptr;
 	ops.xpass_peer = kPow2 ? xpass_peer : nullptr; ops.pass_inv_peer = kPow2 ? pass_inv_peer : nullptr; ops.grid_cap = &g_cap;

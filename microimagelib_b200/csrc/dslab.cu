@@ -106,7 +106,7 @@ extern "C" int milb_dslab_planes(milb_dslab_t *h, void *S, void *S2, const void 
 		oy->pass_fwd((float2 *)S, h->tw[1], h->Z, 0, h->np, st);
 		if (otf) {
 			oz->conv_rows((float2 *)S, (const float2 *)otf, h->tw[2], rows, st);
-			oy->pass_inv((float2 *)S, h->tw[1], h->Z, 0, h->np, st);
+			oy->pass_inv_rows((float2 *)S, h->tw[1], h->Z, 0, h->np, st);
 			milb_count_launches(3);
 		} else {
 			oz->fwd_rows((float2 *)S, h->tw[2], rows, scale, st);
@@ -245,7 +245,8 @@ extern "C" int milb_dslab_planes_peer(milb_dslab_t *h, void *S, void *S2, const 
 			oy->passT((const float2 *)S, (float2 *)S2, h->tw[1], h->Z, 0, h->np, st);
 			oz->convT((float2 *)S2, (float2 *)S, (const float2 *)otf, h->tw[2], h->Y, 0, h->np, st);
 		}
-		oy->pass_inv_peer((const float2 *)S, h->tw[1], h->Z, 0, h->np, &h->to_slabs, st);
+		if (h->zrow) oy->pass_inv_peer_rows((const float2 *)S, h->tw[1], h->Z, 0, h->np, &h->to_slabs, st);
+		else oy->pass_inv_peer((const float2 *)S, h->tw[1], h->Z, 0, h->np, &h->to_slabs, st);
 		milb_count_launches(3);
 		MILB_CUDA_TRY(cudaGetLastError());
 		return MILB_OK;
@@ -272,7 +273,8 @@ extern "C" int milb_dslab_planes_peer(milb_dslab_t *h, void *S, void *S2, const 
 		MILB_CUDA_TRY(cudaEventRecord(h->ev_z[c], st));
 		MILB_CUDA_TRY(cudaStreamWaitEvent(h->side, h->ev_z[c], 0));
 		*cap_y = (c == C - 1) ? 0 : h->side_ctas;
-		oy->pass_inv_peer((const float2 *)S, h->tw[1], h->Z, p0, p1 - p0, &h->to_slabs, h->side);
+		if (h->zrow) oy->pass_inv_peer_rows((const float2 *)S, h->tw[1], h->Z, p0, p1 - p0, &h->to_slabs, h->side);
+		else oy->pass_inv_peer((const float2 *)S, h->tw[1], h->Z, p0, p1 - p0, &h->to_slabs, h->side);
 	}
 	*cap_y = *cap_z = 0;
 	MILB_CUDA_TRY(cudaEventRecord(h->ev_done, h->side));

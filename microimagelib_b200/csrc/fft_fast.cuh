@@ -768,6 +768,78 @@ k_ypassF(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int 
 	if constexpr (PEER) __threadfence_system();
 }
 
+// ------------------------------------------------------------------------------------------------
+// Y pass for N = 1024 next to the row convolution: ONE 16-lane tile (1024 rows x 128 bytes = 128 KB) per SM, in place,
+// two radix-32 stages (one exchange), 512 threads, one butterfly per thread and stage.  k_ypassF's 8192-point tiles are only
+// 8 lanes wide at this length -- 64-byte rows, which the memory system serves at little more than half rate (0.61 of the
+// HBM peak) -- and 16 lanes leave no room for a second landing buffer, so the next tile is requested as soon as every thread
+// has taken its inputs of the LAST stage into registers: the copy then runs behind that stage's butterflies and stores.
+// The length's position order here is the two-stage one (frequency k1 + 32 k2 at row 32 k1 + k2), private to the handles
+// that use this kernel for every Y transform (the row-convolution mode); PEER as in k_ypassF.
+template <int N, bool INV, bool PEER = false>
+__global__ void __launch_bounds__(512, 1)
+k_ypassW(float2 *__restrict__ spec, const float2 *__restrict__ g_tw, int Z, int plane0, int nplanes, const __grid_constant__ PeerMap pm,
+	const __grid_constant__ TileMap tmap)
+{
+	constexpr int L = 16, T = 512, R = 32;
+	static_assert(N == R * R && T == (N / R) * L, "two radix-32 stages, one butterfly per thread");
+	extern __shared__ __align__(128) float2 sm[];
+	float2 *tile = sm, *tw = sm + N * L;
+	__shared__ __align__(8) unsigned long long bar;
+	if (threadIdx.x == 0) {
+		mbar_init(&bar, 1);
+		asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+	}
+	load_tw<N>(tw, g_tw);
+	__syncthreads();
+	const int tpp = Z / L, ntiles = nplanes * tpp;
+	const int lane = threadIdx.x % L, q = threadIdx.x / L;
+	auto issue = [&](int t) { tma_tile_load<N, L>(tile, &tmap, (t / tpp + plane0) * N, (t % tpp) * L, &bar); };
+	int t = blockIdx.x;
+	if (t < ntiles && threadIdx.x == 0) issue(t);
+	for (int it = 0; t < ntiles; t += gridDim.x, it++) {
+		const int tn = t + gridDim.x;
+		mbar_wait(&bar, it & 1);
+		float2 v[R];
+		// first stage in place: forward = stride-32 butterflies with twiddles, inverse = the 32 consecutive rows of block q
+#pragma unroll
+		for (int j = 0; j < R; j++) v[j] = tile[(INV ? (R * q + j) : (q + R * j)) * L + lane];
+		fbfly<R, INV>(v);
+		if (!INV) {
+#pragma unroll
+			for (int j = 1; j < R; j++) v[j] = cmul(v[j], tw[q * j]);
+		}
+#pragma unroll
+		for (int j = 0; j < R; j++) tile[(INV ? (R * q + j) : (q + R * j)) * L + lane] = v[j];
+		__syncthreads();
+		// last stage: inputs to registers, then the tile is free for the next one
+#pragma unroll
+		for (int j = 0; j < R; j++) v[j] = tile[(INV ? (q + R * j) : (R * q + j)) * L + lane];
+		__syncthreads();
+		if (tn < ntiles && threadIdx.x == 0) issue(tn);
+		if (INV) {
+#pragma unroll
+			for (int j = 1; j < R; j++) v[j] = cmulc(v[j], tw[q * j]);
+		}
+		fbfly<R, INV>(v);
+		if constexpr (PEER) {
+			static_assert(INV, "the exchange follows the inverse pass");
+			const long long kx = pm.p0[pm.me] + plane0 + t / tpp;
+			const long long off = kx * pm.ny * (long long)Z + (long long)(t % tpp) * L + lane;
+#pragma unroll
+			for (int j = 0; j < R; j++) {
+				const int r = q + R * j, d = r >> pm.log2ny;
+				((float2 *)pm.base[d])[off + (long long)(r & (pm.ny - 1)) * Z] = v[j];
+			}
+		} else {
+			float2 *p = spec + (long long)(t / tpp + plane0) * N * Z + (long long)(t % tpp) * L + lane;
+#pragma unroll
+			for (int j = 0; j < R; j++) p[(long long)(INV ? (q + R * j) : (R * q + j)) * Z] = v[j];
+		}
+	}
+	if constexpr (PEER) __threadfence_system();
+}
+
 // Z pass on the transposed planes: in [N = Z rows][Yc], lanes along ky'.
 //   CONV : forward, * otf (same layout as `in`), inverse, transposed out [Yc rows][N = Z]
 //   !CONV: forward only, in place, scaled (OTF generation)

@@ -136,6 +136,7 @@ def test_device_resident_handle_matches_host_api():
 
 
 FAST_SHAPES = [(64, 128, 256), (256, 64, 128), (128, 512, 64), (64, 64, 1024), (512, 64, 128), (1024, 64, 64), (128, 256, 512),
+               (64, 1024, 64), (64, 1024, 1024),   # Y = 1024: k_ypassW (16-lane single-buffer tiles) next to the row convolution
                # the 64*k lengths of the compile-time plans, each in every axis role (X pencils / Y planes / Z planes)
                (192, 320, 64), (320, 64, 192), (64, 192, 320), (384, 448, 64), (448, 64, 384), (64, 384, 448),
                (576, 64, 640), (64, 640, 576), (640, 576, 64), (768, 64, 192), (64, 768, 128), (128, 64, 768)]
@@ -223,7 +224,7 @@ def test_pipelined_host_copies_give_the_same_volume(shape, dual, monkeypatch):
 
 
 @pytest.mark.parametrize("shape,dual", [((64, 64, 64), False), ((64, 128, 128), True), ((128, 64, 256), False), ((64, 192, 512), False),
-                                        ((64, 320, 128), True), ((64, 64, 1024), False)])
+                                        ((64, 320, 128), True), ((64, 64, 1024), False), ((64, 1024, 128), False)])
 def test_row_convolution_equals_the_transposing_plane_kernels(shape, dual):
     """k_zrow (Z convolution along the contiguous axis, warp-private pencils, OTFs in its per-row order) runs the same
     butterflies in the same order as k_ypassT + k_zconvT: bit-identical volumes for the lengths that share FastPlan's
@@ -241,7 +242,7 @@ def test_row_convolution_equals_the_transposing_plane_kernels(shape, dual):
         d.run(5)
         outs.append(d.result().copy())
         d.close()
-    if shape[2] == 1024:
+    if 1024 in shape[1:]:   # Z = 1024: the row kernel's 32 x 32 plan; Y = 1024: k_ypassW's, against 8 x 8 x 4 x 4
         assert rel_l2(outs[0], outs[1]) <= 1e-6
     else:
         assert np.array_equal(outs[0], outs[1])

@@ -38,12 +38,12 @@ def _single_gpu(shape, dual, iters):
     return out
 
 
+@pytest.mark.parametrize("shape", [(64, 128, 128), (64, 1024, 128)])   # the second: Y = 1024, k_ypassW and its peer-store variant
 @pytest.mark.parametrize("fused", [False, True])
 @pytest.mark.parametrize("dual", [False, True])
-def test_one_rank_distributed_path_equals_single_gpu_path(dual, fused):
+def test_one_rank_distributed_path_equals_single_gpu_path(dual, fused, shape):
     import torch
     from microimagelib_b200.dist_decon import DistDecon
-    shape = (64, 128, 128)
     a, b, pa, pb = _inputs(shape, dual)
     dd = DistDecon(shape, 2 if dual else 1, fused=fused)
     assert dd.fused == fused
@@ -68,10 +68,10 @@ from microimagelib_b200.dist_decon import DistDecon
 rank = int(os.environ["RANK"]); local = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-shape, dual, iters = (64, 128, 128), True, 3
-a, b, pa, pb = T._inputs(shape, dual)
-ref = T._single_gpu(shape, dual, iters) if rank == 0 else None
-for fused in (False, True):
+dual, iters = True, 3
+for shape, fused in (((64, 128, 128), False), ((64, 128, 128), True), ((64, 1024, 128), True)):
+    a, b, pa, pb = T._inputs(shape, dual)
+    ref = T._single_gpu(shape, dual, iters) if rank == 0 else None
     dd = DistDecon(shape, 2, fused=fused)
     assert dd.fused == fused
     L = dd.L
@@ -104,6 +104,6 @@ def test_two_ranks_nccl_and_fused_exchange(tmp_path):
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if l.startswith("DIST_EQUAL")]
-    assert len(lines) == 2, r.stdout[-1500:] + r.stderr[-3000:]
-    for line in lines:                            # the NCCL all-to-all path and the fused peer-store path
+    assert len(lines) == 3, r.stdout[-1500:] + r.stderr[-3000:]
+    for line in lines:                            # the NCCL all-to-all path, the fused peer-store path, and the latter at Y = 1024
         assert line.split()[2] == "True", line
