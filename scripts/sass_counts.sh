@@ -9,7 +9,7 @@ echo "# cuobjdump -sass of microimagelib_b200/build/*.o (sm_100a), instruction c
 echo "# UTMALDG = TMA tile load (cp.async.bulk.tensor), SYNCS = mbarrier, LDGSTS = cp.async, TEX = texture fetch, BAR = CTA barrier,"
 echo "# MEMBAR/ATOMG/REDG = release / acquire counters of the fused plane stage and of the plane pipeline, UBLKCP = bulk copy (cp.async.bulk) of k_zrow.  No UTC*MMA / HMMA: nothing on this path is a contraction."
 printf "%-78s %6s %7s %6s %5s %6s %4s %5s %6s %5s %5s %5s\n" kernel instr UTMALDG UBLKCP SYNCS LDGSTS TEX BAR MEMBAR ATOM MUFU HMMA
-for f in microimagelib_b200/build/decon_fast_n512.cu.o microimagelib_b200/build/decon_fast_n256.cu.o microimagelib_b200/build/decon_fast_n320.cu.o microimagelib_b200/build/reg.cu.o microimagelib_b200/build/geom.cu.o; do
+for f in microimagelib_b200/build/decon_fast_n512.cu.o microimagelib_b200/build/decon_fast_n256.cu.o microimagelib_b200/build/decon_fast_n320.cu.o microimagelib_b200/build/decon_fast_n1024.cu.o microimagelib_b200/build/reg.cu.o microimagelib_b200/build/geom.cu.o; do
   cuobjdump -sass $f 2>/dev/null | awk -v file=$(basename $f) '
     /Function :/ { name=$3 }
     /^ +\/\*[0-9a-f]+\*\/ / { n[name]++; if ($0 ~ /UTMALDG/) a[name]++; if ($0 ~ /UBLKCP/) u[name]++; if ($0 ~ /SYNCS/) b[name]++; if ($0 ~ /LDGSTS/) c[name]++; if ($0 ~ / TEX| TLD/) d[name]++;
