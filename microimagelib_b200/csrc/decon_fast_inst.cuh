@@ -224,7 +224,11 @@ template <int M> struct YWide<M, true> {
 	static void run(bool inv, float2 *spec, const float2 *tw, int cols, int plane0, int nplanes, const PeerMap *pm, cudaStream_t st)
 	{
 		TileMap tm;
-		make_map2d(tm, spec, 2ll * cols, (long long)M * (plane0 + nplanes), (long long)cols * sizeof(float2), 32, 256);
+		if (!make_map2d(tm, spec, 2ll * cols, (long long)M * (plane0 + nplanes), (long long)cols * sizeof(float2), 32, 256)) {
+			// no other kernel shares this pass's position order, so there is nothing to fall back to (src/api_subfunc.cu:27-37: print and exit)
+			fprintf(stderr, "milb: cuTensorMapEncodeTiled failed for a %d x %d plane buffer\n", M, cols);
+			exit(1);
+		}
 		const int tiles = (cols / 16) * nplanes, cap = (g_cap > 0 && g_cap < g_sms) ? g_cap : g_sms, grid = tiles < cap ? tiles : cap;
 		if (pm) k_ypassW<M, true, true><<<grid, 512, SMW, st>>>(spec, tw, cols, plane0, nplanes, *pm, tm);
 		else if (inv) k_ypassW<M, true><<<grid, 512, SMW, st>>>(spec, tw, cols, plane0, nplanes, PeerMap(), tm);
@@ -280,8 +284,13 @@ int setup()
 				g_use_tma = true;
 			}
 		}
-		const char *we = getenv("MILB_Y_WIDE");
-		g_ywide = kYWide && g_use_tma && !(we && we[0] == '0');
+		// decided once per process: handles prepared earlier keep OTFs in the position order of the Y kernels chosen then
+		static bool decided = false;
+		if (!decided) {
+			const char *we = getenv("MILB_Y_WIDE");
+			g_ywide = kYWide && g_use_tma && !(we && we[0] == '0');
+			decided = true;
+		}
 	}
 	int dev = 0, sms = 148;
 	cudaGetDevice(&dev);
