@@ -24,6 +24,7 @@
 #include "fft_core.h"
 #include "plane_sched.h"
 #include "zrow_core.h"
+#include "xfold_core.h"
 
 #define SMALLVALUE_FAST 0.01f // src/api_subfunc.cu:24
 
@@ -1362,11 +1363,6 @@ template <int N, int L, int T> constexpr int xpassP_ctas()
 #ifndef MILB_X_FOLD
 #define MILB_X_FOLD 1
 #endif
-template <int R0> __device__ __forceinline__ int xfold_row(int slot)
-{
-	const int w = slot >> 1, h = slot & 1;
-	return w == 0 ? (h ? R0 / 2 : 0) : (h ? R0 - w : w);
-}
 
 // XTMA: the half-spectrum rows and the aux rows of a tile arrive by the copy engine (three tensor maps: spectrum rows in boxes of
 // min(N / 2, 256) rows, the last spectrum row, aux rows; one mbarrier per landing buffer) instead of 16 cp.async per thread,
@@ -1458,7 +1454,7 @@ k_xpassP(float2 *__restrict__ vol_io, const float2 *__restrict__ aux, float4 *__
 			if (threadIdx.x < R0 * L) {
 				float2 v[R1];
 				const float4 *sd = SL + frow * L + lane0;                         // rows k1 + R0 * k2, k2 < R1 / 2
-				const float4 *sm_ = SL + (frow ? R0 - frow : R0) * L + lane0;     // mirrors: rows mb + R0 * (R1 - 1 - k2), k2 >= R1 / 2
+				const float4 *sm_ = SL + xfold_mirror_base<R0>(frow) * L + lane0; // mirrors: rows mb + R0 * (R1 - 1 - k2), k2 >= R1 / 2
 #pragma unroll
 				for (int k2 = 0; k2 < R1 / 2; k2++) {
 					float4 ab = sd[k2 * R0 * L];

@@ -3,6 +3,7 @@
 #include "../../microimagelib_b200/csrc/fft_plan.h"
 #include "../../microimagelib_b200/csrc/plane_sched.h"
 #include "../../microimagelib_b200/csrc/zrow_core.h"
+#include "../../microimagelib_b200/csrc/xfold_core.h"
 #include <math.h>
 #include <vector>
 #include <string.h>
@@ -183,5 +184,22 @@ int emul_zrow_maps(int n, int r0, int r1, int *freq_of_otf_index)
 	for (int k1 = 0; k1 < r0; k1++)
 		for (int k2 = 0; k2 < r1; k2++) freq_of_otf_index[k2 * r0 + k1] = k1 + r0 * k2;
 	return n == r0 * r1 ? 0 : -1;
+}
+
+// folded X pass, index rules only (xfold_core.h): for every slot of the radix-r1 stages, the half-spectrum row each of its r1 inputs
+// comes from (row_of[slot * r1 + k2]) and whether it is the mirror output of merge_pair (mirror_of[...]); r0 in {8, 16, 32}
+int emul_xfold_inputs(int r0, int r1, int *row_of, int *mirror_of, int *row_of_slot)
+{
+	for (int s = 0; s < r0; s++) {
+		const int k1 = r0 == 8 ? xfold_row<8>(s) : r0 == 16 ? xfold_row<16>(s) : xfold_row<32>(s);
+		const int mb = r0 == 8 ? xfold_mirror_base<8>(k1) : r0 == 16 ? xfold_mirror_base<16>(k1) : xfold_mirror_base<32>(k1);
+		row_of_slot[s] = k1;
+		for (int k2 = 0; k2 < r1; k2++) {
+			const bool direct = k2 < r1 / 2;
+			row_of[s * r1 + k2] = direct ? k1 + r0 * k2 : mb + r0 * (r1 - 1 - k2);
+			mirror_of[s * r1 + k2] = direct ? 0 : 1;
+		}
+	}
+	return 0;
 }
 }

@@ -114,3 +114,31 @@ def test_row_convolution_lanes(lib, n):
     assert lib.emul_zrow(n, d.ctypes.data_as(F), K.ctypes.data_as(F), 1, C.c_float(1.0), C.byref(conflicts)) == 0
     ref = np.fft.ifft(np.fft.fft(x.astype(np.complex128)) * np.fft.fft(k.astype(np.complex128)))
     assert np.linalg.norm(d - ref) / np.linalg.norm(ref) < 1e-6
+
+
+@pytest.mark.parametrize("r0,r1", [(16, 32), (16, 16), (8, 16)])
+def test_folded_x_pass_index_rules(lib, r0, r1):
+    """xfold_core.h: every slot of the radix-r1 stages builds the frequencies k1 + r0 * k2 of its row from the half spectrum
+    (directly for k2 < r1 / 2, as mirrors N - k otherwise), mirror partners sit in adjacent slots (the two halves of one warp
+    at 16 lanes), and the split covers every row 0 .. N / 2 of the half spectrum exactly once."""
+    n = r0 * r1
+    row_of = np.zeros(r0 * r1, np.int32)
+    mirror = np.zeros(r0 * r1, np.int32)
+    rows = np.zeros(r0, np.int32)
+    assert lib.emul_xfold_inputs(r0, r1, row_of.ctypes.data_as(I), mirror.ctypes.data_as(I), rows.ctypes.data_as(I)) == 0
+    assert sorted(rows.tolist()) == list(range(r0))
+    rng = np.random.default_rng(r0 * r1)
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    A, B, Cs = np.fft.fft(a), np.fft.fft(b), np.fft.fft(a + 1j * b)
+    for s in range(r0):
+        k1 = int(rows[s])
+        assert int(rows[s ^ 1]) == ((r0 - k1) % r0 if k1 not in (0, r0 // 2) else (r0 // 2 if k1 == 0 else 0))
+        for k2 in range(r1):
+            k = int(row_of[s * r1 + k2])
+            assert 0 <= k <= n // 2
+            ck, cn = A[k] + 1j * B[k], np.conj(A[k]) + 1j * np.conj(B[k])   # merge_pair of half-spectrum row k
+            got = cn if mirror[s * r1 + k2] else ck
+            assert abs(got - Cs[k1 + r0 * k2]) < 1e-9 * n
+    # split: slot pairs (k1, r0 - k1) output rows k1 + r0 * k2, k2 < r1 / 2; row 0 also k2 = r1 / 2
+    out = [k1 + r0 * k2 for k1 in range(r0) for k2 in range(r1 // 2)] + [n // 2]
+    assert sorted(out) == list(range(n // 2 + 1))
